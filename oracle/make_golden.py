@@ -1,0 +1,174 @@
+"""Generate tests/golden/*.npz by running the REAL reference (stub-loaded, unmodified).
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden
+
+Every fixture stores the inputs (or the seed + a fingerprint of the regenerated input when
+the input is too large to commit) and the reference's own outputs of
+`Signal.get_csm()` (classes/signal.py:948) and
+`BeamformerDASFrequency.get_beamformer_map()` (beamforming/beamforming.py:805).
+While generating, the oracle restatement is checked against the reference on each case and
+the script aborts if they disagree (that is the oracle's pin).
+"""
+
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader, restatement as R  # noqa: E402
+from dsptoolbox_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+SCALINGS = ["AmplitudeSpectrum", "AmplitudeSpectralDensity", "PowerSpectrum",
+            "PowerSpectralDensity", "FFTBackward", "FFTForward", "FFTOrthogonal"]
+
+
+def rel_to_max(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def ref_csm(dsp, x, fs, wl, window_enum, overlap, detrend, scaling_name):
+    s = dsp.Signal(None, x.copy(), fs)
+    s.set_spectrum_parameters(
+        method=dsp.SpectrumMethod.WelchPeriodogram, window_length_samples=wl,
+        window_type=window_enum, overlap_percent=overlap, detrend=detrend, average="mean",
+        scaling=getattr(dsp.SpectrumScaling, scaling_name))
+    return s.get_csm()
+
+
+def ref_map(dsp, x, fs, wl, mic_pos, grid, formulation, fc, frac, remove_diag, c=343):
+    s = dsp.Signal(None, x.copy(), fs)
+    s.set_spectrum_parameters(window_length_samples=wl)
+    bf = dsp.beamforming.BeamformerDASFrequency(
+        s, dsp.beamforming.MicArray(mic_pos), grid,
+        dsp.beamforming.SteeringVector(getattr(dsp.beamforming.SteeringVectorType, formulation)), c=c)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = bf.get_beamformer_map(fc, frac, remove_diag)
+    return m, np.asarray(bf.f_range_hz)
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    dsp = ref_loader.load()
+    W = dsp.Window
+
+    # ---- geometry of example_data/array.xml (config 1) -------------------------------
+    arr = ref_loader.read_array_xml()
+    np.savez(os.path.join(GOLDEN, "array_xml_positions.npz"), **arr)
+
+    # ---- case A: small CSM, all seven scalings ----------------------------------------
+    mic = synth.positions_to_xyz(synth.disc_array(4, 0.3, seed=3))
+    fs = 8000
+    x = synth.point_source_recording(mic, 3000, fs, noise_sigma=0.3, seed=11)
+    out = dict(x=x, fs=fs, wl=128, overlap=50, detrend=True, window="hann")
+    for sc in SCALINGS:
+        f, c = ref_csm(dsp, x, fs, 128, W.Hann, 50, True, sc)
+        _, c1 = R.csm_welch(x, fs, 128, "hann", 50, True, sc)
+        _, c2 = R.csm_welch_pairwise(x, fs, 128, "hann", 50, True, sc)
+        e1, e2 = rel_to_max(c1, c), rel_to_max(c2, c)
+        print(f"A {sc:26s} oracle-vs-ref rel-to-max: vectorised {e1:.2e} pairwise {e2:.2e}")
+        assert e1 < 1e-13 and e2 < 1e-13
+        out["csm_" + sc] = c
+    out["f"] = f
+    np.savez_compressed(os.path.join(GOLDEN, "csm_small_scalings.npz"), **out)
+
+    # ---- case B: Welch parameter variants ----------------------------------------------
+    variants = [
+        dict(tag="ov75_hamming", L=2500, wl=64, overlap=75, detrend=True, window=("Hamming", "hamming")),
+        dict(tag="ov0_boxcar_nodetrend", L=2048, wl=256, overlap=0, detrend=False, window=("Boxcar", "boxcar")),
+        dict(tag="ov33_blackman_Lmultiple", L=43 * 86, wl=128, overlap=33, detrend=True, window=("Blackman", "blackman")),
+        dict(tag="ov50_kaiser8_wl8", L=999, wl=8, overlap=50, detrend=True, window=("Kaiser", ("kaiser", 8.0))),
+        dict(tag="ov90_flattop_short", L=300, wl=512, overlap=90, detrend=True, window=("Flattop", "flattop")),
+    ]
+    mic3 = synth.positions_to_xyz(synth.disc_array(3, 0.2, seed=5))
+    outB = {}
+    for v in variants:
+        xv = synth.point_source_recording(mic3, v["L"], fs, noise_sigma=0.5, seed=21)
+        wenum = getattr(W, v["window"][0])
+        if isinstance(v["window"][1], tuple):
+            wenum = wenum.with_extra_parameter(v["window"][1][1])
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            f, c = ref_csm(dsp, xv, fs, v["wl"], wenum, v["overlap"], v["detrend"], "PowerSpectralDensity")
+            _, c1 = R.csm_welch(xv, fs, v["wl"], v["window"][1], v["overlap"], v["detrend"], "PowerSpectralDensity")
+        e1 = rel_to_max(c1, c)
+        print(f"B {v['tag']:28s} oracle-vs-ref {e1:.2e}")
+        assert e1 < 1e-13
+        outB["x_" + v["tag"]] = xv
+        outB["csm_" + v["tag"]] = c
+    np.savez_compressed(os.path.join(GOLDEN, "csm_variants.npz"), fs=fs, **outB)
+
+    # ---- case C: small DAS maps: 4 steering formulations x diag removal x band widths ---
+    rng = np.random.default_rng(17)
+    micp = dict(x=rng.uniform(-0.4, 0.4, 10), y=rng.uniform(-0.4, 0.4, 10), z=rng.uniform(-0.05, 0.05, 10))
+    micxyz = synth.positions_to_xyz(micp)
+    fs = 16000
+    xm = synth.point_source_recording(micxyz, 6000, fs, source_xyz=(0.15, -0.1, 0.8), noise_sigma=0.2, seed=31)
+    l1, l2 = np.linspace(-0.4, 0.4, 9), np.linspace(-0.3, 0.3, 7)
+    grid = dsp.beamforming.Regular2DGrid(l1, l2, ("x", "y"), 0.8)
+    gxyz = grid.coordinates
+    outC = dict(x=xm, fs=fs, wl=256, mic_x=micp["x"], mic_y=micp["y"], mic_z=micp["z"], line1=l1, line2=l2, value3=0.8)
+    fref, cref = ref_csm(dsp, xm, fs, 256, W.Hann, 50, True, "FFTBackward")
+    for form in ["Classic", "Inverse", "TruePower", "TrueLocation"]:
+        for (fc, frac, rd, tag) in [(2000.0, 3, True, "third_rd"), (2000.0, 3, False, "third_full"),
+                                    (3000.0, 0, True, "single_rd"), (1500.0, 1, True, "octave_rd"),
+                                    (2500.0, 12, False, "twelfth_full")]:
+            m, fr = ref_map(dsp, xm, fs, 256, micp, grid, form, fc, frac, rd)
+            mo = R.das_map(fref, cref, micxyz, gxyz, fc, frac, rd, 343.0, form).reshape(m.shape)
+            ml = R.das_map_loop(fref, cref, micxyz, gxyz, fc, frac, rd, 343.0, form).reshape(m.shape)
+            e, el = rel_to_max(mo, m), rel_to_max(ml, m)
+            print(f"C {form:13s} {tag:13s} F={R.band_bins(fref, fc, frac)} oracle-vs-ref {e:.2e} loop {el:.2e}")
+            assert e < 1e-12 and el < 1e-12
+            outC[f"map_{form}_{tag}"] = m
+            outC[f"frange_{form}_{tag}"] = fr
+    # 3-D and line grids, plain Grid
+    g3 = dsp.beamforming.Regular3DGrid(np.linspace(-0.2, 0.2, 4), np.linspace(-0.2, 0.2, 3), np.linspace(0.6, 1.0, 5))
+    m3, _ = ref_map(dsp, xm, fs, 256, micp, g3, "TrueLocation", 2000.0, 3, True)
+    outC["map3d"] = m3
+    gl = dsp.beamforming.LineGrid(np.linspace(-0.5, 0.5, 11), "y", 0.8, 0.1)
+    ml_, _ = ref_map(dsp, xm, fs, 256, micp, gl, "TrueLocation", 2000.0, 3, True)
+    outC["mapline"] = ml_
+    outC["mapline_coords"] = gl.coordinates
+    np.savez_compressed(os.path.join(GOLDEN, "das_small.npz"), **outC)
+
+    # ---- case D: config 1 (array.xml, 1 s @ 48 kHz, nfft 1024, 50x50 grid, 4 kHz third) ---
+    micxyz = synth.positions_to_xyz(arr)
+    fs = 48000
+    x1 = synth.point_source_recording(micxyz, fs, fs, noise_sigma=0.1, seed=1)
+    print("D running the reference at config 1 (about 15 s) ...")
+    f1, c1 = ref_csm(dsp, x1, fs, 1024, W.Hann, 50, True, "FFTBackward")
+    _, co = R.csm_welch(x1, fs, 1024, "hann", 50, True, "FFTBackward")
+    print(f"D csm oracle-vs-ref {rel_to_max(co, c1):.2e}")
+    assert rel_to_max(co, c1) < 1e-13
+    l = np.linspace(-0.5, 0.5, 50)
+    grid1 = dsp.beamforming.Regular2DGrid(l, l, ("x", "y"), 1.0)
+    m1, fr1 = ref_map(dsp, x1, fs, 1024, arr, grid1, "TrueLocation", 4000.0, 3, True)
+    mo = R.das_map(f1, c1, micxyz, grid1.coordinates, 4000.0, 3, True).reshape(m1.shape)
+    print(f"D map oracle-vs-ref {rel_to_max(mo, m1):.2e}; argmax {np.unravel_index(np.argmax(m1), m1.shape)}")
+    assert rel_to_max(mo, m1) < 1e-12
+    rs = np.random.default_rng(5)
+    nb, M = c1.shape[0], c1.shape[1]
+    idx = np.stack([rs.integers(1, nb, 6000), rs.integers(0, M, 6000), rs.integers(0, M, 6000)], axis=1)
+    np.savez_compressed(
+        os.path.join(GOLDEN, "cfg1.npz"), fs=fs, seed=1, noise_sigma=0.1, wl=1024,
+        x_fingerprint=np.array([x1.sum(), np.abs(x1).sum(), x1[12345, 7], x1[-1, -1]]),
+        csm_idx=idx, csm_vals=c1[idx[:, 0], idx[:, 1], idx[:, 2]],
+        csm_bins=np.array([1, 85, 512]), csm_full_bins=c1[[1, 85, 512]],
+        csm_diag_bin85=np.diagonal(c1[85]).copy(), map=m1, f_range=fr1)
+    print("golden vectors written to", GOLDEN)
+
+
+if __name__ == "__main__":
+    main()

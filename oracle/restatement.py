@@ -1,0 +1,320 @@
+"""CPU restatement (numpy/scipy, float64) of the reference's Welch-CSM + DAS-map path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``dsptoolbox_b200`` may import this module; it is
+used by ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl
+reference`` legs of ``bench.py`` as the checker / CPU baseline, never as the product.
+
+Parity pin: every function here is checked against the *real* reference (imported from
+``/root/reference`` with its I/O/plot dependencies stubbed, see ``oracle/ref_loader.py``)
+by ``oracle/make_golden.py`` (which also writes ``tests/golden/*.npz``) and, whenever the
+reference tree is present, by ``tests/test_oracle_vs_reference.py``.  The committed golden
+vectors are outputs of the reference itself, so the oracle is pinned on the GPU box too.
+
+Every function cites the reference lines it restates (paths relative to
+``/root/reference/dsptoolbox``).
+
+Two flavours are provided for each stage:
+
+* ``*_pairwise`` / ``*_loop``  -- keep the reference's own loop structure (one Welch call
+  per channel pair, one ``multi_dot`` per grid point and bin).  These are the "reference
+  arm" timed by ``bench.py --impl reference``.
+* the vectorised forms -- the same arithmetic as batched BLAS calls; the strong CPU
+  baseline and the checker used at larger sizes.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+from scipy.integrate import simpson as _scipy_simpson
+from scipy.signal.windows import get_window as _scipy_get_window
+
+# --------------------------------------------------------------------------- scalings
+# standard/enums.py:21-229 (SpectrumScaling).  Names are the lower-cased enum members.
+AMPLITUDE_SCALINGS = (
+    "amplitudespectrum",
+    "amplitudespectraldensity",
+    "fftbackward",
+    "fftforward",
+    "fftorthogonal",
+)  # enums.py:77-92
+PHYSICAL_SCALINGS = (
+    "amplitudespectrum",
+    "amplitudespectraldensity",
+    "powerspectrum",
+    "powerspectraldensity",
+)  # enums.py:109-123
+
+
+def fft_norm(scaling: str) -> str:
+    """enums.py:53-75."""
+    scaling = scaling.lower()
+    if scaling == "fftforward":
+        return "forward"
+    if scaling == "fftorthogonal":
+        return "ortho"
+    return "backward"
+
+
+def scaling_factor(scaling: str, wl: int, fs: int, window: np.ndarray) -> float:
+    """enums.py:183-229 with a window always passed (as `_welch` does, :165)."""
+    scaling = scaling.lower()
+    if scaling == "fftbackward":
+        return 1.0
+    if scaling == "fftforward":
+        return 1.0 / wl
+    if scaling == "fftorthogonal":
+        return (1.0 / wl) ** 0.5
+    if scaling in ("amplitudespectraldensity", "powerspectraldensity"):
+        factor = (2.0 / np.sum(window**2) / fs) ** 0.5
+    else:
+        factor = 2.0**0.5 / np.sum(window)
+    if scaling in AMPLITUDE_SCALINGS:
+        return float(factor)
+    return float(factor**2.0)
+
+
+# --------------------------------------------------------------------------- framing
+def frame_count(wl: int, step: int, length: int) -> tuple[int, int]:
+    """helpers/other.py:181-213 with zero_padding=True: (frames, padded samples)."""
+    n_frames = int(np.ceil(length / step))
+    pad = wl - int(length % step)
+    return n_frames, pad
+
+
+def framed(x: np.ndarray, wl: int, step: int) -> np.ndarray:
+    """standard/_framed_signal_representation.py:9-67 for one or more channels.
+
+    x: (L, ch) -> (wl, K, ch) float64, tail zero padded (helpers/other.py:216-259).
+    """
+    x = np.asarray(x, dtype=np.float64)
+    L = x.shape[0]
+    K, pad = frame_count(wl, step, L)
+    xp = np.concatenate([x, np.zeros((pad, x.shape[1]))], axis=0)
+    idx = np.arange(wl)[:, None] + step * np.arange(K)[None, :]
+    return xp[idx, :]
+
+
+def welch_window(window, wl: int) -> np.ndarray:
+    """_spectral_methods.py:103-105 (periodic window, fftbins=True)."""
+    return _scipy_get_window(window, wl, fftbins=True)
+
+
+def welch_step(wl: int, overlap_percent: float) -> int:
+    """_spectral_methods.py:106-107."""
+    return wl - int(overlap_percent / 100 * wl)
+
+
+# --------------------------------------------------------------------------- stage 1
+def channel_spectra(x, wl, window, overlap_percent, detrend, scaling) -> np.ndarray:
+    """Windowed, de-meaned frame spectra of every channel.
+
+    _spectral_methods.py:120-148: frames * window, THEN minus the frame mean, then rfft
+    with the scaling's norm.  Returns complex128 (nb, K, ch).
+    """
+    w = welch_window(window, wl)
+    step = welch_step(wl, overlap_percent)
+    fr = framed(x, wl, step)
+    fr *= w[:, None, None]
+    if detrend:
+        fr -= np.mean(fr, axis=0)
+    return np.fft.rfft(fr, axis=0, norm=fft_norm(scaling))
+
+
+def _finish_welch(csd, scaling, wl, fs, window):
+    """_spectral_methods.py:164-171 on an averaged cross-spectrum (bins on axis 0)."""
+    scaling = scaling.lower()
+    if scaling in PHYSICAL_SCALINGS:
+        csd = csd * scaling_factor(scaling, wl, fs, window)
+        csd[np.array([0, -1]), ...] /= 2
+    if scaling in AMPLITUDE_SCALINGS:
+        csd = np.sqrt(csd)
+    return csd
+
+
+def welch_pair(x, y, fs, window, wl, overlap_percent, detrend, scaling):
+    """One `_welch(x, y)` call (_spectral_methods.py:10-173, average='mean').
+
+    x, y are 1-D; y=None gives the real auto-spectrum.
+    """
+    w = welch_window(window, wl)
+    X = channel_spectra(np.asarray(x)[:, None], wl, window, overlap_percent, detrend, scaling)[..., 0]
+    if y is None:
+        sp = np.abs(X) ** 2.0
+    else:
+        Y = channel_spectra(np.asarray(y)[:, None], wl, window, overlap_percent, detrend, scaling)[..., 0]
+        sp = X.conjugate() * Y
+    csd = np.mean(sp, axis=1)
+    return _finish_welch(csd, scaling, wl, fs, w)
+
+
+def csm_welch_pairwise(x, fs, wl=1024, window="hann", overlap_percent=50, detrend=True,
+                       scaling="fftbackward", pairs=None):
+    """`_csm_welch` with the reference's own loop structure (_spectral_methods.py:285-371).
+
+    ``pairs`` (list of (ind1, ind2), ind2 >= ind1) restricts the double loop to a sub-sample
+    (used to time the reference arm on a bounded sample); entries outside stay zero.
+    """
+    x = np.asarray(x)
+    M = x.shape[1]
+    nb = wl // 2 + 1
+    csm = np.zeros((nb, M, M), dtype=np.complex128)
+    todo = pairs if pairs is not None else [(i, j) for i in range(M) for j in range(i, M)]
+    for ind1, ind2 in todo:
+        csm[:, ind2, ind1] = welch_pair(
+            x[:, ind1], x[:, ind2] if ind1 != ind2 else None, fs, window, wl,
+            overlap_percent, detrend, scaling)
+        if ind1 == ind2:
+            csm[:, ind1, ind2] *= 0.5
+    csm += np.swapaxes(csm, 1, 2).conjugate()
+    return np.fft.rfftfreq(wl, 1 / fs), csm
+
+
+def csm_welch(x, fs, wl=1024, window="hann", overlap_percent=50, detrend=True,
+              scaling="fftbackward", chunk_bins: int = 128):
+    """Vectorised `_csm_welch`: every channel transformed once, one zgemm per bin block.
+
+    Same arithmetic as `csm_welch_pairwise`:
+    S[f, j, i] = mean_k X_k[f, j] conj(X_k[f, i]) for j >= i, scaling/sqrt applied to the
+    lower-triangle value, upper triangle = conjugate of the lower one
+    (_spectral_methods.py:351-369).
+    """
+    x = np.asarray(x)
+    M = x.shape[1]
+    nb = wl // 2 + 1
+    w = welch_window(window, wl)
+    X = channel_spectra(x, wl, window, overlap_percent, detrend, scaling)  # (nb, K, M)
+    K = X.shape[1]
+    csm = np.empty((nb, M, M), dtype=np.complex128)
+    for b0 in range(0, nb, chunk_bins):
+        Xb = X[b0:b0 + chunk_bins]                      # (b, K, M)
+        # S[f, j, i] = sum_k X[f,k,j] conj(X[f,k,i]) / K
+        csm[b0:b0 + chunk_bins] = np.matmul(np.swapaxes(Xb, 1, 2), Xb.conjugate()) / K
+    lower = np.tril(np.ones((M, M), dtype=bool))
+    S = _finish_welch(csm, scaling, wl, fs, w)
+    # mirror the (possibly sqrt-ed) lower triangle; the diagonal stays as computed
+    out = np.where(lower[None], S, 0)
+    strict = np.tril(np.ones((M, M), dtype=bool), -1)
+    out = out + np.swapaxes(np.where(strict[None], S, 0), 1, 2).conjugate()
+    return np.fft.rfftfreq(wl, 1 / fs), out
+
+
+# --------------------------------------------------------------------------- stage 2
+def distance_matrix(x: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """helpers/other.py:131-153 (expansion formula, NOT direct differences)."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    y = np.atleast_2d(np.asarray(y, dtype=np.float64))
+    return np.sqrt(np.sum(x**2, axis=1, keepdims=True) + np.sum(y.T**2, axis=0, keepdims=True)
+                   - 2 * x @ y.T)
+
+
+def array_center(mic_xyz: np.ndarray) -> tuple[int, np.ndarray]:
+    """beamforming/beamforming.py:517-541: the mic closest to the centroid."""
+    center = np.mean(mic_xyz, axis=0)
+    d = distance_matrix(mic_xyz, center[None, :])[:, 0]
+    ind = int(np.argmin(d))
+    return ind, mic_xyz[ind]
+
+
+def steering_vector(wave_number, grid_xyz, mic_xyz, formulation="truelocation") -> np.ndarray:
+    """beamforming/beamforming.py:1515-1703 -> complex128 (F, M, G)."""
+    k = np.atleast_1d(np.asarray(wave_number, dtype=np.float64))
+    N = mic_xyz.shape[0]
+    _, pc = array_center(mic_xyz)
+    rt0 = distance_matrix(grid_xyz, pc[None, :])[:, 0]          # (G,)
+    rti = distance_matrix(grid_xyz, mic_xyz).T                  # (M, G)
+    phase = np.exp(-1j * k[:, None, None] * (rti[None] - rt0[None, None, :]))
+    formulation = formulation.lower()
+    if formulation == "classic":
+        return 1 / N * phase
+    if formulation == "inverse":
+        return rti[None] / N / rt0[None, None, :] * phase
+    rtj = np.sum(1 / distance_matrix(mic_xyz, grid_xyz) ** 2, axis=0)   # (G,)
+    if formulation == "truepower":
+        return 1 / rt0[None, None, :] / rti[None] / rtj[None, None, :] * phase
+    if formulation == "truelocation":
+        return 1 / rti[None] / np.sqrt(N * rtj[None, None, :]) * phase
+    raise ValueError(formulation)
+
+
+def fractional_octave_band(fc: float, fraction) -> np.ndarray:
+    """helpers/other.py:156-178."""
+    if fraction == 0:
+        return np.array([fc, fc])
+    return np.array([fc * 2 ** (-1 / fraction / 2), fc * 2 ** (1 / fraction / 2)])
+
+
+def band_bins(f: np.ndarray, fc: float, fraction) -> tuple[int, int]:
+    """beamforming.py:849-856 + helpers/other.py:9-31: half-open bin range [id1, id2)."""
+    lo, hi = fractional_octave_band(fc, fraction)
+    id1 = int(np.argmin(np.abs(lo - f)))
+    id2 = int(np.argmin(np.abs(hi - f)))
+    if id1 == id2:
+        id2 += 1
+    return id1, id2
+
+
+def simpson_weights(n: int, dx: float) -> np.ndarray:
+    """Weights w with simpson(y, dx=dx) == y @ w (scipy.integrate.simpson, beamforming.py:876)."""
+    return _scipy_simpson(np.eye(n), dx=dx, axis=1)
+
+
+def _prepare_csm(csm, M, remove_diag):
+    csm = np.array(csm, dtype=np.complex128, copy=True)
+    if remove_diag:
+        csm *= M / (M - 1)                              # beamforming.py:843
+        idx = np.arange(M)
+        csm[:, idx, idx] = 0                            # :844-845 (all bins)
+    return csm
+
+
+def das_map_loop(f, csm, mic_xyz, grid_xyz, fc, fraction=3, remove_diag=True, c=343.0,
+                 formulation="truelocation", grid_subset=None):
+    """`BeamformerDASFrequency.get_beamformer_map` keeping the reference's loops
+    (beamforming.py:841-878): dense h, one multi_dot per (grid point, bin).
+
+    ``grid_subset`` (indices) evaluates only those grid points (bounded sample for timing).
+    Returns the flat float64 map (len G or len(grid_subset)).
+    """
+    M = mic_xyz.shape[0]
+    csm = _prepare_csm(csm, M, remove_diag)
+    id1, id2 = band_bins(f, fc, fraction)
+    fsel = f[id1:id2]
+    csm = csm[id1:id2]
+    k = fsel * np.pi * 2 / c
+    g = grid_xyz if grid_subset is None else grid_xyz[np.asarray(grid_subset)]
+    h = steering_vector(k, g, mic_xyz, formulation)
+    h_H = np.swapaxes(h, 1, 2).conjugate()
+    out = np.zeros((g.shape[0], len(fsel)))
+    for gi in range(g.shape[0]):
+        for fi in range(len(fsel)):
+            out[gi, fi] = np.linalg.multi_dot([h_H[fi, gi, :], csm[fi], h[fi, :, gi]]).real
+    if remove_diag:
+        out[out < 0] = 0
+    if len(fsel) > 1:
+        return _scipy_simpson(out, dx=fsel[1] - fsel[0], axis=1)
+    return out[:, 0]
+
+
+def das_map(f, csm, mic_xyz, grid_xyz, fc, fraction=3, remove_diag=True, c=343.0,
+            formulation="truelocation", chunk_points: int = 2048, return_per_bin=False):
+    """Vectorised DAS map: P[g,f] = Re(h^H C h) as batched matmul + einsum, grid-chunked so
+    the dense steering array never exceeds chunk_points * F * M complex128."""
+    M = mic_xyz.shape[0]
+    csm = _prepare_csm(csm, M, remove_diag)
+    id1, id2 = band_bins(f, fc, fraction)
+    fsel = f[id1:id2]
+    csm = csm[id1:id2]
+    k = fsel * np.pi * 2 / c
+    G = grid_xyz.shape[0]
+    P = np.empty((G, len(fsel)))
+    for g0 in range(0, G, chunk_points):
+        h = steering_vector(k, grid_xyz[g0:g0 + chunk_points], mic_xyz, formulation)  # (F,M,g)
+        t = np.matmul(csm, h)                                                         # (F,M,g)
+        P[g0:g0 + chunk_points] = np.einsum("fmg,fmg->gf", h.conjugate(), t).real
+    if remove_diag:
+        P[P < 0] = 0
+    if return_per_bin:
+        return P
+    if len(fsel) > 1:
+        return P @ simpson_weights(len(fsel), fsel[1] - fsel[0])
+    return P[:, 0]
