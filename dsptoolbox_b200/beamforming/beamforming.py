@@ -1,0 +1,307 @@
+"""Grids, microphone array, steering vectors and the frequency-domain delay-and-sum beamformer.
+
+Call-compatible with reference beamforming/beamforming.py for Grid (:35-75), Regular2DGrid
+(:78-173), Regular3DGrid (:218-295), LineGrid (:366-422), MicArray (:425-602), SteeringVector
+(:605-647), BaseBeamformer/BeamformerGridded (:650-796) and BeamformerDASFrequency (:799-880).
+`get_beamformer_map` keeps the reference's side effects (stdout banner, `self.map`,
+`self.f_range_hz`, returned copy) but runs on the GPU: the CSM stays on the device, steering
+vectors are synthesised inside the map kernel, and the grid may be sharded over ranks (dist.py).
+The other beamformers of the reference (CleanSC, Orthogonal, Functional, MVDR, DASTime) and the
+source simulator are outside this round's scope.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .. import engine
+from .. import _native as N
+from ..classes import Signal
+from ..helpers.other import _get_fractional_octave_bandwidth, find_nearest_points_index_in_vector
+from ._beamforming import BasePoints
+from .enums import SteeringVectorType
+
+nxs = np.newaxis
+
+
+# =========================================================================== grids
+class Grid(BasePoints):
+    """Arbitrary set of grid points (right-handed cartesian coordinates in metres)."""
+
+    def __init__(self, positions: dict):
+        super().__init__(positions)
+
+    def reconstruct_map_shape(self, map):
+        """Identity for a plain grid; regular grids reshape the flat map to their lattice."""
+        return map
+
+
+class Regular2DGrid(Grid):
+    """Rectangular lattice line1 x line2 in the plane spanned by `dimensions`, third coordinate fixed."""
+
+    def __init__(self, line1, line2, dimensions, value3):
+        assert len(dimensions) == 2, (
+            "dimensions must contain exactly two strings specifying to which directions line1 and line2 correspond")
+        assert len(np.unique(dimensions)) == len(dimensions), "There are repeated dimensions"
+        dimensions = [d.lower() for d in dimensions]
+        self.extent_dimensions = dimensions
+        value3 = np.asarray(value3).squeeze()
+        assert value3.ndim == 0, "value3 can only be a single value"
+        line1, line2 = np.asarray(line1).squeeze(), np.asarray(line2).squeeze()
+        self.original_lengths = (len(line1), len(line2))
+        a, b = np.meshgrid(line1, line2, indexing="ij")       # line1 is the slow axis
+        third = [ax for ax in ("x", "y", "z") if ax not in dimensions][0]
+        super().__init__({dimensions[0]: a.ravel(), dimensions[1]: b.ravel(),
+                          third: np.full(a.size, float(value3))})
+
+    def reconstruct_map_shape(self, map_vector):
+        assert map_vector.ndim == 1, "The passed map should be a vector (flattened)"
+        assert len(map_vector) == self.number_of_points, "Length of passed vector does not match the number of points"
+        return map_vector.reshape(self.original_lengths)
+
+
+class Regular3DGrid(Grid):
+    """Box lattice line_x x line_y x line_z (x slowest, z fastest)."""
+
+    def __init__(self, line_x, line_y, line_z):
+        self.lines = tuple(np.asarray(v).squeeze() for v in (line_x, line_y, line_z))
+        assert all(v.ndim == 1 for v in self.lines), "Shape of lines is invalid"
+        self.original_lengths = tuple(len(v) for v in self.lines)
+        xx, yy, zz = np.meshgrid(*self.lines, indexing="ij")
+        super().__init__(dict(x=xx.ravel(), y=yy.ravel(), z=zz.ravel()))
+
+    def reconstruct_map_shape(self, map_vector):
+        assert map_vector.ndim == 1, "The passed map should be a vector (flattened)"
+        assert len(map_vector) == self.number_of_points, "Length of passed vector does not match the number of points"
+        return map_vector.reshape(self.original_lengths)
+
+
+class LineGrid(Grid):
+    """Points along one coordinate axis; the next axes (cyclic x->y->z->x) are held at value2, value3."""
+
+    def __init__(self, line, dimension: str, value2: float, value3: float):
+        line = np.atleast_1d(np.squeeze(line))
+        assert line.ndim == 1, "Line has an invalid shape"
+        dimension = dimension.lower()
+        order = ["x", "y", "z"]
+        assert dimension in order, "Dimension should be x, y or z"
+        i = order.index(dimension)
+        second, third = order[(i + 1) % 3], order[(i + 2) % 3]
+        self.extent_dimension = dimension
+        super().__init__({dimension: line, second: np.full(len(line), float(value2)),
+                          third: np.full(len(line), float(value3))})
+
+
+# =========================================================================== microphones
+class MicArray(BasePoints):
+    """Microphone positions; channel order must match the multichannel signal."""
+
+    def __init__(self, positions: dict):
+        super().__init__(positions)
+        self._center = None
+        self._aperture_min = None
+
+    def _pairwise(self):
+        if self._aperture_min is None:
+            d = np.array(self.get_distances_to_point(self._coordinates), dtype=float, ndmin=2)
+            off = ~np.eye(d.shape[0], dtype=bool)
+            self._aperture_min = (float(np.max(d[off])), float(np.min(d[off])))
+        return self._aperture_min
+
+    @property
+    def aperture(self):
+        return self._pairwise()[0]
+
+    @property
+    def min_distance(self):
+        return self._pairwise()[1]
+
+    def _locate_center(self):
+        if self._center is None:
+            centroid = np.mean(self._coordinates, axis=0)
+            ind = int(np.argmin(self.get_distances_to_point(centroid)))
+            self._center = (self._coordinates[ind, :].copy(), ind)
+        return self._center
+
+    @property
+    def array_center_coordinates(self):
+        """Coordinates of the microphone closest to the centroid (reference :517-541)."""
+        return self._locate_center()[0]
+
+    @property
+    def array_center_channel_number(self):
+        return self._locate_center()[1]
+
+    def he_to_hz(self, he: float, c: float = 343) -> float:
+        return he * c / self.aperture
+
+    def hz_to_he(self, f_hz: float, c: float = 343) -> float:
+        return f_hz * self.aperture / c
+
+    def get_maximum_frequency_range(self, lowest_he: float = 4, c: float = 343) -> list:
+        return [self.he_to_hz(lowest_he, c=c), c / self.min_distance / 2]
+
+
+# =========================================================================== steering vectors
+_STEER_CODE = {SteeringVectorType.Classic: N.STEER_CLASSIC, SteeringVectorType.Inverse: N.STEER_INVERSE,
+               SteeringVectorType.TruePower: N.STEER_TRUE_POWER, SteeringVectorType.TrueLocation: N.STEER_TRUE_LOCATION}
+
+
+def _dense_steering(code, wave_number, grid, mic):
+    k = np.atleast_1d(wave_number)
+    assert k.ndim == 1, "Wave number should be a 1D-array"
+    h = engine.steering_vector(k, mic._coordinates, mic.array_center_coordinates, grid._coordinates, code)
+    return h.cpu().numpy()
+
+
+def classic_steering(wave_number, grid: Grid, mic: MicArray):
+    """Formulation 1: exp(-jk(r_ti - r_t0)) / N -> complex128 (frequency, nmics, ngrid)."""
+    return _dense_steering(N.STEER_CLASSIC, wave_number, grid, mic)
+
+
+def inverse_steering(wave_number, grid: Grid, mic: MicArray):
+    """Formulation 2: r_ti / (N r_t0) exp(-jk(r_ti - r_t0))."""
+    return _dense_steering(N.STEER_INVERSE, wave_number, grid, mic)
+
+
+def true_power_steering(wave_number, grid: Grid, mic: MicArray):
+    """Formulation 3: exp(-jk(r_ti - r_t0)) / (r_t0 r_ti sum_j r_tj^-2)."""
+    return _dense_steering(N.STEER_TRUE_POWER, wave_number, grid, mic)
+
+
+def true_location_steering(wave_number, grid: Grid, mic: MicArray):
+    """Formulation 4: exp(-jk(r_ti - r_t0)) / (r_ti sqrt(N sum_j r_tj^-2))."""
+    return _dense_steering(N.STEER_TRUE_LOCATION, wave_number, grid, mic)
+
+
+_STEER_FUNCS = {SteeringVectorType.Classic: classic_steering, SteeringVectorType.Inverse: inverse_steering,
+                SteeringVectorType.TruePower: true_power_steering,
+                SteeringVectorType.TrueLocation: true_location_steering}
+
+
+class SteeringVector:
+    """Holds the steering-vector formulation; `get_vector(k, grid=, mic=)` materialises it."""
+
+    def __init__(self, formulation: SteeringVectorType = SteeringVectorType.TrueLocation):
+        if formulation not in _STEER_FUNCS:
+            raise ValueError("Incorrect formulation. Use either classic, inverse, true power or true location")
+        self.formulation = formulation
+        self.get_vector = _STEER_FUNCS[formulation]
+
+
+def _steering_code(st_vec: SteeringVector) -> int:
+    for kind, fn in _STEER_FUNCS.items():
+        if st_vec.get_vector is fn:
+            return _STEER_CODE[kind]
+    raise ValueError("Incorrect formulation. Use either classic, inverse, true power or true location")
+
+
+# =========================================================================== Simpson weights
+def simpson_weights(n: int, dx: float):
+    """w such that scipy.integrate.simpson(y, dx=dx) == y @ w for n equally spaced samples.
+
+    Composite Simpson for an odd sample count; for an even count scipy (>= 1.11) integrates the
+    first n-1 samples with Simpson and the last interval with the three-point correction
+    (-1/12, 2/3, 5/12) -- the reference calls it at beamforming.py:876.
+    """
+    assert n >= 2
+    w = np.zeros(n)
+    if n == 2:
+        w[:] = 0.5
+        return w * dx
+    m = n if n % 2 == 1 else n - 1
+    w[:m] = 2.0 / 3.0
+    w[1:m:2] = 4.0 / 3.0
+    w[0] = w[m - 1] = 1.0 / 3.0
+    if m != n:
+        w[n - 3] += -1.0 / 12.0
+        w[n - 2] += 2.0 / 3.0
+        w[n - 1] += 5.0 / 12.0
+    return w * dx
+
+
+# =========================================================================== beamformers
+class BaseBeamformer:
+    def __init__(self, multi_channel_signal: Signal, mic_array: MicArray, c: float = 343):
+        assert isinstance(multi_channel_signal, Signal), "multi_channel_signal should be of type Signal"
+        assert type(mic_array) is MicArray, "mic_array should be of type MicArray"
+        assert c > 0, "Speed of sound should be bigger than 0"
+        assert multi_channel_signal.number_of_channels == mic_array.number_of_points, (
+            "Number of channels in the signal and number of microphones do not match")
+        self.signal = multi_channel_signal
+        self.mics = mic_array
+        self.c = c
+
+    def get_frequency_range_from_he(self, range_he=[4, 10]) -> list:
+        assert len(range_he) == 2, "Range in He should have length two"
+        return [self.mics.he_to_hz(range_he[0], c=self.c), self.mics.he_to_hz(range_he[1], c=self.c)]
+
+    def show_info(self):
+        print(f"Beamformer: {getattr(self, 'beamformer_type', 'base')}; mics: {self.mics.number_of_points}; c: {self.c}")
+
+
+class BeamformerGridded(BaseBeamformer):
+    def __init__(self, multi_channel_signal: Signal, mic_array: MicArray, grid: Grid,
+                 steering_vector: SteeringVector, c: float = 343):
+        super().__init__(multi_channel_signal, mic_array, c)
+        assert type(steering_vector) is SteeringVector, "steering_vector should be of type SteeringVector"
+        assert issubclass(type(grid), Grid), "grid should be a Grid object"
+        self.grid = grid
+        self.st_vec = steering_vector
+
+
+class BeamformerDASFrequency(BeamformerGridded):
+    """Delay-and-sum beamforming in the frequency domain."""
+
+    beamformer_type = "Delay-and-sum (Frequency)"
+
+    def get_beamformer_map(self, center_frequency_hz: float, octave_fraction: int = 3,
+                           remove_csm_diagonal: bool = True):
+        """Map of integrated beamformer power in the (1/octave_fraction)-octave band around
+        `center_frequency_hz`; float64 array shaped by `grid.reconstruct_map_shape`."""
+        self.center_frequency_hz = center_frequency_hz
+        self.octave_fraction = octave_fraction
+        self.f_range_hz = _get_fractional_octave_bandwidth(center_frequency_hz, octave_fraction)
+        txt = "Beamformer computation has started successfully:"
+        print("\n" + txt)
+        print("-" * len(txt))
+        print("...csm...")
+        f, csm_dev = self._csm_device()
+        print("...Steering vector...")
+        flat = self._map_from_device_csm(f, csm_dev, remove_csm_diagonal)
+        self.map = self.grid.reconstruct_map_shape(flat)
+        return self.map.copy()
+
+    # -- pieces, overridable by the distributed front-end ------------------------------------
+    def _csm_device(self):
+        return self.signal.get_csm_device()
+
+    def _select_bins(self, f):
+        ids = find_nearest_points_index_in_vector(self.f_range_hz, f)
+        id1, id2 = int(ids[0]), int(ids[1])
+        if id1 == id2:               # a single bin
+            id2 += 1
+        return id1, id2              # half open: the upper band-edge bin is excluded
+
+    def _grid_rows(self):
+        """Rows of the grid this process evaluates (all of them on a single GPU)."""
+        return 0, self.grid.number_of_points
+
+    def _map_from_device_csm(self, f, csm_dev, remove_csm_diagonal, per_bin: bool = False):
+        id1, id2 = self._select_bins(f)
+        fsel = f[id1:id2]
+        nbins = id2 - id1
+        self.f_range_hz = np.array([fsel[0], fsel[-1]])
+        weights = simpson_weights(nbins, fsel[1] - fsel[0]) if nbins > 1 else np.ones(1)
+        mode = engine.resolve_map_mode()
+        op = engine.das_prepare(csm_dev, id1, nbins, remove_csm_diagonal, mode)
+        print("...Apply...")
+        g0, g1 = self._grid_rows()
+        out, pb = engine.das_map(op, self.mics.number_of_points, fsel, weights, self.c, self.mics._coordinates,
+                                 self.mics.array_center_coordinates, self.grid._coordinates[g0:g1],
+                                 _steering_code(self.st_vec), remove_csm_diagonal, mode, per_bin=per_bin)
+        self._per_bin_device = pb
+        return self._gather_map(out)
+
+    def _gather_map(self, out_dev):
+        return out_dev.cpu().numpy()

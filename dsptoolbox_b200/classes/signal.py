@@ -1,0 +1,176 @@
+"""`Signal`: the reference's time-series container, restricted to what the CSM path needs.
+
+API-compatible with reference classes/signal.py for: the constructor (:57-115), `time_data`
+(:215-301), `sampling_rate_hz` (:321-348), `set_spectrum_parameters` (:497-588),
+`spectrum_scaling` / `spectrum_method` (:590-666), `get_csm` (:948-1007) and
+`number_of_channels` / `len()`.  Plotting, file I/O, filtering, STFT etc. are out of scope
+ and raise NotImplementedError.
+
+`get_csm()` returns fresh host arrays like the reference; `get_csm_device()` is the additional
+zero-copy accessor the beamformers use so the matrix never crosses PCIe between the stages.
+"""
+
+from __future__ import annotations
+
+from warnings import warn
+
+import numpy as np
+
+from ..standard import _spectral_methods as _sm
+from ..standard.enums import SpectrumMethod, SpectrumScaling, Window
+from ._multichannel_data import MultichannelData
+
+
+class Signal(MultichannelData):
+    def __init__(self, path: str | None = None, time_data=None, sampling_rate_hz: int | None = None,
+                 constrain_amplitude: bool = False, activate_cache: bool = False):
+        self.constrain_amplitude = constrain_amplitude
+        self.activate_cache = activate_cache
+        if path is not None:
+            assert time_data is None, "Constructor cannot take a path and a vector at the same time"
+            assert sampling_rate_hz is None, "Constructor cannot take a path and a sampling rate at the same time"
+            raise NotImplementedError("Audio file reading is outside the accelerated path; pass time_data")
+        assert time_data is not None, "Either a path to an audio file or a time vector has to be passed"
+        assert sampling_rate_hz is not None, "A sampling rate should be passed!"
+        self.sampling_rate_hz = sampling_rate_hz
+        self.time_data = time_data
+        self.set_spectrum_parameters()
+
+    @staticmethod
+    def from_time_data(time_data, sampling_rate_hz: int, constrain_amplitude: bool = True):
+        return Signal(None, time_data, sampling_rate_hz, constrain_amplitude)
+
+    # ---- state ---------------------------------------------------------------------------
+    def _invalidate(self):
+        self._csm_dirty = True
+        self._csm_dev = None
+
+    def _get_data(self):
+        return self._time_data
+
+    # ---- time data -------------------------------------------------------------------------
+    @property
+    def time_data(self):
+        return self._time_data
+
+    @time_data.setter
+    def time_data(self, new_time_data):
+        td = np.atleast_2d(new_time_data).squeeze()
+        assert td.ndim <= 2, (f"{td.ndim} are too many dimensions for time data. Dimensions should"
+                              " be [time samples, channels]")
+        if td.ndim < 2:
+            td = td[..., None]
+        if td.shape[1] > td.shape[0]:      # more columns than rows: rows are channels
+            td = td.T
+        imag = None
+        if np.iscomplexobj(td):
+            imag, td = np.imag(td), np.real(td)
+        self._amplitude_scale_factor = 1.0
+        if self.constrain_amplitude:
+            peak = np.max(np.abs(td))
+            if imag is not None:
+                peak = max(peak, np.max(np.abs(imag)))
+            if peak > 1.0:
+                td /= peak
+                if imag is not None:
+                    imag /= peak
+                warn("Signal was over 0 dBFS, normalizing to 0 dBFS peak level was triggered")
+                self._amplitude_scale_factor = 1.0 / peak
+        self._time_data = td
+        self.time_data_imaginary = imag
+        self._invalidate()
+
+    @property
+    def amplitude_scale_factor(self) -> float:
+        return self._amplitude_scale_factor
+
+    @property
+    def sampling_rate_hz(self) -> int:
+        return self._sampling_rate_hz
+
+    @sampling_rate_hz.setter
+    def sampling_rate_hz(self, new_sampling_rate_hz):
+        assert type(new_sampling_rate_hz) is int, "Sampling rate can only be an integer"
+        self._sampling_rate_hz = new_sampling_rate_hz
+        self._invalidate()
+
+    @property
+    def length_samples(self) -> int:
+        return self._time_data.shape[0]
+
+    @property
+    def length_seconds(self) -> float:
+        return len(self) / self.sampling_rate_hz
+
+    # ---- spectrum parameters -----------------------------------------------------------------
+    def set_spectrum_parameters(self, method: SpectrumMethod = SpectrumMethod.WelchPeriodogram,
+                                smoothing: int = 0, pad_to_fast_length: bool = True,
+                                window_length_samples: int = 1024, window_type: Window = Window.Hann,
+                                overlap_percent: float = 50, detrend: bool = True, average: str = "mean",
+                                scaling: SpectrumScaling = SpectrumScaling.FFTBackward):
+        new = dict(method=method, smoothing=smoothing, pad_to_fast_length=pad_to_fast_length,
+                   window_length_samples=window_length_samples, window_type=window_type,
+                   overlap_percent=overlap_percent, detrend=detrend, average=average, scaling=scaling)
+        old = getattr(self, "_spectrum_parameters", None)
+        if old is None or any(old[k] != new[k] for k in old):
+            self._spectrum_parameters = new
+            self._invalidate()
+        return self
+
+    @property
+    def spectrum_scaling(self) -> SpectrumScaling:
+        return self._spectrum_parameters["scaling"]
+
+    @spectrum_scaling.setter
+    def spectrum_scaling(self, new_scaling: SpectrumScaling):
+        assert isinstance(new_scaling, SpectrumScaling)
+        self._spectrum_parameters["scaling"] = new_scaling
+        self._invalidate()
+
+    @property
+    def spectrum_method(self) -> SpectrumMethod:
+        return self._spectrum_parameters["method"]
+
+    @spectrum_method.setter
+    def spectrum_method(self, new_method: SpectrumMethod):
+        assert isinstance(new_method, SpectrumMethod)
+        self._spectrum_parameters["method"] = new_method
+        self._invalidate()
+
+    # ---- cross-spectral matrix -----------------------------------------------------------------
+    def _compute_csm_device(self, frame_range=None, reduce_fn=None):
+        p = self._spectrum_parameters
+        if self.spectrum_method != SpectrumMethod.WelchPeriodogram:
+            raise NotImplementedError("SpectrumMethod.FFT cross-spectral matrices are outside the accelerated path")
+        return _sm.csm_welch_device(self.time_data, self.sampling_rate_hz, p["window_length_samples"],
+                                    p["window_type"], p["overlap_percent"], p["detrend"], p["average"],
+                                    p["scaling"], frame_range=frame_range, reduce_fn=reduce_fn)
+
+    def get_csm_device(self, force_computation: bool = False):
+        """(f, csm) with csm a complex128 CUDA tensor (frequency, channels, channels).
+
+        With `activate_cache` the tensor is kept on the device between calls under the same
+        invalidation rules as the reference's host cache (signal.py:163-171, 973-1007); the
+        returned tensor is then shared, not copied.
+        """
+        assert self.number_of_channels > 1, (
+            "Cross spectral matrix can only be computed when at least two channels are available")
+        if self._csm_dev is None or force_computation or self._csm_dirty:
+            f, csm = self._compute_csm_device()
+            if not self.activate_cache:
+                return f, csm
+            self._csm_dev = (f, csm)
+            self._csm_dirty = False
+        return self._csm_dev[0].copy(), self._csm_dev[1]
+
+    def get_csm(self, force_computation: bool = False):
+        """Cross-spectral matrix as fresh host arrays (f float64 [nb], csm complex128 [nb, M, M])."""
+        f, csm = self.get_csm_device(force_computation)
+        return f, csm.cpu().numpy()
+
+    # ---- explicitly out of scope -------------------------------------------------------------------
+    def get_spectrum(self, *a, **k):
+        raise NotImplementedError("Signal.get_spectrum is outside the accelerated path (SURVEY.md section 8f)")
+
+    def get_spectrogram(self, *a, **k):
+        raise NotImplementedError("Signal.get_spectrogram is outside the accelerated path (SURVEY.md section 8f)")

@@ -1,0 +1,265 @@
+// K2 (per-bin Hermitian rank-K accumulation on the FP64 tensor pipe) and K2e (finalize).
+//
+// Replaces the M(M+1)/2 `_welch` calls of _csm_welch (standard/_spectral_methods.py:351-369):
+// with X_f in C^{M x K} the spectra of bin f over all channels and frames,
+//   S_f[j,i] = sum_k X_f[j,k] conj(X_f[i,k])   (j >= i),
+// i.e. the reference's conj(rfft(x_i)) * rfft(x_j) summed over frames (:141-152).
+//
+// K2 design: one CTA = one 64x64 block of the lower block-triangle of one bin; 4 warps, each
+// a 32x32 sub-block as 4x4 m8n8k4 FP64 MMA tiles with real and imaginary accumulators.
+// The complex product is mapped onto real DMMAs:
+//   Sr += Ar*Br^T + Ai*Bi^T          Si += Ai*Br^T + Ar*(-Bi)^T
+// Frames are streamed in chunks of 16 through a cp.async double buffer; the spectra layout
+// [bin][channel][frame] makes every tile row one contiguous run.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64;        // block rows/cols
+constexpr int KC = 16;        // frames per chunk
+constexpr int HERK_THREADS = 128;
+
+template <typename TIN> struct HerkSmem {
+    // row pitch in bytes: KC elements + padding chosen so that the 8 rows x 4 k fragment
+    // pattern of m8n8k4 is bank-conflict free (see fragment loads below)
+    static constexpr int ELEM = int(sizeof(cx<TIN>));
+    static constexpr int PITCH = KC * ELEM + (sizeof(TIN) == 8 ? 64 : 32);
+    static constexpr int TILE = BM * PITCH;
+    static constexpr int BYTES = 2 /*stages*/ * 2 /*A,B*/ * TILE;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <typename TIN> __device__ __forceinline__ double2 load_frag(const unsigned char *p);
+template <> __device__ __forceinline__ double2 load_frag<double>(const unsigned char *p) {
+    return *reinterpret_cast<const double2 *>(p);
+}
+template <> __device__ __forceinline__ double2 load_frag<float>(const unsigned char *p) {
+    float2 v = *reinterpret_cast<const float2 *>(p);
+    return make_double2(double(v.x), double(v.y));
+}
+
+// Issue the cp.async copies of one 64-row x KC-frame tile (rows >= M are left untouched: they
+// were zeroed once before the main loop).
+template <typename TIN>
+__device__ __forceinline__ void load_tile(unsigned char *dst, const cx<TIN> *__restrict__ Xf, int row0,
+                                          int M, int64_t Kp, int64_t kbase, int tid) {
+    using SM = HerkSmem<TIN>;
+    constexpr int SEG_PER_ROW = KC * SM::ELEM / 16;        // 16-byte segments per row
+    constexpr int TOTAL = BM * SEG_PER_ROW;
+#pragma unroll
+    for (int s = tid; s < TOTAL; s += HERK_THREADS) {
+        int r = s / SEG_PER_ROW, seg = s - r * SEG_PER_ROW;
+        int row = row0 + r;
+        if (row < M) {
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(Xf + int64_t(row) * Kp + kbase) + seg * 16;
+            cp_async16(dst + r * SM::PITCH + seg * 16, src);
+        }
+    }
+}
+
+template <typename TIN>
+__global__ void __launch_bounds__(HERK_THREADS)
+herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, double2 *__restrict__ S, int accumulate) {
+    using SM = HerkSmem<TIN>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wj = warp >> 1, wi = warp & 1;
+
+    // decode the lower-triangular block pair
+    const int p = blockIdx.x;
+    int bj = int((sqrtf(8.0f * float(p) + 1.0f) - 1.0f) * 0.5f);
+    while ((bj + 1) * (bj + 2) / 2 <= p) ++bj;
+    while (bj * (bj + 1) / 2 > p) --bj;
+    const int bi = p - bj * (bj + 1) / 2;
+    const bool diag = (bi == bj);
+    const int f = blockIdx.y;
+    const int rowA0 = bj * BM, rowB0 = bi * BM;
+    const cx<TIN> *Xf = X + int64_t(f) * M * Kp;
+
+    unsigned char *As[2] = {smem, smem + 2 * SM::TILE};
+    unsigned char *Bs[2] = {diag ? As[0] : smem + SM::TILE, diag ? As[1] : smem + 3 * SM::TILE};
+
+    // rows past M contribute zeros
+    for (int i = tid; i < SM::BYTES / 16; i += HERK_THREADS) reinterpret_cast<int4 *>(smem)[i] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+
+    double sr[4][4][2], si[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { sr[a][b][0] = sr[a][b][1] = 0.0; si[a][b][0] = si[a][b][1] = 0.0; }
+
+    const int nchunks = int(Kp / KC);
+    load_tile<TIN>(As[0], Xf, rowA0, M, Kp, 0, tid);
+    if (!diag) load_tile<TIN>(Bs[0], Xf, rowB0, M, Kp, 0, tid);
+    cp_async_commit();
+
+    const int frow = lane >> 2, fk = lane & 3;
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c & 1;
+        if (c + 1 < nchunks) {
+            load_tile<TIN>(As[st ^ 1], Xf, rowA0, M, Kp, int64_t(c + 1) * KC, tid);
+            if (!diag) load_tile<TIN>(Bs[st ^ 1], Xf, rowB0, M, Kp, int64_t(c + 1) * KC, tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const unsigned char *At = As[st] + (wj * 32 + frow) * SM::PITCH + fk * SM::ELEM;
+        const unsigned char *Bt = Bs[st] + (wi * 32 + frow) * SM::PITCH + fk * SM::ELEM;
+#pragma unroll
+        for (int ks = 0; ks < KC / 4; ++ks) {
+            double2 a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[q] = load_frag<TIN>(At + q * 8 * SM::PITCH + ks * 4 * SM::ELEM);
+                b[q] = load_frag<TIN>(Bt + q * 8 * SM::PITCH + ks * 4 * SM::ELEM);
+            }
+#pragma unroll
+            for (int jb = 0; jb < 4; ++jb)
+#pragma unroll
+                for (int ib = 0; ib < 4; ++ib) {
+                    dmma(sr[jb][ib][0], sr[jb][ib][1], a[jb].x, b[ib].x);
+                    dmma(sr[jb][ib][0], sr[jb][ib][1], a[jb].y, b[ib].y);
+                    dmma(si[jb][ib][0], si[jb][ib][1], a[jb].y, b[ib].x);
+                    dmma(si[jb][ib][0], si[jb][ib][1], a[jb].x, -b[ib].y);
+                }
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: C fragment (row = lane/4, cols 2*(lane%4)+{0,1}) ----
+    double2 *Sf = S + int64_t(f) * M * M;
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+        const int j = rowA0 + wj * 32 + jb * 8 + (lane >> 2);
+        if (j >= M) continue;
+#pragma unroll
+        for (int ib = 0; ib < 4; ++ib) {
+            const int i0 = rowB0 + wi * 32 + ib * 8 + 2 * (lane & 3);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = i0 + e;
+                if (i < M) {
+                    double2 v = make_double2(sr[jb][ib][e], si[jb][ib][e]);
+                    double2 *dst = Sf + int64_t(j) * M + i;
+                    if (accumulate) { double2 o = *dst; v.x += o.x; v.y += o.y; }
+                    *dst = v;
+                }
+            }
+        }
+    }
+}
+
+// Principal complex square root (numpy's np.sqrt on complex128, _spectral_methods.py:170-171).
+__device__ __forceinline__ double2 csqrt_principal(double2 z) {
+    const double a = z.x, b = z.y;
+    if (a == 0.0 && b == 0.0) return make_double2(0.0, b);
+    const double r = hypot(a, b);
+    if (a >= 0.0) {
+        const double t = sqrt(0.5 * (a + r));
+        return make_double2(t, b / (2.0 * t));
+    }
+    const double t = sqrt(0.5 * (r - a));
+    return make_double2(fabs(b) / (2.0 * t), copysign(t, b));
+}
+
+// K2e: one 32x32 tile of the lower triangle per CTA; mirrored tile written through smem.
+__global__ void __launch_bounds__(256)
+csm_finalize_kernel(const double2 *__restrict__ S, int M, int nb, double inv_frames, double factor,
+                    int halve_edges, int amplitude_sqrt, double2 *__restrict__ out) {
+    __shared__ double2 tile[32][33];
+    const int p = blockIdx.x;
+    int tj = int((sqrtf(8.0f * float(p) + 1.0f) - 1.0f) * 0.5f);
+    while ((tj + 1) * (tj + 2) / 2 <= p) ++tj;
+    while (tj * (tj + 1) / 2 > p) --tj;
+    const int ti = p - tj * (tj + 1) / 2;
+    const int f = blockIdx.y;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    double scale = inv_frames * factor;
+    const bool edge = halve_edges && (f == 0 || f == nb - 1);
+    const double2 *Sf = S + int64_t(f) * M * M;
+    double2 *of = out + int64_t(f) * M * M;
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        const int j = tj * 32 + ty + r, i = ti * 32 + tx;
+        double2 v = make_double2(0.0, 0.0);
+        if (j < M && i < M && i <= j) {
+            v = Sf[int64_t(j) * M + i];
+            // order of the reference: mean, *factor, /2 on the edge bins, sqrt
+            v.x *= inv_frames; v.y *= inv_frames;
+            v.x *= factor; v.y *= factor;
+            if (edge) { v.x *= 0.5; v.y *= 0.5; }
+            if (i == j) v.y = 0.0;
+            if (amplitude_sqrt) v = (i == j) ? make_double2(sqrt(v.x), 0.0) : csqrt_principal(v);
+            of[int64_t(j) * M + i] = v;
+        }
+        tile[ty + r][tx] = v;
+    }
+    (void)scale;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        // mirrored element: row i = ti*32 + (ty+r), col j = tj*32 + tx, strictly above the diagonal
+        const int i = ti * 32 + ty + r, j = tj * 32 + tx;
+        if (i < M && j < M && i < j) {
+            double2 v = tile[tx][ty + r];
+            of[int64_t(i) * M + j] = make_double2(v.x, -v.y);
+        }
+    }
+}
+
+template <typename TIN>
+int launch_herk(const void *X, int M, int64_t Kp, int nb, void *S, int accumulate, cudaStream_t st) {
+    using SM = HerkSmem<TIN>;
+    auto kern = herk_dmma_kernel<TIN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        B2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES));
+        attr_done = true;
+    }
+    const int nbk = (M + BM - 1) / BM;
+    dim3 grid((unsigned)(nbk * (nbk + 1) / 2), (unsigned)nb);
+    kern<<<grid, HERK_THREADS, SM::BYTES, st>>>((const cx<TIN> *)X, M, Kp, (double2 *)S, accumulate);
+    B2_LAUNCH_OK("b2_csm_herk");
+    return B2_OK;
+}
+
+}  // namespace
+
+extern "C" int b2_csm_herk(const void *X_dev, int M, int64_t Kp, int nb, void *S_dev, int accumulate,
+                           int precision, void *stream) {
+    B2_REQUIRE(X_dev && S_dev, B2_EINVAL, "b2_csm_herk: null pointer");
+    B2_REQUIRE(M > 0 && nb > 0 && nb <= 65535, B2_EINVAL, "b2_csm_herk: bad M=%d / nb=%d", M, nb);
+    B2_REQUIRE(Kp > 0 && Kp % KC == 0, B2_EINVAL, "b2_csm_herk: Kp=%lld must be a positive multiple of %d", (long long)Kp, KC);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == B2_F64) return launch_herk<double>(X_dev, M, Kp, nb, S_dev, accumulate, st);
+    if (precision == B2_F32) return launch_herk<float>(X_dev, M, Kp, nb, S_dev, accumulate, st);
+    b2_set_error("b2_csm_herk: bad precision %d", precision);
+    return B2_EINVAL;
+}
+
+extern "C" int b2_csm_finalize(const void *S_dev, int M, int nb, double inv_frames, double factor,
+                               int halve_edges, int amplitude_sqrt, void *csm_out_dev, void *stream) {
+    B2_REQUIRE(S_dev && csm_out_dev, B2_EINVAL, "b2_csm_finalize: null pointer");
+    B2_REQUIRE(M > 0 && nb > 0 && nb <= 65535, B2_EINVAL, "b2_csm_finalize: bad M=%d / nb=%d", M, nb);
+    const int nt = (M + 31) / 32;
+    dim3 grid((unsigned)(nt * (nt + 1) / 2), (unsigned)nb);
+    csm_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const double2 *)S_dev, M, nb, inv_frames, factor,
+                                                                halve_edges, amplitude_sqrt, (double2 *)csm_out_dev);
+    B2_LAUNCH_OK("b2_csm_finalize");
+    return B2_OK;
+}

@@ -1,0 +1,373 @@
+// K0 (channel gather / zero-pad / convert) and K1 (frame + window + detrend + real FFT).
+//
+// Replaces, for every channel at once, what the reference does per channel PAIR:
+//   _get_framed_signal  (standard/_framed_signal_representation.py:50-65)
+//   window, mean removal, np.fft.rfft in _welch (standard/_spectral_methods.py:126-148)
+//
+// K1 design (HBM-bound): one CTA owns FR consecutive frames of ONE channel.  The frames are
+// read from the channel-major padded copy with vector loads, multiplied by the window on the
+// way into shared memory, packed as wl/2 complex points (z[n] = y[2n] + i*y[2n+1]), and
+// transformed by an in-place shared-memory Stockham FFT (radix 8/4/2, register-staged,
+// autosorting).  The real-FFT untangling is fused into the store, which writes, for every
+// bin, the FR frames as one contiguous run of the [bin][channel][frame] spectra layout that
+// the rank-K kernel consumes without transposition.
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- compile-time geometry
+template <typename T, int LOG2NC> struct Geo {
+    static constexpr int NC = 1 << LOG2NC;              // complex points = wl / 2
+    static constexpr int N = 2 * NC;                    // wl
+    static constexpr int NCP = NC + (NC >> 3);          // 1 pad slot per 8 points
+    static constexpr int PITCH = NCP + 1;               // per-frame pitch (staggers frames)
+    static constexpr int CXB = int(sizeof(cx<T>));
+    static constexpr int frames_fit(int fr) { return fr * PITCH * CXB <= 72 * 1024; }
+    static constexpr int FR = frames_fit(16) ? 16 : frames_fit(8) ? 8 : frames_fit(4) ? 4 : frames_fit(2) ? 2 : 1;
+    static constexpr int VPT = sizeof(T) == 8 ? 16 : 32;  // complex values held per thread
+    static constexpr int NT_RAW = FR * NC / VPT;
+    static constexpr int NT = NT_RAW < 64 ? 64 : (NT_RAW > 1024 ? 1024 : NT_RAW);
+    static constexpr int SMEM = FR * PITCH * CXB;
+};
+
+__device__ __forceinline__ int padidx(int i) { return i + (i >> 3); }
+
+// ---------------------------------------------------------------- small DFTs, natural order
+template <typename C> __device__ __forceinline__ void dft2(C &a, C &b) {
+    C t = a; a = cadd(t, b); b = csub(t, b);
+}
+template <typename C> __device__ __forceinline__ void dft4(C &v0, C &v1, C &v2, C &v3) {
+    C t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3), t3 = cmul_mi(csub(v1, v3));
+    v0 = cadd(t0, t2); v2 = csub(t0, t2); v1 = cadd(t1, t3); v3 = csub(t1, t3);
+}
+template <typename T> __device__ __forceinline__ void dft8(cx<T> *v) {
+    using C = cx<T>;
+    C e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    C o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+    dft4(e0, e1, e2, e3);
+    dft4(o0, o1, o2, o3);
+    const T h = T(0.70710678118654752440);
+    // o1 *= (1 - i)/sqrt2 ; o2 *= -i ; o3 *= (-1 - i)/sqrt2
+    C w1 = mk<T>((o1.x + o1.y) * h, (o1.y - o1.x) * h);
+    C w2 = cmul_mi(o2);
+    C w3 = mk<T>((o3.y - o3.x) * h, -(o3.x + o3.y) * h);
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, w1); v[5] = csub(e1, w1);
+    v[2] = cadd(e2, w2); v[6] = csub(e2, w2);
+    v[3] = cadd(e3, w3); v[7] = csub(e3, w3);
+}
+template <typename T, int R> __device__ __forceinline__ void dftR(cx<T> *v) {
+    if constexpr (R == 8) dft8<T>(v);
+    else if constexpr (R == 4) dft4(v[0], v[1], v[2], v[3]);
+    else dft2(v[0], v[1]);
+}
+
+// One Stockham pass over all FR frames in the CTA: radix R, NS = product of earlier radices.
+template <typename T, int LOG2NC, int R, int NS>
+__device__ __forceinline__ void stockham_pass(cx<T> *s, const cx<T> *__restrict__ tw, int tid) {
+    using G = Geo<T, LOG2NC>;
+    constexpr int NC = G::NC, J = NC / R;                // butterflies per frame
+    constexpr int TOTAL = G::FR * J;
+    constexpr int ITEMS = (TOTAL + G::NT - 1) / G::NT;
+    cx<T> v[ITEMS][R];
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        int item = tid + it * G::NT;
+        if (item < TOTAL) {
+            int fr = item / J, j = item - fr * J;
+            int k = j & (NS - 1);
+            cx<T> *base = s + fr * G::PITCH;
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[it][r] = base[padidx(j + r * J)];
+            if constexpr (NS > 1) {
+                constexpr int TSTEP = G::N / (NS * R);
+#pragma unroll
+                for (int r = 1; r < R; ++r) v[it][r] = cmul(v[it][r], tw[k * r * TSTEP]);
+            }
+            dftR<T, R>(v[it]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        int item = tid + it * G::NT;
+        if (item < TOTAL) {
+            int fr = item / J, j = item - fr * J;
+            int k = j & (NS - 1);
+            int j0 = (j - k) * R + k;
+            cx<T> *base = s + fr * G::PITCH;
+#pragma unroll
+            for (int r = 0; r < R; ++r) base[padidx(j0 + r * NS)] = v[it][r];
+        }
+    }
+    __syncthreads();
+}
+
+// Run all passes: radix 8 while >= 8 points remain, then one radix 4 / 2 pass.
+template <typename T, int LOG2NC, int NS>
+__device__ __forceinline__ void stockham_all(cx<T> *s, const cx<T> *__restrict__ tw, int tid) {
+    constexpr int NC = 1 << LOG2NC;
+    constexpr int REM = NC / NS;
+    if constexpr (REM >= 8) {
+        stockham_pass<T, LOG2NC, 8, NS>(s, tw, tid);
+        stockham_all<T, LOG2NC, NS * 8>(s, tw, tid);
+    } else if constexpr (REM == 4) {
+        stockham_pass<T, LOG2NC, 4, NS>(s, tw, tid);
+    } else if constexpr (REM == 2) {
+        stockham_pass<T, LOG2NC, 2, NS>(s, tw, tid);
+    }
+}
+
+template <typename T, int LOG2NC>
+__global__ void __launch_bounds__(Geo<T, LOG2NC>::NT)
+welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframes,
+                  const T *__restrict__ window, const cx<T> *__restrict__ tw, int detrend,
+                  T scale, cx<T> *__restrict__ X, int M, int64_t Kp, int vec_ok) {
+    using G = Geo<T, LOG2NC>;
+    using C = cx<T>;
+    constexpr int NC = G::NC, FR = G::FR, NT = G::NT, NW = NT / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *s = reinterpret_cast<C *>(smem_raw);
+    __shared__ T warp_part[NW];
+    __shared__ T frame_mean;
+
+    const int tid = threadIdx.x;
+    const int m = blockIdx.y;
+    const int64_t k0 = int64_t(blockIdx.x) * FR;
+    const T *xrow = xc + int64_t(m) * Lp;
+
+    // ---- load + window (frames beyond nframes are all-zero) ----
+    for (int fr = 0; fr < FR; ++fr) {
+        const int64_t k = k0 + fr;
+        C *base = s + fr * G::PITCH;
+        if (k < nframes) {
+            const T *src = xrow + k * int64_t(step);
+            if (vec_ok) {
+                const C *src2 = reinterpret_cast<const C *>(src);
+                const C *w2 = reinterpret_cast<const C *>(window);
+                for (int n = tid; n < NC; n += NT) {
+                    C x = __ldg(src2 + n), w = __ldg(w2 + n);
+                    base[padidx(n)] = mk<T>(x.x * w.x, x.y * w.y);
+                }
+            } else {
+                for (int n = tid; n < NC; n += NT)
+                    base[padidx(n)] = mk<T>(src[2 * n] * window[2 * n], src[2 * n + 1] * window[2 * n + 1]);
+            }
+        } else {
+            for (int n = tid; n < NC; n += NT) base[padidx(n)] = mk<T>(T(0), T(0));
+        }
+    }
+    __syncthreads();
+
+    // ---- mean removal of the windowed (zero-padded) frame: _spectral_methods.py:136-137 ----
+    if (detrend) {
+        for (int fr = 0; fr < FR; ++fr) {
+            C *base = s + fr * G::PITCH;
+            T acc = T(0);
+            for (int n = tid; n < NC; n += NT) { C z = base[padidx(n)]; acc += z.x + z.y; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if ((tid & 31) == 0) warp_part[tid >> 5] = acc;
+            __syncthreads();
+            if (tid == 0) {
+                T tot = T(0);
+                for (int w = 0; w < NW; ++w) tot += warp_part[w];
+                frame_mean = tot / T(G::N);
+            }
+            __syncthreads();
+            const T mu = frame_mean;
+            for (int n = tid; n < NC; n += NT) {
+                C z = base[padidx(n)];
+                base[padidx(n)] = mk<T>(z.x - mu, z.y - mu);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- wl/2-point complex FFT of every frame ----
+    stockham_all<T, LOG2NC, 1>(s, tw, tid);
+
+    // ---- untangle to the wl/2+1 real-FFT bins and store [bin][channel][frame] ----
+    const T half = T(0.5) * scale;
+    for (int idx = tid; idx < (NC + 1) * FR; idx += NT) {
+        const int fr = idx % FR, kf = idx / FR;
+        const C *base = s + fr * G::PITCH;
+        C a = base[padidx(kf & (NC - 1))];
+        C b = cconj(base[padidx((NC - kf) & (NC - 1))]);
+        C w = __ldg(tw + kf);
+        C sum = cadd(a, b), dif = cmul(w, csub(a, b));
+        // X = 0.5*(a+b) - 0.5*i*w*(a-b)
+        C out = mk<T>((sum.x + dif.y) * half, (sum.y - dif.x) * half);
+        X[(int64_t(kf) * M + m) * Kp + (k0 + fr)] = out;
+    }
+}
+
+template <typename T>
+__global__ void twiddle_kernel(cx<T> *tw, int N) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < N) {
+        double sn, cs;
+        sincospi(2.0 * double(t) / double(N), &sn, &cs);
+        tw[t] = mk<T>(T(cs), T(-sn));
+    }
+}
+
+// ---------------------------------------------------------------- K0
+// time-major source (stride_m == 1 typical): 32x32 tile transpose through shared memory.
+template <typename IN, typename OUT>
+__global__ void gather_transpose_kernel(const IN *__restrict__ x, int64_t stride_t, int64_t stride_m,
+                                        int64_t t0, int64_t nt, int M, OUT *__restrict__ out, int64_t Lp) {
+    __shared__ OUT tile[32][33];
+    const int64_t tb = int64_t(blockIdx.x) * 32;
+    const int mb = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        int64_t t = tb + ty + r;
+        int m = mb + tx;
+        OUT v = OUT(0);
+        if (t < nt && m < M) v = OUT(x[(t0 + t) * stride_t + int64_t(m) * stride_m]);
+        tile[ty + r][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        int m = mb + ty + r;
+        int64_t t = tb + tx;
+        if (m < M && t < Lp) out[int64_t(m) * Lp + t] = tile[tx][ty + r];
+    }
+}
+
+// channel-major source (stride_t == 1): plain convert/copy with zero fill.
+template <typename IN, typename OUT>
+__global__ void gather_rows_kernel(const IN *__restrict__ x, int64_t stride_m, int64_t t0, int64_t nt,
+                                   OUT *__restrict__ out, int64_t Lp) {
+    const int m = blockIdx.y;
+    const IN *src = x + int64_t(m) * stride_m + t0;
+    OUT *dst = out + int64_t(m) * Lp;
+    for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < Lp; t += int64_t(gridDim.x) * blockDim.x)
+        dst[t] = t < nt ? OUT(src[t]) : OUT(0);
+}
+
+template <typename IN, typename OUT>
+int launch_gather(const void *x, int64_t stride_t, int64_t stride_m, int64_t t0, int64_t nt, int M,
+                  void *out, int64_t Lp, cudaStream_t st) {
+    if (stride_t == 1 && stride_m != 1) {
+        int64_t bx = (Lp + 255) / 256;
+        if (bx > 4096) bx = 4096;
+        gather_rows_kernel<IN, OUT><<<dim3((unsigned)bx, M), 256, 0, st>>>(
+            (const IN *)x, stride_m, t0, nt, (OUT *)out, Lp);
+    } else {
+        dim3 grid((unsigned)((Lp + 31) / 32), (unsigned)((M + 31) / 32));
+        gather_transpose_kernel<IN, OUT><<<grid, dim3(32, 8), 0, st>>>(
+            (const IN *)x, stride_t, stride_m, t0, nt, M, (OUT *)out, Lp);
+    }
+    B2_LAUNCH_OK("b2_prepare_channels");
+    return B2_OK;
+}
+
+template <typename T, int LOG2NC>
+int launch_rfft(const void *xc, int64_t Lp, int M, int step, int64_t nframes, const void *window,
+                const void *tw, int detrend, double scale, void *X, int64_t Kp, cudaStream_t st) {
+    using G = Geo<T, LOG2NC>;
+    auto kern = welch_rfft_kernel<T, LOG2NC>;
+    static bool attr_done = false;   // per instantiation
+    if (!attr_done) {
+        B2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+        attr_done = true;
+    }
+    B2_REQUIRE(Kp % G::FR == 0, B2_EINVAL, "b2_welch_rfft: Kp=%lld must be a multiple of %d", (long long)Kp, G::FR);
+    int vec_ok = (step % 2 == 0) && (Lp % 2 == 0) && (reinterpret_cast<uintptr_t>(xc) % (2 * sizeof(T)) == 0) &&
+                 (reinterpret_cast<uintptr_t>(window) % (2 * sizeof(T)) == 0);
+    dim3 grid((unsigned)(Kp / G::FR), (unsigned)M);
+    kern<<<grid, G::NT, G::SMEM, st>>>((const T *)xc, Lp, step, nframes, (const T *)window,
+                                      (const cx<T> *)tw, detrend, T(scale), (cx<T> *)X, M, Kp, vec_ok);
+    B2_LAUNCH_OK("b2_welch_rfft");
+    return B2_OK;
+}
+
+template <typename T>
+int dispatch_rfft(int log2nc, const void *xc, int64_t Lp, int M, int step, int64_t nframes,
+                  const void *window, const void *tw, int detrend, double scale, void *X, int64_t Kp,
+                  cudaStream_t st) {
+    switch (log2nc) {
+#define B2_CASE(L) case L: return launch_rfft<T, L>(xc, Lp, M, step, nframes, window, tw, detrend, scale, X, Kp, st);
+        B2_CASE(2) B2_CASE(3) B2_CASE(4) B2_CASE(5) B2_CASE(6) B2_CASE(7) B2_CASE(8)
+        B2_CASE(9) B2_CASE(10) B2_CASE(11) B2_CASE(12) B2_CASE(13)
+#undef B2_CASE
+    default: break;
+    }
+    b2_set_error("b2_welch_rfft: window length 2^%d is outside the shared-memory FFT range [8, 16384]", log2nc + 1);
+    return B2_EUNSUPPORTED;
+}
+
+template <typename T> int frame_tile(int log2nc) {
+    switch (log2nc) {
+#define B2_CASE(L) case L: return Geo<T, L>::FR;
+        B2_CASE(2) B2_CASE(3) B2_CASE(4) B2_CASE(5) B2_CASE(6) B2_CASE(7) B2_CASE(8)
+        B2_CASE(9) B2_CASE(10) B2_CASE(11) B2_CASE(12) B2_CASE(13)
+#undef B2_CASE
+    default: return -1;
+    }
+}
+
+}  // namespace
+
+extern "C" int b2_welch_frames(int64_t L, int wl, int step, int64_t *frames, int64_t *pad) {
+    B2_REQUIRE(L > 0 && wl > 0 && step > 0, B2_EINVAL, "b2_welch_frames: L, wl and step must be positive");
+    if (frames) *frames = (L + step - 1) / step;
+    if (pad) *pad = wl - (L % step);
+    return B2_OK;
+}
+
+extern "C" int b2_welch_frame_tile(int wl, int precision) {
+    int l2 = ilog2_exact(wl);
+    if (l2 < 3 || l2 > 14) { b2_set_error("b2_welch_frame_tile: unsupported window length %d", wl); return B2_EUNSUPPORTED; }
+    return precision == B2_F64 ? frame_tile<double>(l2 - 1) : frame_tile<float>(l2 - 1);
+}
+
+extern "C" int b2_fft_twiddles(int wl, int precision, void *twiddle_dev, void *stream) {
+    B2_REQUIRE(twiddle_dev != nullptr, B2_EINVAL, "b2_fft_twiddles: null output");
+    B2_REQUIRE(ilog2_exact(wl) >= 3, B2_EINVAL, "b2_fft_twiddles: wl=%d must be a power of two >= 8", wl);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == B2_F64) twiddle_kernel<double><<<(wl + 255) / 256, 256, 0, st>>>((double2 *)twiddle_dev, wl);
+    else if (precision == B2_F32) twiddle_kernel<float><<<(wl + 255) / 256, 256, 0, st>>>((float2 *)twiddle_dev, wl);
+    else { b2_set_error("b2_fft_twiddles: bad precision %d", precision); return B2_EINVAL; }
+    B2_LAUNCH_OK("b2_fft_twiddles");
+    return B2_OK;
+}
+
+extern "C" int b2_prepare_channels(const void *x_dev, int in_dtype, int64_t stride_t, int64_t stride_m,
+                                   int64_t t0, int64_t nt, int M, void *out_dev, int64_t Lp,
+                                   int precision, void *stream) {
+    B2_REQUIRE(x_dev && out_dev, B2_EINVAL, "b2_prepare_channels: null pointer");
+    B2_REQUIRE(M > 0 && nt >= 0 && Lp >= nt && t0 >= 0, B2_EINVAL,
+               "b2_prepare_channels: bad sizes M=%d nt=%lld Lp=%lld t0=%lld", M, (long long)nt, (long long)Lp, (long long)t0);
+    B2_REQUIRE(stride_t > 0 && stride_m > 0, B2_EINVAL, "b2_prepare_channels: strides must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_dtype == B2_F64 && precision == B2_F64) return launch_gather<double, double>(x_dev, stride_t, stride_m, t0, nt, M, out_dev, Lp, st);
+    if (in_dtype == B2_F64 && precision == B2_F32) return launch_gather<double, float>(x_dev, stride_t, stride_m, t0, nt, M, out_dev, Lp, st);
+    if (in_dtype == B2_F32 && precision == B2_F64) return launch_gather<float, double>(x_dev, stride_t, stride_m, t0, nt, M, out_dev, Lp, st);
+    if (in_dtype == B2_F32 && precision == B2_F32) return launch_gather<float, float>(x_dev, stride_t, stride_m, t0, nt, M, out_dev, Lp, st);
+    b2_set_error("b2_prepare_channels: bad dtype/precision %d/%d", in_dtype, precision);
+    return B2_EINVAL;
+}
+
+extern "C" int b2_welch_rfft(const void *xc_dev, int64_t Lp, int M, int wl, int step, int64_t nframes,
+                             const void *window_dev, const void *twiddle_dev, int detrend,
+                             double fft_scale, void *X_out_dev, int64_t Kp, int precision, void *stream) {
+    B2_REQUIRE(xc_dev && window_dev && twiddle_dev && X_out_dev, B2_EINVAL, "b2_welch_rfft: null pointer");
+    int l2 = ilog2_exact(wl);
+    B2_REQUIRE(l2 >= 3 && l2 <= 18, B2_EINVAL,
+               "b2_welch_rfft: Window length should be a power of 2 between [8, 262_144] (got %d)", wl);
+    B2_REQUIRE(step > 0 && step <= wl, B2_EINVAL, "b2_welch_rfft: step=%d must be in (0, wl]", step);
+    B2_REQUIRE(M > 0 && M <= 65535, B2_EINVAL, "b2_welch_rfft: M=%d out of range", M);
+    B2_REQUIRE(nframes >= 0 && nframes <= Kp, B2_EINVAL, "b2_welch_rfft: nframes=%lld exceeds Kp=%lld", (long long)nframes, (long long)Kp);
+    B2_REQUIRE(nframes == 0 || Lp >= (nframes - 1) * int64_t(step) + wl, B2_EINVAL,
+               "b2_welch_rfft: padded length Lp=%lld too short for %lld frames", (long long)Lp, (long long)nframes);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == B2_F64) return dispatch_rfft<double>(l2 - 1, xc_dev, Lp, M, step, nframes, window_dev, twiddle_dev, detrend, fft_scale, X_out_dev, Kp, st);
+    if (precision == B2_F32) return dispatch_rfft<float>(l2 - 1, xc_dev, Lp, M, step, nframes, window_dev, twiddle_dev, detrend, fft_scale, X_out_dev, Kp, st);
+    b2_set_error("b2_welch_rfft: bad precision %d", precision);
+    return B2_EINVAL;
+}

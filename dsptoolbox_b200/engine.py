@@ -1,0 +1,271 @@
+"""Device-side orchestration of the two stages (host logic only; all arithmetic is in libb2dsp).
+
+PyTorch is used for what it is good at here: owning device memory, streams and (in
+dist.py) the NCCL process group.  Nothing in this file computes on the CPU.
+
+Stage 1 (Welch CSM), replacing standard/_spectral_methods.py:285-371 of the reference:
+    K0 b2_prepare_channels -> K1 b2_welch_rfft -> K2 b2_csm_herk -> [all-reduce] -> K2e b2_csm_finalize
+Stage 2 (DAS map), replacing beamforming/beamforming.py:841-878:
+    K3a b2_das_prepare -> K3 b2_das_map
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _native as N
+
+
+# --------------------------------------------------------------------------- configuration
+@dataclass
+class Config:
+    """Run-time switches of the accelerated path (the reference has none: SURVEY.md section 5)."""
+
+    #: "fp64" = strict (fp64 FFT + fp64 tensor-core accumulation, meets rtol 1e-5 on any data),
+    #: "fp32" = fast (fp32 FFT and spectra, fp64 accumulation).
+    csm_precision: str = "fp64"
+    #: "auto", "simt_f64", "simt_f32", "tf32", "tf32x3"
+    map_mode: str = "auto"
+    #: device spectra buffer budget in bytes; longer recordings are processed in frame chunks
+    spectra_budget_bytes: int = 24 << 30
+    #: last-call statistics (kernel times are only filled when `profile` is on)
+    profile: bool = False
+    stats: dict = field(default_factory=dict)
+
+
+config = Config()
+
+_PREC = {"fp64": N.F64, "fp32": N.F32}
+_MAP_MODES = {"simt_f64": N.MAP_SIMT_F64, "simt_f32": N.MAP_SIMT_F32, "tf32": N.MAP_TC_TF32,
+              "tf32x3": N.MAP_TC_TF32X3}
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("dsptoolbox_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def tc_map_available() -> bool:
+    """True when the tcgen05 map kernel is compiled into the library."""
+    return N.lib().b2_das_operand_bytes(64, 1, N.MAP_TC_TF32X3) > 0
+
+
+def resolve_map_mode(mode: str | None = None) -> int:
+    mode = (mode or config.map_mode).lower()
+    if mode == "auto":
+        return N.MAP_TC_TF32X3 if tc_map_available() else N.MAP_SIMT_F32
+    if mode not in _MAP_MODES:
+        raise ValueError(f"unknown map mode {mode!r}")
+    return _MAP_MODES[mode]
+
+
+# --------------------------------------------------------------------------- helpers
+def welch_frames(length: int, wl: int, step: int) -> tuple[int, int]:
+    """(frames, zero padding) -- reference helpers/other.py:181-213 with zero_padding=True."""
+    k, p = ctypes.c_int64(), ctypes.c_int64()
+    N.check(N.lib().b2_welch_frames(length, wl, step, ctypes.byref(k), ctypes.byref(p)), "welch_frames")
+    return k.value, p.value
+
+
+_twiddle_cache: dict = {}
+
+
+def _twiddles(wl: int, prec: int, device):
+    torch = _torch()
+    key = (wl, prec, str(device))
+    tw = _twiddle_cache.get(key)
+    if tw is None:
+        tw = torch.empty(wl, dtype=torch.complex128 if prec == N.F64 else torch.complex64, device=device)
+        N.check(N.lib().b2_fft_twiddles(wl, prec, N.ptr(tw), N.stream_handle()), "b2_fft_twiddles")
+        _twiddle_cache[key] = tw
+    return tw
+
+
+def _as_device_block(x, t0: int, t1: int, device):
+    """Upload rows [t0, t1) of the (L, M) recording without changing its memory order.
+
+    Returns (tensor, in_dtype code, stride_t, stride_m) for b2_prepare_channels.  `x` may be a
+    numpy array (host; C- or F-ordered views are uploaded as they lie) or a CUDA tensor.
+    """
+    torch = _torch()
+    if isinstance(x, torch.Tensor):
+        if x.dtype not in (torch.float32, torch.float64):
+            x = x.to(torch.float64)
+        xs = x[t0:t1]
+        if xs.device.type != "cuda":
+            xs = xs.to(device, non_blocking=True)
+        code = N.F64 if xs.dtype == torch.float64 else N.F32
+        return xs, code, xs.stride(0), xs.stride(1)
+    x = np.asarray(x)
+    if x.dtype not in (np.float32, np.float64):
+        x = x.astype(np.float64)          # the reference upcasts when framing
+    code = N.F64 if x.dtype == np.float64 else N.F32
+    xs = x[t0:t1]
+    if xs.flags.c_contiguous:
+        t = torch.from_numpy(xs).to(device, non_blocking=True)
+        return t, code, t.stride(0), t.stride(1)
+    if xs.T.flags.c_contiguous:          # (channels, time) storage seen through Signal's transpose
+        t = torch.from_numpy(xs.T).to(device, non_blocking=True)
+        return t, code, t.stride(1), t.stride(0)
+    t = torch.from_numpy(np.ascontiguousarray(xs)).to(device, non_blocking=True)
+    return t, code, t.stride(0), t.stride(1)
+
+
+class _Timer:
+    """CUDA-event stopwatch on the current stream, active only under config.profile."""
+
+    def __init__(self):
+        self.marks = []
+
+    def mark(self, name):
+        if config.profile:
+            torch = _torch()
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def report(self) -> dict:
+        if not config.profile or len(self.marks) < 2:
+            return {}
+        torch = _torch()
+        torch.cuda.synchronize()
+        out = {}
+        for (_, a), (n, b) in zip(self.marks[:-1], self.marks[1:]):
+            out[n] = out.get(n, 0.0) + a.elapsed_time(b)
+        return out
+
+
+# --------------------------------------------------------------------------- stage 1
+def csm_partial_sums(x, length: int, wl: int, step: int, window: np.ndarray, detrend: bool,
+                     fft_scale: float, frame_range: tuple[int, int] | None = None,
+                     precision: str | None = None, device=None):
+    """Un-normalised per-bin sums S_f = sum_k X_k X_k^H over the frames in `frame_range`.
+
+    Returns (S, n_frames_total): S is a complex128 CUDA tensor (nb, M, M) whose lower triangle
+    (row >= col) is valid.  Partial sums of disjoint frame ranges add up to the full sum, which
+    is what makes the stage frame-shardable.
+    """
+    torch = _torch()
+    lib = N.lib()
+    prec = _PREC[(precision or config.csm_precision).lower()]
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    M = int(x.shape[1])
+    K_total, _ = welch_frames(length, wl, step)
+    k0, k1 = frame_range if frame_range is not None else (0, K_total)
+    assert 0 <= k0 <= k1 <= K_total, "frame range outside the recording"
+    nb = wl // 2 + 1
+    rdt = torch.float64 if prec == N.F64 else torch.float32
+    cdt = torch.complex128 if prec == N.F64 else torch.complex64
+    st = N.stream_handle()
+    timer = _Timer()
+
+    tile = N.check(lib.b2_welch_frame_tile(wl, prec), "b2_welch_frame_tile")
+    tile = max(16, tile)
+    bytes_per_frame = nb * M * (16 if prec == N.F64 else 8)
+    max_frames = max(tile, (config.spectra_budget_bytes // bytes_per_frame) // tile * tile)
+
+    win = torch.from_numpy(np.ascontiguousarray(window, dtype=np.float64)).to(device).to(rdt)
+    tw = _twiddles(wl, prec, device)
+    S = torch.empty((nb, M, M), dtype=torch.complex128, device=device)
+    first = True
+    timer.mark("start")
+    kc = k0
+    if k1 == k0:
+        S.zero_()
+    while kc < k1:
+        kn = min(k1, kc + max_frames)
+        nfr = kn - kc
+        Kp = (nfr + tile - 1) // tile * tile
+        t0 = kc * step
+        t1 = min(length, (kn - 1) * step + wl)           # samples beyond `length` are the zero padding
+        Lp = (Kp - 1) * step + wl
+        Lp += (-Lp) % 4
+        xs, code, s_t, s_m = _as_device_block(x, t0, t1, device)
+        timer.mark("h2d")
+        xc = torch.empty((M, Lp), dtype=rdt, device=device)
+        N.check(lib.b2_prepare_channels(N.ptr(xs), code, s_t, s_m, 0, t1 - t0, M, N.ptr(xc), Lp, prec, st),
+                "b2_prepare_channels")
+        timer.mark("k0_prepare")
+        X = torch.empty((nb, M, Kp), dtype=cdt, device=device)
+        N.check(lib.b2_welch_rfft(N.ptr(xc), Lp, M, wl, step, nfr, N.ptr(win), N.ptr(tw), int(bool(detrend)),
+                                  float(fft_scale), N.ptr(X), Kp, prec, st), "b2_welch_rfft")
+        timer.mark("k1_rfft")
+        N.check(lib.b2_csm_herk(N.ptr(X), M, Kp, nb, N.ptr(S), 0 if first else 1, prec, st), "b2_csm_herk")
+        timer.mark("k2_herk")
+        first = False
+        kc = kn
+        del xs, xc, X
+    config.stats["csm"] = dict(times_ms=timer.report(), frames=k1 - k0, frames_total=K_total, M=M, nb=nb,
+                               precision="fp64" if prec == N.F64 else "fp32")
+    return S, K_total
+
+
+def csm_finalize(S, n_frames: int, factor: float, halve_edges: bool, amplitude_sqrt: bool):
+    """Average / scale / sqrt / mirror the summed spectra -> complex128 (nb, M, M) CUDA tensor."""
+    torch = _torch()
+    nb, M, _ = S.shape
+    out = torch.empty_like(S)
+    N.check(N.lib().b2_csm_finalize(N.ptr(S), M, nb, 1.0 / float(n_frames), float(factor), int(bool(halve_edges)),
+                                    int(bool(amplitude_sqrt)), N.ptr(out), N.stream_handle()), "b2_csm_finalize")
+    return out
+
+
+# --------------------------------------------------------------------------- stage 2
+def das_prepare(csm_dev, bin0: int, nbins: int, remove_diag: bool, mode: int):
+    """Build the map kernel's operand for bins [bin0, bin0+nbins) of a device CSM."""
+    torch = _torch()
+    lib = N.lib()
+    nb, M, _ = csm_dev.shape
+    nbytes = N.check(lib.b2_das_operand_bytes(M, nbins, mode), "b2_das_operand_bytes")
+    op = torch.empty(nbytes, dtype=torch.uint8, device=csm_dev.device)
+    N.check(lib.b2_das_prepare(N.ptr(csm_dev), M, nb, bin0, nbins, int(bool(remove_diag)), N.ptr(op), mode,
+                               N.stream_handle()), "b2_das_prepare")
+    return op
+
+
+def das_map(op, M: int, freqs: np.ndarray, weights: np.ndarray, c: float, mic_xyz: np.ndarray,
+            center_xyz: np.ndarray, grid_xyz, steering: int, clamp_negative: bool, mode: int,
+            per_bin: bool = False):
+    """Run K3 over all rows of `grid_xyz` ((G,3) numpy or CUDA float64 tensor).
+
+    Returns (map [G] float64 CUDA tensor, per-bin [G, F] tensor or None).
+    """
+    torch = _torch()
+    lib = N.lib()
+    device = op.device
+    nbins = len(freqs)
+    f_dev = torch.from_numpy(np.ascontiguousarray(freqs, dtype=np.float64)).to(device)
+    w_dev = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64)).to(device)
+    mic_dev = torch.from_numpy(np.ascontiguousarray(mic_xyz, dtype=np.float64)).to(device)
+    if isinstance(grid_xyz, torch.Tensor):
+        g_dev = grid_xyz.to(device=device, dtype=torch.float64).contiguous()
+    else:
+        g_dev = torch.from_numpy(np.ascontiguousarray(grid_xyz, dtype=np.float64)).to(device)
+    G = g_dev.shape[0]
+    out = torch.empty(G, dtype=torch.float64, device=device)
+    pb = torch.empty((G, nbins), dtype=torch.float64, device=device) if per_bin else None
+    N.check(lib.b2_das_map(N.ptr(op), M, nbins, N.ptr(f_dev), N.ptr(w_dev), float(c), N.ptr(mic_dev),
+                           N.vec3(center_xyz), N.ptr(g_dev), G, steering, int(bool(clamp_negative)),
+                           N.ptr(out), N.ptr(pb), mode, N.stream_handle()), "b2_das_map")
+    return out, pb
+
+
+def steering_vector(wave_numbers: np.ndarray, mic_xyz: np.ndarray, center_xyz: np.ndarray,
+                    grid_xyz: np.ndarray, steering: int):
+    """Dense complex128 (F, M, G) steering array on the device (small problems only)."""
+    torch = _torch()
+    device = torch.device("cuda", torch.cuda.current_device())
+    k_dev = torch.from_numpy(np.ascontiguousarray(wave_numbers, dtype=np.float64)).to(device)
+    mic_dev = torch.from_numpy(np.ascontiguousarray(mic_xyz, dtype=np.float64)).to(device)
+    g_dev = torch.from_numpy(np.ascontiguousarray(grid_xyz, dtype=np.float64)).to(device)
+    F, M, G = len(wave_numbers), mic_xyz.shape[0], grid_xyz.shape[0]
+    h = torch.empty((F, M, G), dtype=torch.complex128, device=device)
+    N.check(N.lib().b2_steering_vector(N.ptr(k_dev), F, N.ptr(mic_dev), M, N.vec3(center_xyz), N.ptr(g_dev), G,
+                                       steering, N.ptr(h), N.stream_handle()), "b2_steering_vector")
+    return h

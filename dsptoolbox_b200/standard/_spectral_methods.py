@@ -1,0 +1,118 @@
+"""Welch cross-spectra on the GPU behind the reference's private entry points.
+
+`_csm_welch` and `_welch` keep the signatures, return types and error behaviour of
+reference standard/_spectral_methods.py:285-371 and :10-173; the arithmetic runs in
+libb2dsp (K0/K1/K2/K2e, see engine.py).  Instead of one Welch call per channel pair, every
+channel is transformed once and each bin's cross-spectral matrix is one Hermitian rank-K
+update on the tensor cores.
+
+Not supported on the GPU path (raises NotImplementedError, there is no CPU fallback):
+average="median" (reference :153-162) and window lengths above 16384.
+"""
+
+from __future__ import annotations
+
+from warnings import warn
+
+import numpy as np
+from scipy.signal import check_COLA
+
+from .. import engine
+from .enums import SpectrumScaling, Window
+
+
+def _validate(window_length_samples, overlap_percent, average):
+    # same checks and messages as the reference (_spectral_methods.py:89-100)
+    valid_window_sizes = [int(2 ** p) for p in range(3, 19)]
+    assert window_length_samples in valid_window_sizes, (
+        "Window length should be a power of 2 between [8, 262_144] or [2**3, 2**18]")
+    assert overlap_percent >= 0 and overlap_percent < 100, "overlap_percent should be between 0 and 100"
+    assert average in ("mean", "median"), f"{average} is not valid. Use either mean or median"
+    if average == "median":
+        raise NotImplementedError(
+            "average='median' needs every per-frame cross-spectrum and is not part of the B200 path")
+
+
+def _window_and_step(window_type, window_length_samples, overlap_percent):
+    """Periodic scipy window, hop size and the COLA warning of the reference (:103-114)."""
+    spec = window_type.to_scipy_format() if isinstance(window_type, Window) else window_type
+    from scipy.signal.windows import get_window
+
+    window = get_window(spec, window_length_samples, fftbins=True)
+    overlap_samples = int(overlap_percent / 100 * window_length_samples)
+    step = window_length_samples - overlap_samples
+    if not check_COLA(window, nperseg=len(window), noverlap=overlap_samples):
+        warn("Selected window type and overlap do not meet the constant overlap and add constraint! "
+             "Results might be distorted")
+    return window, step
+
+
+def _scaling_terms(scaling: SpectrumScaling, window_length_samples: int, fs_hz: int, window):
+    """(fft_scale, factor, halve_edges, amplitude_sqrt) -- reference :141-148 and :164-171."""
+    factor = 1.0
+    halve = scaling.has_physical_units()
+    if halve:
+        factor = float(np.squeeze(scaling.get_scaling_factor(window_length_samples, fs_hz, window)))
+    return scaling.fft_scale(window_length_samples), factor, halve, scaling.is_amplitude_scaling()
+
+
+def csm_welch_device(time_data, sampling_rate_hz, window_length_samples, window_type, overlap_percent,
+                     detrend, average, scaling, frame_range=None, reduce_fn=None):
+    """Welch CSM left on the device: (f [numpy], csm [CUDA complex128 tensor (nb, M, M)]).
+
+    `frame_range` restricts this process to a shard of the Welch frames and `reduce_fn` (e.g. an
+    NCCL all-reduce, see dist.py) is applied to the partial sums before the non-linear
+    finalisation -- the frame-sharded multi-GPU form of the same computation.
+    """
+    _validate(window_length_samples, overlap_percent, average)
+    if not hasattr(time_data, "shape") or len(time_data.shape) != 2:
+        time_data = np.atleast_2d(np.asarray(time_data))
+    window, step = _window_and_step(window_type, window_length_samples, overlap_percent)
+    fft_scale, factor, halve, amp = _scaling_terms(scaling, window_length_samples, sampling_rate_hz, window)
+    S, n_frames = engine.csm_partial_sums(
+        time_data, int(time_data.shape[0]), window_length_samples, step, window, detrend, fft_scale,
+        frame_range=frame_range)
+    if reduce_fn is not None:
+        S = reduce_fn(S)
+    csm = engine.csm_finalize(S, n_frames, factor, halve, amp)
+    f = np.fft.rfftfreq(window_length_samples, 1 / sampling_rate_hz)
+    return f, csm
+
+
+def _csm_welch(time_data, sampling_rate_hz: int, window_length_samples: int, window_type,
+               overlap_percent, detrend: bool, average: str, scaling: SpectrumScaling):
+    """Cross-spectral matrix (frequency, channels, channels) with Welch's method.
+
+    Drop-in for reference _spectral_methods.py:285-371: returns host arrays
+    (f float64 [nb], csm complex128 [nb, M, M]).
+    """
+    f, csm = csm_welch_device(time_data, sampling_rate_hz, window_length_samples, window_type,
+                              overlap_percent, detrend, average, scaling)
+    return f, csm.cpu().numpy()
+
+
+def _welch(x, y, fs_hz: int, window_type, window_length_samples: int, overlap_percent: float,
+           detrend: bool, average: str, scaling: SpectrumScaling):
+    """Auto (y=None, real) or cross (complex) spectral density of 1-D or (time, channel) data.
+
+    Drop-in for reference _spectral_methods.py:10-173, evaluated as entries of a small CSM:
+    csd[:, c] = mean_k conj(X_c) Y_c is element [y_c, x_c] of the CSM of the stacked channels.
+    """
+    x = np.asarray(x).squeeze()
+    auto = y is None
+    if not auto:
+        y = np.asarray(y).squeeze()
+        assert x.shape == y.shape, "Shapes of data do not match"
+    assert x.ndim <= 2, f"{x.shape} are too many dimensions. Use flat arrays or 2D-Arrays instead"
+    flat = x.ndim == 1
+    xs = x[:, None] if flat else x
+    ch = xs.shape[1]
+    stacked = xs if auto else np.concatenate([xs, y[:, None] if flat else y], axis=1)
+    _, csm = csm_welch_device(stacked, fs_hz, window_length_samples, window_type, overlap_percent,
+                              detrend, average, scaling)
+    idx = np.arange(ch)
+    if auto:
+        out = csm[:, idx, idx].real.cpu().numpy()
+    else:
+        out = csm[:, idx + ch, idx].cpu().numpy()
+    return out[:, 0] if flat else out

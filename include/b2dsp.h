@@ -1,0 +1,138 @@
+/*
+ * b2dsp.h -- C ABI of the B200 (sm_100a) Welch-CSM + delay-and-sum-map path.
+ *
+ * The reference (nico-franco-gomez/dsptoolbox v0.8) is pure Python and has no FFI of its
+ * own: its boundary for this path is Python-object level.  Each entry point below therefore
+ * cites the reference *function* whose arithmetic it replaces (paths relative to
+ * /root/reference/dsptoolbox).  The Python host side in dsptoolbox_b200/ binds these with
+ * ctypes and mirrors the reference's classes (Signal, MicArray, Grid,
+ * BeamformerDASFrequency); INTEGRATION.md shows the monkey-patch a reference maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B2_E* code otherwise; it never throws,
+ *     never exits, and stores a human-readable message retrievable with b2_last_error()
+ *     (thread-local).
+ *   - all *_dev pointers are DEVICE pointers on the current CUDA device; the library does no
+ *     allocation and no synchronisation: kernels are enqueued on `stream` (a cudaStream_t
+ *     passed as void*, 0 = default stream) and the caller owns every buffer.
+ *   - precision: B2_F64 = strict (fp64 FFT, fp64 tensor-core DMMA accumulation);
+ *                B2_F32 = fast   (fp32 FFT, fp32 spectra).
+ *   - complex numbers are interleaved (re, im).
+ */
+#ifndef B2DSP_H
+#define B2DSP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_EINVAL (-1)     /* bad argument (shape, alignment, enum)            */
+#define B2_EUNSUPPORTED (-2) /* valid in the reference but outside the GPU path */
+#define B2_ECUDA (-3)      /* CUDA runtime / launch error                       */
+
+#define B2_F64 0
+#define B2_F32 1
+
+/* steering-vector formulations, beamforming/enums.py:4-18 */
+#define B2_STEER_CLASSIC 0
+#define B2_STEER_INVERSE 1
+#define B2_STEER_TRUE_POWER 2
+#define B2_STEER_TRUE_LOCATION 3
+
+/* map arithmetic */
+#define B2_MAP_SIMT_F64 0  /* fp64 CUDA-core kernel (strict checker-grade)                 */
+#define B2_MAP_SIMT_F32 1  /* fp32 CUDA-core kernel                                         */
+#define B2_MAP_TC_TF32 2   /* tcgen05 tensor cores, single-pass TF32, fp32 accumulate       */
+#define B2_MAP_TC_TF32X3 3 /* tcgen05 tensor cores, split-TF32 (3 products), fp32 accumulate */
+
+int b2_version(void);
+const char *b2_last_error(void);
+
+/* Number of Welch frames and zero-padding for a signal of L samples:
+ * helpers/other.py:181-213 (_compute_number_frames, zero_padding=True):
+ * frames = ceil(L/step), pad = wl - L % step. */
+int b2_welch_frames(int64_t L, int wl, int step, int64_t *frames, int64_t *pad);
+
+/* Frames-per-CTA granularity of b2_welch_rfft for (wl, precision); the frame capacity Kp
+ * of the spectra buffer must be a multiple of max(16, this). */
+int b2_welch_frame_tile(int wl, int precision);
+
+/* Fill the length-wl twiddle table exp(-2*pi*i*t/wl), t = 0..wl-1, in the precision's
+ * complex type (replaces pocketfft's plan inside np.fft.rfft, _spectral_methods.py:142). */
+int b2_fft_twiddles(int wl, int precision, void *twiddle_dev, void *stream);
+
+/* K0: gather the caller's (L, M) recording (any strides, float32 or float64) into the
+ * channel-major, zero-padded device layout the FFT kernel reads:
+ *   out[m][t] = x[(t0+t)*stride_t + m*stride_m]  for t < nt, 0 for nt <= t < Lp.
+ * Replaces the zero-padding of helpers/other.py:216-259 (_pad_trim) and the float64 upcast
+ * of _framed_signal_representation.py:57-59.  in_dtype: B2_F64 / B2_F32; strides in elements. */
+int b2_prepare_channels(const void *x_dev, int in_dtype, int64_t stride_t, int64_t stride_m,
+                        int64_t t0, int64_t nt, int M, void *out_dev, int64_t Lp,
+                        int precision, void *stream);
+
+/* K1: framing + window + (optional) mean removal + real FFT, all frames of all channels.
+ * Replaces _get_framed_signal (_framed_signal_representation.py:50-65) and the
+ * window / detrend / np.fft.rfft lines of _welch (_spectral_methods.py:126-148).
+ *   xc_dev      (M, Lp) channel-major samples from b2_prepare_channels, Lp >= (Kp-1)*step+wl
+ *   window_dev  wl window values in the precision's real type
+ *   fft_scale   1, 1/wl or 1/sqrt(wl): the rfft norm of enums.py:53-75
+ *   X_out_dev   spectra [wl/2+1][M][Kp] complex (k contiguous); frames >= nframes are
+ *               written as zeros so the rank-K update may run over whole tiles. */
+int b2_welch_rfft(const void *xc_dev, int64_t Lp, int M, int wl, int step, int64_t nframes,
+                  const void *window_dev, const void *twiddle_dev, int detrend,
+                  double fft_scale, void *X_out_dev, int64_t Kp, int precision, void *stream);
+
+/* K2: per-bin Hermitian rank-K accumulation S_f (+)= X_f X_f^H, lower block triangle.
+ * Replaces the M(M+1)/2 `_welch` calls of _csm_welch (_spectral_methods.py:351-369) and the
+ * frame sum of np.mean (:152); the division by the frame count happens in b2_csm_finalize
+ * so partial sums of frame shards can be all-reduced first.
+ *   X_dev   [nb][M][Kp] complex spectra (precision's complex type)
+ *   S_dev   [nb][M][M] complex128 sums; entries with row >= col are valid on return
+ *   accumulate  0: overwrite, 1: add to the existing sums */
+int b2_csm_herk(const void *X_dev, int M, int64_t Kp, int nb, void *S_dev, int accumulate,
+                int precision, void *stream);
+
+/* K2e: averaging, physical scaling, DC/Nyquist halving, element-wise principal complex
+ * sqrt, Hermitian mirroring.  Replaces _welch (_spectral_methods.py:152,164-171) and
+ * _csm_welch (:355-369).  csm_out_dev: [nb][M][M] complex128, fully populated. */
+int b2_csm_finalize(const void *S_dev, int M, int nb, double inv_frames, double factor,
+                    int halve_edges, int amplitude_sqrt, void *csm_out_dev, void *stream);
+
+/* K3a: operand preparation for the map: diagonal removal + M/(M-1) gain
+ * (beamforming/beamforming.py:841-845), bin selection (:853-855) and the split of the
+ * Hermitian matrix into L = strict lower triangle + diag/2 so that h^H C h = 2 Re(h^H L h).
+ *   csm_dev   [nb][M][M] complex128;  bins [bin0, bin0+nbins)
+ *   op_dev    operand buffer of b2_das_operand_bytes(M, nbins, mode) bytes */
+int64_t b2_das_operand_bytes(int M, int nbins, int mode);
+int b2_das_prepare(const void *csm_dev, int M, int nb, int bin0, int nbins, int remove_diag,
+                   void *op_dev, int mode, void *stream);
+
+/* K3: delay-and-sum map of grid points [0, G): steering vectors synthesised on the fly
+ * (beamforming.py:1515-1703), P[g,f] = Re(h^H C_f h) (:863-868), clamp at 0 when
+ * clamp_negative (:871-872), weighted sum over the bins with `weights` = Simpson weights
+ * (:875-876) or {1.0} for a single bin (:878).
+ *   grid_xyz_dev  (G, 3) float64     mic_xyz_dev (M, 3) float64
+ *   center_xyz    reference mic (beamforming.py:517-541), host pointer to 3 doubles
+ *   freqs_dev     nbins float64 bin frequencies in Hz
+ *   weights_dev   nbins float64
+ *   map_out_dev   G float64
+ *   per_bin_out_dev  optional (G, nbins) float64 of the clamped per-bin powers, or NULL */
+int b2_das_map(const void *op_dev, int M, int nbins, const void *freqs_dev,
+               const void *weights_dev, double c, const void *mic_xyz_dev,
+               const double *center_xyz, const void *grid_xyz_dev, int64_t G, int steering,
+               int clamp_negative, void *map_out_dev, void *per_bin_out_dev, int mode,
+               void *stream);
+
+/* Steering vectors materialised like the reference's SteeringVector.get_vector
+ * (beamforming.py:1515-1703): h_out_dev complex128 [nbins][M][G].  Small problems only. */
+int b2_steering_vector(const void *wave_numbers_dev, int nbins, const void *mic_xyz_dev, int M,
+                       const double *center_xyz, const void *grid_xyz_dev, int64_t G,
+                       int steering, void *h_out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2DSP_H */

@@ -1,0 +1,179 @@
+"""Stage 2 parity: steering vectors and BeamformerDASFrequency.get_beamformer_map on the GPU.
+Tolerance (north star): within 1e-4 of the map maximum and 0.01 dB (top 20 dB), see parity.py."""
+
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import dsptoolbox_b200 as dsp  # noqa: E402
+from dsptoolbox_b200 import engine, synth  # noqa: E402
+from oracle import restatement as R  # noqa: E402
+from parity import assert_map_close  # noqa: E402
+
+BF = dsp.beamforming
+MODES = ["simt_f64", "simt_f32"] + (["tf32x3", "tf32"] if engine.tc_map_available() else [])
+
+
+def quiet_map(bf, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()) as buf:
+        m = bf.get_beamformer_map(*a, **k)
+    return m, buf.getvalue()
+
+
+@pytest.fixture(autouse=True)
+def _reset():
+    engine.config.map_mode = "auto"
+    engine.config.csm_precision = "fp64"
+    yield
+    engine.config.map_mode = "auto"
+
+
+def test_steering_vector_known_answer():
+    """Mirror of reference tests/test_beamforming.py:58-101 (triple-loop re-derivation)."""
+    xs = np.arange(0, 1.1, 0.25)
+    xx, yy, zz = np.meshgrid(xs, xs, xs, indexing="ij")
+    ma = BF.MicArray(dict(x=xx.flatten(), y=yy.flatten(), z=zz.flatten()))
+    g = BF.Regular2DGrid(np.arange(-0.5, 0.5, 0.1), np.arange(-0.5, 0.5, 0.1), ["x", "y"], value3=1)
+    r0 = ma.array_center_coordinates
+    k = np.array([1000, 1200]) * np.pi * 2 / 343
+    N = ma.number_of_points
+    gc, mc = g.coordinates, ma.coordinates
+    h = np.zeros((len(k), N, g.number_of_points), dtype=np.complex128)
+    for i0, kn in enumerate(k):
+        for i1 in range(N):
+            for i2 in range(g.number_of_points):
+                rti = np.sqrt(np.sum((gc[i2] - mc[i1]) ** 2))
+                rt0 = np.sqrt(np.sum((gc[i2] - r0) ** 2))
+                h[i0, i1, i2] = 1 / N * np.exp(-1j * kn * (rti - rt0))
+    h_intern = BF.SteeringVector(formulation=BF.SteeringVectorType.Classic).get_vector(k, g, ma)
+    assert h_intern.shape == h.shape and h_intern.dtype == np.complex128
+    assert np.all(np.isclose(h_intern, h))
+    for t in BF.SteeringVectorType:
+        hv = BF.SteeringVector(t).get_vector(k, g, ma)
+        assert np.allclose(hv, R.steering_vector(k, gc, mc, t.name), rtol=1e-11, atol=1e-15)
+
+
+def _golden_setup(g):
+    pos = dict(x=g["mic_x"], y=g["mic_y"], z=g["mic_z"])
+    sig = dsp.Signal(None, g["x"].copy(), int(g["fs"]), activate_cache=True)
+    sig.set_spectrum_parameters(window_length_samples=int(g["wl"]))
+    return sig, BF.MicArray(pos)
+
+
+CASES = [(2000.0, 3, True, "third_rd"), (2000.0, 3, False, "third_full"), (3000.0, 0, True, "single_rd"),
+         (1500.0, 1, True, "octave_rd"), (2500.0, 12, False, "twelfth_full")]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("form", ["Classic", "Inverse", "TruePower", "TrueLocation"])
+def test_golden_small_maps(golden_dir, mode, form):
+    g = np.load(os.path.join(golden_dir, "das_small.npz"))
+    sig, ma = _golden_setup(g)
+    grid = BF.Regular2DGrid(g["line1"], g["line2"], ("x", "y"), float(g["value3"]))
+    engine.config.map_mode = mode
+    bf = BF.BeamformerDASFrequency(sig, ma, grid, BF.SteeringVector(getattr(BF.SteeringVectorType, form)))
+    for fc, frac, rd, tag in CASES:
+        m, out = quiet_map(bf, fc, frac, rd)
+        ref = g[f"map_{form}_{tag}"]
+        assert m.dtype == np.float64
+        rel = 1e-4 if mode != "simt_f64" else 1e-9
+        assert_map_close(m, ref, rel=rel)
+        assert np.allclose(bf.f_range_hz, g[f"frange_{form}_{tag}"])
+        assert "...csm..." in out and "...Apply..." in out          # same banner as the reference
+        assert np.array_equal(bf.map, m) and bf.map is not m
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_golden_other_grids(golden_dir, mode):
+    g = np.load(os.path.join(golden_dir, "das_small.npz"))
+    sig, ma = _golden_setup(g)
+    engine.config.map_mode = mode
+    g3 = BF.Regular3DGrid(np.linspace(-0.2, 0.2, 4), np.linspace(-0.2, 0.2, 3), np.linspace(0.6, 1.0, 5))
+    m3, _ = quiet_map(BF.BeamformerDASFrequency(sig, ma, g3, BF.SteeringVector()), 2000.0, 3, True)
+    assert m3.shape == (4, 3, 5)
+    assert_map_close(m3, g["map3d"])
+    gl = BF.LineGrid(np.linspace(-0.5, 0.5, 11), "y", 0.8, 0.1)
+    assert np.allclose(gl.coordinates, g["mapline_coords"])
+    ml, _ = quiet_map(BF.BeamformerDASFrequency(sig, ma, gl, BF.SteeringVector()), 2000.0, 3, True)
+    assert_map_close(ml, g["mapline"])
+    plain = BF.Grid(dict(x=g3.coordinates[:, 0], y=g3.coordinates[:, 1], z=g3.coordinates[:, 2]))
+    mp, _ = quiet_map(BF.BeamformerDASFrequency(sig, ma, plain, BF.SteeringVector()), 2000.0, 3, True)
+    assert mp.shape == (60,) and np.array_equal(mp, m3.ravel())
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_config1_golden_map(golden_dir, mode):
+    """BASELINE.json configs[0] end to end through the drop-in API."""
+    g = np.load(os.path.join(golden_dir, "cfg1.npz"))
+    arr = np.load(os.path.join(golden_dir, "array_xml_positions.npz"))
+    pos = dict(x=arr["x"], y=arr["y"], z=arr["z"])
+    fs = int(g["fs"])
+    x = synth.point_source_recording(synth.positions_to_xyz(pos), fs, fs, noise_sigma=float(g["noise_sigma"]), seed=int(g["seed"]))
+    sig = dsp.Signal(None, x, fs)
+    l = np.linspace(-0.5, 0.5, 50)
+    engine.config.map_mode = mode
+    bf = BF.BeamformerDASFrequency(sig, BF.MicArray(pos), BF.Regular2DGrid(l, l, ("x", "y"), 1.0), BF.SteeringVector())
+    m, _ = quiet_map(bf, 4000.0, 3, True)
+    e = assert_map_close(m, g["map"])
+    assert np.unravel_index(np.argmax(m), m.shape) == (29, 15)
+    assert np.allclose(bf.f_range_hz, g["f_range"])
+    print(mode, e)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("M,G,wl,fc,frac", [(5, 37, 128, 1500.0, 1), (33, 130, 256, 3000.0, 3), (64, 257, 256, 2000.0, 2),
+                                           (100, 64, 128, 2500.0, 6), (125, 40, 64, 2000.0, 0)])
+def test_against_oracle_ragged(mode, M, G, wl, fc, frac):
+    """Mic counts off the 32-padding, grid sizes off the tile, odd/even bin counts, single bin.
+    (125 mics / octave_fraction 0 is the shape of reference tests/test_beamforming.py:130-191.)"""
+    rng = np.random.default_rng(M + G)
+    pos = dict(x=rng.uniform(-0.5, 0.5, M), y=rng.uniform(-0.5, 0.5, M), z=rng.uniform(-0.02, 0.02, M))
+    mic = synth.positions_to_xyz(pos)
+    fs = 16000
+    x = synth.point_source_recording(mic, 6000, fs, source_xyz=(0.1, 0.1, 0.9), noise_sigma=0.3, seed=M)
+    gp = dict(x=rng.uniform(-0.6, 0.6, G), y=rng.uniform(-0.6, 0.6, G), z=rng.uniform(0.7, 1.1, G))
+    sig = dsp.Signal(None, x, fs).set_spectrum_parameters(window_length_samples=wl)
+    engine.config.map_mode = mode
+    grid = BF.Grid(gp)
+    for form in (BF.SteeringVectorType.TrueLocation, BF.SteeringVectorType.TruePower):
+        for rd in (True, False):
+            bf = BF.BeamformerDASFrequency(sig, BF.MicArray(pos), grid, BF.SteeringVector(form), c=340.0)
+            m, _ = quiet_map(bf, fc, frac, rd)
+            fo, co = R.csm_welch(x, fs, wl, "hann", 50, True, "fftbackward")
+            mo = R.das_map(fo, co, mic, grid.coordinates, fc, frac, rd, 340.0, form.name)
+            assert_map_close(m, mo)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_per_bin_powers_and_linearity(mode):
+    rng = np.random.default_rng(3)
+    M, G = 24, 96
+    pos = dict(x=rng.uniform(-0.5, 0.5, M), y=rng.uniform(-0.5, 0.5, M), z=np.zeros(M))
+    mic = synth.positions_to_xyz(pos)
+    x = synth.point_source_recording(mic, 8000, 16000, source_xyz=(0.0, 0.2, 1.0), noise_sigma=0.2, seed=3)
+    sig = dsp.Signal(None, x, 16000, activate_cache=True).set_spectrum_parameters(window_length_samples=256)
+    grid = BF.Grid(dict(x=rng.uniform(-0.6, 0.6, G), y=rng.uniform(-0.6, 0.6, G), z=np.full(G, 1.0)))
+    engine.config.map_mode = mode
+    bf = BF.BeamformerDASFrequency(sig, BF.MicArray(pos), grid, BF.SteeringVector())
+    f, csm = sig.get_csm_device()
+    with contextlib.redirect_stdout(io.StringIO()):
+        bf.f_range_hz = np.array([1800.0, 2600.0])
+        flat = bf._map_from_device_csm(f, csm, True, per_bin=True)
+        pb = bf._per_bin_device.cpu().numpy()
+        flat2 = bf._map_from_device_csm(f, 3.0 * csm, True)
+    fo, co = R.csm_welch(x, 16000, 256, "hann", 50, True, "fftbackward")
+    id1, id2 = bf._select_bins(fo)
+    k = fo[id1:id2] * 2 * np.pi / 343
+    C = R._prepare_csm(co, M, True)[id1:id2]
+    h = R.steering_vector(k, grid.coordinates, mic)
+    P = np.einsum("fmg,fmn,fng->gf", h.conj(), C, h).real
+    P[P < 0] = 0
+    assert np.max(np.abs(pb - P)) <= 1e-4 * P.max()
+    assert np.allclose(flat2, 3.0 * flat, rtol=1e-5, atol=1e-6 * flat.max())          # linear in the CSM
+    assert np.all(flat >= 0)                                                          # clamped

@@ -1,0 +1,91 @@
+"""The oracle (numpy restatement) against the golden vectors produced by the REAL reference
+(oracle/make_golden.py).  CPU only."""
+
+import os
+
+import numpy as np
+import pytest
+
+from dsptoolbox_b200 import synth
+from oracle import restatement as R
+
+SCALINGS = ["AmplitudeSpectrum", "AmplitudeSpectralDensity", "PowerSpectrum", "PowerSpectralDensity",
+            "FFTBackward", "FFTForward", "FFTOrthogonal"]
+
+
+def rel_to_max(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+@pytest.mark.parametrize("scaling", SCALINGS)
+def test_csm_all_scalings(golden_dir, scaling):
+    g = np.load(os.path.join(golden_dir, "csm_small_scalings.npz"))
+    f, c = R.csm_welch(g["x"], int(g["fs"]), int(g["wl"]), "hann", 50, True, scaling)
+    assert np.array_equal(f, g["f"])
+    assert rel_to_max(c, g["csm_" + scaling]) < 1e-13
+    _, cp = R.csm_welch_pairwise(g["x"], int(g["fs"]), int(g["wl"]), "hann", 50, True, scaling)
+    assert rel_to_max(cp, g["csm_" + scaling]) < 1e-13
+
+
+VARIANTS = [("ov75_hamming", 64, 75, True, "hamming"), ("ov0_boxcar_nodetrend", 256, 0, False, "boxcar"),
+            ("ov33_blackman_Lmultiple", 128, 33, True, "blackman"), ("ov50_kaiser8_wl8", 8, 50, True, ("kaiser", 8.0)),
+            ("ov90_flattop_short", 512, 90, True, "flattop")]
+
+
+@pytest.mark.parametrize("tag,wl,ov,detrend,window", VARIANTS)
+def test_csm_variants(golden_dir, tag, wl, ov, detrend, window):
+    g = np.load(os.path.join(golden_dir, "csm_variants.npz"))
+    _, c = R.csm_welch(g["x_" + tag], int(g["fs"]), wl, window, ov, detrend, "PowerSpectralDensity")
+    assert rel_to_max(c, g["csm_" + tag]) < 1e-13
+
+
+MAP_CASES = [(2000.0, 3, True, "third_rd"), (2000.0, 3, False, "third_full"), (3000.0, 0, True, "single_rd"),
+             (1500.0, 1, True, "octave_rd"), (2500.0, 12, False, "twelfth_full")]
+
+
+@pytest.mark.parametrize("form", ["Classic", "Inverse", "TruePower", "TrueLocation"])
+@pytest.mark.parametrize("fc,frac,rd,tag", MAP_CASES)
+def test_das_small(golden_dir, form, fc, frac, rd, tag):
+    g = np.load(os.path.join(golden_dir, "das_small.npz"))
+    mic = np.stack([g["mic_x"], g["mic_y"], g["mic_z"]], axis=1)
+    a, b = np.meshgrid(g["line1"], g["line2"], indexing="ij")
+    grid = np.stack([a.ravel(), b.ravel(), np.full(a.size, float(g["value3"]))], axis=1)
+    f, c = R.csm_welch(g["x"], int(g["fs"]), int(g["wl"]), "hann", 50, True, "fftbackward")
+    ref = g[f"map_{form}_{tag}"]
+    m = R.das_map(f, c, mic, grid, fc, frac, rd, 343.0, form).reshape(ref.shape)
+    assert rel_to_max(m, ref) < 1e-12
+    ml = R.das_map_loop(f, c, mic, grid, fc, frac, rd, 343.0, form, grid_subset=np.arange(0, 63, 7))
+    assert rel_to_max(ml, ref.ravel()[::7]) < 1e-12
+    id1, id2 = R.band_bins(f, fc, frac)
+    assert np.allclose(g[f"frange_{form}_{tag}"], [f[id1], f[id2 - 1]])
+
+
+def test_config1(golden_dir):
+    """BASELINE.json configs[0]: array.xml geometry, 1 s @ 48 kHz, nfft 1024, 50x50 grid, 4 kHz third octave."""
+    g = np.load(os.path.join(golden_dir, "cfg1.npz"))
+    arr = np.load(os.path.join(golden_dir, "array_xml_positions.npz"))
+    mic = synth.positions_to_xyz(arr)
+    fs = int(g["fs"])
+    x = synth.point_source_recording(mic, fs, fs, noise_sigma=float(g["noise_sigma"]), seed=int(g["seed"]))
+    fp = np.array([x.sum(), np.abs(x).sum(), x[12345, 7], x[-1, -1]])
+    assert np.allclose(fp, g["x_fingerprint"], rtol=1e-12), "synthetic input is not reproducible on this numpy"
+    f, c = R.csm_welch(x, fs, int(g["wl"]), "hann", 50, True, "fftbackward")
+    idx = g["csm_idx"]
+    got = c[idx[:, 0], idx[:, 1], idx[:, 2]]
+    assert np.max(np.abs(got - g["csm_vals"]) / np.abs(g["csm_vals"])) < 1e-9
+    assert rel_to_max(c[g["csm_bins"]], g["csm_full_bins"]) < 1e-13
+    l = np.linspace(-0.5, 0.5, 50)
+    a, b = np.meshgrid(l, l, indexing="ij")
+    grid = np.stack([a.ravel(), b.ravel(), np.ones(a.size)], axis=1)
+    m = R.das_map(f, c, mic, grid, 4000.0, 3, True).reshape(50, 50)
+    assert rel_to_max(m, g["map"]) < 1e-12
+    assert np.unravel_index(np.argmax(m), m.shape) == (29, 15)       # grid node nearest (0.1, -0.2)
+
+
+def test_simpson_weights_match_scipy():
+    from scipy.integrate import simpson
+
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 4, 7, 20, 21):
+        y = rng.standard_normal((5, n))
+        assert np.allclose(y @ R.simpson_weights(n, 0.3), simpson(y, dx=0.3, axis=1), rtol=1e-13)
