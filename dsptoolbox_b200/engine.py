@@ -101,7 +101,7 @@ def _as_device_block(x, t0: int, t1: int, device):
         if xs.device.type != "cuda":
             xs = xs.to(device, non_blocking=True)
         code = N.F64 if xs.dtype == torch.float64 else N.F32
-        return xs, code, xs.stride(0), xs.stride(1)
+        return xs, code, max(1, xs.stride(0)), max(1, xs.stride(1))
     x = np.asarray(x)
     if x.dtype not in (np.float32, np.float64):
         x = x.astype(np.float64)          # the reference upcasts when framing
@@ -109,12 +109,12 @@ def _as_device_block(x, t0: int, t1: int, device):
     xs = x[t0:t1]
     if xs.flags.c_contiguous:
         t = torch.from_numpy(xs).to(device, non_blocking=True)
-        return t, code, t.stride(0), t.stride(1)
+        return t, code, xs.shape[1], 1
     if xs.T.flags.c_contiguous:          # (channels, time) storage seen through Signal's transpose
         t = torch.from_numpy(xs.T).to(device, non_blocking=True)
-        return t, code, t.stride(1), t.stride(0)
+        return t, code, 1, xs.shape[0]
     t = torch.from_numpy(np.ascontiguousarray(xs)).to(device, non_blocking=True)
-    return t, code, t.stride(0), t.stride(1)
+    return t, code, xs.shape[1], 1
 
 
 class _Timer:
