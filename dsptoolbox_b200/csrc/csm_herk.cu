@@ -10,7 +10,7 @@
 // The complex product is mapped onto real DMMAs:
 //   Sr += Ar*Br^T + Ai*Bi^T          Si += Ai*Br^T + Ar*(-Bi)^T
 // Frames are streamed in chunks of 16 through a cp.async double buffer; the spectra layout
-// [bin][channel][frame] makes every tile row one contiguous run.
+// [frame chunk][bin][channel][16 frames] makes every 64-row tile one contiguous 16 KB run.
 #include "common.cuh"
 
 namespace {
@@ -51,10 +51,11 @@ template <> __device__ __forceinline__ double2 load_frag<float>(const unsigned c
 }
 
 // Issue the cp.async copies of one 64-row x KC-frame tile (rows >= M are left untouched: they
-// were zeroed once before the main loop).
+// were zeroed once before the main loop).  Xc points at [chunk][bin] of the chunk-major spectra
+// layout, i.e. at an (M x 16) row-major block whose rows are 16 consecutive frames.
 template <typename TIN>
-__device__ __forceinline__ void load_tile(unsigned char *dst, const cx<TIN> *__restrict__ Xf, int row0,
-                                          int M, int64_t Kp, int64_t kbase, int tid) {
+__device__ __forceinline__ void load_tile(unsigned char *dst, const cx<TIN> *__restrict__ Xc, int row0,
+                                          int M, int tid) {
     using SM = HerkSmem<TIN>;
     constexpr int SEG_PER_ROW = KC * SM::ELEM / 16;        // 16-byte segments per row
     constexpr int TOTAL = BM * SEG_PER_ROW;
@@ -63,7 +64,7 @@ __device__ __forceinline__ void load_tile(unsigned char *dst, const cx<TIN> *__r
         int r = s / SEG_PER_ROW, seg = s - r * SEG_PER_ROW;
         int row = row0 + r;
         if (row < M) {
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(Xf + int64_t(row) * Kp + kbase) + seg * 16;
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(Xc + int64_t(row) * KC) + seg * 16;
             cp_async16(dst + r * SM::PITCH + seg * 16, src);
         }
     }
@@ -71,7 +72,7 @@ __device__ __forceinline__ void load_tile(unsigned char *dst, const cx<TIN> *__r
 
 template <typename TIN>
 __global__ void __launch_bounds__(HERK_THREADS)
-herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, double2 *__restrict__ S, int accumulate) {
+herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, double2 *__restrict__ S, int accumulate) {
     using SM = HerkSmem<TIN>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -86,7 +87,8 @@ herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, double2 *__re
     const bool diag = (bi == bj);
     const int f = blockIdx.y;
     const int rowA0 = bj * BM, rowB0 = bi * BM;
-    const cx<TIN> *Xf = X + int64_t(f) * M * Kp;
+    const cx<TIN> *Xf = X + int64_t(f) * M * KC;          // chunk 0 of this bin
+    const int64_t chunk_stride = int64_t(nb) * M * KC;   // elements between frame chunks
 
     unsigned char *As[2] = {smem, smem + 2 * SM::TILE};
     unsigned char *Bs[2] = {diag ? As[0] : smem + SM::TILE, diag ? As[1] : smem + 3 * SM::TILE};
@@ -102,16 +104,17 @@ herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, double2 *__re
         for (int b = 0; b < 4; ++b) { sr[a][b][0] = sr[a][b][1] = 0.0; si[a][b][0] = si[a][b][1] = 0.0; }
 
     const int nchunks = int(Kp / KC);
-    load_tile<TIN>(As[0], Xf, rowA0, M, Kp, 0, tid);
-    if (!diag) load_tile<TIN>(Bs[0], Xf, rowB0, M, Kp, 0, tid);
+    load_tile<TIN>(As[0], Xf, rowA0, M, tid);
+    if (!diag) load_tile<TIN>(Bs[0], Xf, rowB0, M, tid);
     cp_async_commit();
 
     const int frow = lane >> 2, fk = lane & 3;
     for (int c = 0; c < nchunks; ++c) {
         const int st = c & 1;
         if (c + 1 < nchunks) {
-            load_tile<TIN>(As[st ^ 1], Xf, rowA0, M, Kp, int64_t(c + 1) * KC, tid);
-            if (!diag) load_tile<TIN>(Bs[st ^ 1], Xf, rowB0, M, Kp, int64_t(c + 1) * KC, tid);
+            const cx<TIN> *Xn = Xf + int64_t(c + 1) * chunk_stride;
+            load_tile<TIN>(As[st ^ 1], Xn, rowA0, M, tid);
+            if (!diag) load_tile<TIN>(Bs[st ^ 1], Xn, rowB0, M, tid);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -189,7 +192,6 @@ csm_finalize_kernel(const double2 *__restrict__ S, int M, int nb, double inv_fra
     const int ti = p - tj * (tj + 1) / 2;
     const int f = blockIdx.y;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    double scale = inv_frames * factor;
     const bool edge = halve_edges && (f == 0 || f == nb - 1);
     const double2 *Sf = S + int64_t(f) * M * M;
     double2 *of = out + int64_t(f) * M * M;
@@ -209,7 +211,6 @@ csm_finalize_kernel(const double2 *__restrict__ S, int M, int nb, double inv_fra
         }
         tile[ty + r][tx] = v;
     }
-    (void)scale;
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 32; r += 8) {
@@ -233,7 +234,7 @@ int launch_herk(const void *X, int M, int64_t Kp, int nb, void *S, int accumulat
     }
     const int nbk = (M + BM - 1) / BM;
     dim3 grid((unsigned)(nbk * (nbk + 1) / 2), (unsigned)nb);
-    kern<<<grid, HERK_THREADS, SM::BYTES, st>>>((const cx<TIN> *)X, M, Kp, (double2 *)S, accumulate);
+    kern<<<grid, HERK_THREADS, SM::BYTES, st>>>((const cx<TIN> *)X, M, Kp, nb, (double2 *)S, accumulate);
     B2_LAUNCH_OK("b2_csm_herk");
     return B2_OK;
 }

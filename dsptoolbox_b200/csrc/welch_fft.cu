@@ -9,8 +9,8 @@
 // way into shared memory, packed as wl/2 complex points (z[n] = y[2n] + i*y[2n+1]), and
 // transformed by an in-place shared-memory Stockham FFT (radix 8/4/2, register-staged,
 // autosorting).  The real-FFT untangling is fused into the store, which writes, for every
-// bin, the FR frames as one contiguous run of the [bin][channel][frame] spectra layout that
-// the rank-K kernel consumes without transposition.
+// bin, the FR frames as one contiguous run of the [frame chunk][bin][channel][16 frames] spectra
+// layout that the rank-K kernel consumes without transposition.
 #include "common.cuh"
 
 namespace {
@@ -132,8 +132,9 @@ welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframe
     __shared__ T frame_mean;
 
     const int tid = threadIdx.x;
-    const int m = blockIdx.y;
-    const int64_t k0 = int64_t(blockIdx.x) * FR;
+    const int m = blockIdx.x;                               // channel fastest: neighbours share a frame chunk
+    const int64_t k0 = int64_t(blockIdx.y) * FR;
+    const int64_t nb = NC + 1;
     const T *xrow = xc + int64_t(m) * Lp;
 
     // ---- load + window (frames beyond nframes are all-zero) ----
@@ -198,7 +199,11 @@ welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframe
         C sum = cadd(a, b), dif = cmul(w, csub(a, b));
         // X = 0.5*(a+b) - 0.5*i*w*(a-b)
         C out = mk<T>((sum.x + dif.y) * half, (sum.y - dif.x) * half);
-        X[(int64_t(kf) * M + m) * Kp + (k0 + fr)] = out;
+        // spectra layout [frame chunk of 16][bin][channel][16 frames]: all CTAs of one frame chunk
+        // write inside one (nb * M * 16)-element window, and the rank-K kernel reads whole tiles
+        // of it as contiguous runs
+        const int64_t k = k0 + fr;
+        X[(((k >> 4) * nb + kf) * M + m) * 16 + (k & 15)] = out;
     }
 }
 
@@ -279,7 +284,8 @@ int launch_rfft(const void *xc, int64_t Lp, int M, int step, int64_t nframes, co
     B2_REQUIRE(Kp % G::FR == 0, B2_EINVAL, "b2_welch_rfft: Kp=%lld must be a multiple of %d", (long long)Kp, G::FR);
     int vec_ok = (step % 2 == 0) && (Lp % 2 == 0) && (reinterpret_cast<uintptr_t>(xc) % (2 * sizeof(T)) == 0) &&
                  (reinterpret_cast<uintptr_t>(window) % (2 * sizeof(T)) == 0);
-    dim3 grid((unsigned)(Kp / G::FR), (unsigned)M);
+    B2_REQUIRE(Kp % 16 == 0 && Kp / G::FR <= 65535, B2_EINVAL, "b2_welch_rfft: Kp=%lld must be a multiple of 16 (and at most %d)", (long long)Kp, 65535 * G::FR);
+    dim3 grid((unsigned)M, (unsigned)(Kp / G::FR));
     kern<<<grid, G::NT, G::SMEM, st>>>((const T *)xc, Lp, step, nframes, (const T *)window,
                                       (const cx<T> *)tw, detrend, T(scale), (cx<T> *)X, M, Kp, vec_ok);
     B2_LAUNCH_OK("b2_welch_rfft");

@@ -1,0 +1,131 @@
+"""One-process-per-GPU sharding of the two stages (torch.distributed; NCCL on the B200 box,
+gloo in the CPU tests).
+
+Stage 1 -- Welch frames are sharded: rank r owns the contiguous frame range
+`frame_shard(K, r, R)`, reads only the samples those frames touch (a halo of wl - step samples
+overlaps the neighbour), accumulates the UN-normalised sums S_f^(r), and ONE all-reduce(sum)
+over NVLink gives every rank the full sum.  The non-linear finalisation (mean, scaling,
+element-wise sqrt, mirroring) runs after the reduction on every rank, so all ranks hold the
+full CSM for stage 2.
+Stage 2 -- grid points are sharded (`grid_shard`); the only communication is the final
+all-gather of G floats.
+
+The reference has no distributed path; results are identical to the
+single-GPU path up to the summation order of the frame sums.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .beamforming.beamforming import BeamformerDASFrequency
+
+
+# --------------------------------------------------------------------------- index math
+def split_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced [begin, end) share of range(n) for `rank` (first n % world ranks get one more)."""
+    assert 0 <= rank < world
+    base, extra = divmod(n, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def frame_shard(n_frames: int, rank: int, world: int) -> tuple[int, int]:
+    return split_range(n_frames, rank, world)
+
+
+def grid_shard(n_points: int, rank: int, world: int) -> tuple[int, int]:
+    return split_range(n_points, rank, world)
+
+
+def shard_sample_range(frames: tuple[int, int], step: int, wl: int, length: int) -> tuple[int, int]:
+    """Samples [t0, t1) of the recording that the frames [k0, k1) read; the tail beyond
+    `length` is the reference's zero padding (helpers/other.py:207-209) and is not stored."""
+    k0, k1 = frames
+    if k1 <= k0:
+        return 0, 0
+    return k0 * step, min(length, (k1 - 1) * step + wl)
+
+
+# --------------------------------------------------------------------------- collectives
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def world() -> tuple[int, int]:
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def allreduce_sum_(t):
+    """In-place sum over ranks of a real or complex tensor (complex goes as interleaved reals)."""
+    import torch
+
+    dist = _dist()
+    if world()[1] == 1:
+        return t
+    dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def allgather_rows(local, counts: list[int]):
+    """Concatenate per-rank 1-D tensors of (possibly unequal) lengths `counts` on every rank."""
+    import torch
+
+    dist = _dist()
+    if world()[1] == 1:
+        return local
+    nmax = max(counts)
+    padded = torch.zeros(nmax, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    parts = [torch.empty_like(padded) for _ in counts]
+    dist.all_gather(parts, padded)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+
+
+# --------------------------------------------------------------------------- front-ends
+def get_csm_device_sharded(signal):
+    """Frame-sharded `Signal.get_csm_device()`: every rank returns the full (f, csm)."""
+    from . import engine
+
+    rank, nranks = world()
+    p = signal._spectrum_parameters
+    wl = p["window_length_samples"]
+    step = wl - int(p["overlap_percent"] / 100 * wl)
+    k_total, _ = engine.welch_frames(signal.length_samples, wl, step)
+    return signal._compute_csm_device(frame_range=frame_shard(k_total, rank, nranks), reduce_fn=allreduce_sum_)
+
+
+class DistributedBeamformerDASFrequency(BeamformerDASFrequency):
+    """`BeamformerDASFrequency` whose CSM is frame-sharded and whose grid is point-sharded over the
+    ranks of the default process group.  Every rank returns the complete map."""
+
+    def _csm_device(self):
+        return get_csm_device_sharded(self.signal)
+
+    def _grid_rows(self):
+        rank, nranks = world()
+        return grid_shard(self.grid.number_of_points, rank, nranks)
+
+    def _gather_map(self, out_dev):
+        _, nranks = world()
+        G = self.grid.number_of_points
+        counts = [b - a for a, b in (grid_shard(G, r, nranks) for r in range(nranks))]
+        return allgather_rows(out_dev, counts).cpu().numpy()
+
+
+def simulate_frame_sharding(n_frames: int, world_size: int) -> list[tuple[int, int]]:
+    """All shards of a world (host-side helper for tests and for single-GPU emulation of R ranks)."""
+    shards = [frame_shard(n_frames, r, world_size) for r in range(world_size)]
+    assert shards[0][0] == 0 and shards[-1][1] == n_frames
+    assert all(a[1] == b[0] for a, b in zip(shards[:-1], shards[1:]))
+    return shards
+
+
+__all__ = ["split_range", "frame_shard", "grid_shard", "shard_sample_range", "allreduce_sum_",
+           "allgather_rows", "get_csm_device_sharded", "DistributedBeamformerDASFrequency",
+           "simulate_frame_sharding", "world", "np"]

@@ -38,6 +38,14 @@ class Config:
 
 config = Config()
 
+#: number of libb2dsp kernel launches issued by this process (bench.py reports it as gpu_launches)
+launches = 0
+
+
+def _count(n: int = 1):
+    global launches
+    launches += n
+
 _PREC = {"fp64": N.F64, "fp32": N.F32}
 _MAP_MODES = {"simt_f64": N.MAP_SIMT_F64, "simt_f32": N.MAP_SIMT_F32, "tf32": N.MAP_TC_TF32,
               "tf32x3": N.MAP_TC_TF32X3}
@@ -144,12 +152,13 @@ class _Timer:
 # --------------------------------------------------------------------------- stage 1
 def csm_partial_sums(x, length: int, wl: int, step: int, window: np.ndarray, detrend: bool,
                      fft_scale: float, frame_range: tuple[int, int] | None = None,
-                     precision: str | None = None, device=None):
+                     precision: str | None = None, device=None, row_offset: int = 0):
     """Un-normalised per-bin sums S_f = sum_k X_k X_k^H over the frames in `frame_range`.
 
     Returns (S, n_frames_total): S is a complex128 CUDA tensor (nb, M, M) whose lower triangle
     (row >= col) is valid.  Partial sums of disjoint frame ranges add up to the full sum, which
-    is what makes the stage frame-shardable.
+    is what makes the stage frame-shardable.  `x` may hold only the rows
+    [row_offset, row_offset + x.shape[0]) of the recording of `length` samples (a rank's shard).
     """
     torch = _torch()
     lib = N.lib()
@@ -186,17 +195,21 @@ def csm_partial_sums(x, length: int, wl: int, step: int, window: np.ndarray, det
         t1 = min(length, (kn - 1) * step + wl)           # samples beyond `length` are the zero padding
         Lp = (Kp - 1) * step + wl
         Lp += (-Lp) % 4
-        xs, code, s_t, s_m = _as_device_block(x, t0, t1, device)
+        assert t0 >= row_offset and t1 - row_offset <= x.shape[0], "frame range reads samples outside this shard"
+        xs, code, s_t, s_m = _as_device_block(x, t0 - row_offset, t1 - row_offset, device)
         timer.mark("h2d")
         xc = torch.empty((M, Lp), dtype=rdt, device=device)
         N.check(lib.b2_prepare_channels(N.ptr(xs), code, s_t, s_m, 0, t1 - t0, M, N.ptr(xc), Lp, prec, st),
                 "b2_prepare_channels")
+        _count()
         timer.mark("k0_prepare")
         X = torch.empty((nb, M, Kp), dtype=cdt, device=device)
         N.check(lib.b2_welch_rfft(N.ptr(xc), Lp, M, wl, step, nfr, N.ptr(win), N.ptr(tw), int(bool(detrend)),
                                   float(fft_scale), N.ptr(X), Kp, prec, st), "b2_welch_rfft")
+        _count()
         timer.mark("k1_rfft")
         N.check(lib.b2_csm_herk(N.ptr(X), M, Kp, nb, N.ptr(S), 0 if first else 1, prec, st), "b2_csm_herk")
+        _count()
         timer.mark("k2_herk")
         first = False
         kc = kn
@@ -213,6 +226,7 @@ def csm_finalize(S, n_frames: int, factor: float, halve_edges: bool, amplitude_s
     out = torch.empty_like(S)
     N.check(N.lib().b2_csm_finalize(N.ptr(S), M, nb, 1.0 / float(n_frames), float(factor), int(bool(halve_edges)),
                                     int(bool(amplitude_sqrt)), N.ptr(out), N.stream_handle()), "b2_csm_finalize")
+    _count()
     return out
 
 
@@ -226,6 +240,7 @@ def das_prepare(csm_dev, bin0: int, nbins: int, remove_diag: bool, mode: int):
     op = torch.empty(nbytes, dtype=torch.uint8, device=csm_dev.device)
     N.check(lib.b2_das_prepare(N.ptr(csm_dev), M, nb, bin0, nbins, int(bool(remove_diag)), N.ptr(op), mode,
                                N.stream_handle()), "b2_das_prepare")
+    _count()
     return op
 
 
@@ -253,6 +268,7 @@ def das_map(op, M: int, freqs: np.ndarray, weights: np.ndarray, c: float, mic_xy
     N.check(lib.b2_das_map(N.ptr(op), M, nbins, N.ptr(f_dev), N.ptr(w_dev), float(c), N.ptr(mic_dev),
                            N.vec3(center_xyz), N.ptr(g_dev), G, steering, int(bool(clamp_negative)),
                            N.ptr(out), N.ptr(pb), mode, N.stream_handle()), "b2_das_map")
+    _count()
     return out, pb
 
 

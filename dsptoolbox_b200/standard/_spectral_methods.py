@@ -57,12 +57,15 @@ def _scaling_terms(scaling: SpectrumScaling, window_length_samples: int, fs_hz: 
 
 
 def csm_welch_device(time_data, sampling_rate_hz, window_length_samples, window_type, overlap_percent,
-                     detrend, average, scaling, frame_range=None, reduce_fn=None):
+                     detrend, average, scaling, frame_range=None, reduce_fn=None, total_length=None,
+                     row_offset=0):
     """Welch CSM left on the device: (f [numpy], csm [CUDA complex128 tensor (nb, M, M)]).
 
     `frame_range` restricts this process to a shard of the Welch frames and `reduce_fn` (e.g. an
     NCCL all-reduce, see dist.py) is applied to the partial sums before the non-linear
-    finalisation -- the frame-sharded multi-GPU form of the same computation.
+    finalisation -- the frame-sharded multi-GPU form of the same computation.  A rank may pass
+    only its rows of the recording: `time_data` then holds rows [row_offset, row_offset + len) of a
+    recording of `total_length` samples.
     """
     _validate(window_length_samples, overlap_percent, average)
     if not hasattr(time_data, "shape") or len(time_data.shape) != 2:
@@ -70,8 +73,9 @@ def csm_welch_device(time_data, sampling_rate_hz, window_length_samples, window_
     window, step = _window_and_step(window_type, window_length_samples, overlap_percent)
     fft_scale, factor, halve, amp = _scaling_terms(scaling, window_length_samples, sampling_rate_hz, window)
     S, n_frames = engine.csm_partial_sums(
-        time_data, int(time_data.shape[0]), window_length_samples, step, window, detrend, fft_scale,
-        frame_range=frame_range)
+        time_data, int(total_length if total_length is not None else time_data.shape[0]),
+        window_length_samples, step, window, detrend, fft_scale, frame_range=frame_range,
+        row_offset=row_offset)
     if reduce_fn is not None:
         S = reduce_fn(S)
     csm = engine.csm_finalize(S, n_frames, factor, halve, amp)

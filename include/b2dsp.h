@@ -79,8 +79,9 @@ int b2_prepare_channels(const void *x_dev, int in_dtype, int64_t stride_t, int64
  *   xc_dev      (M, Lp) channel-major samples from b2_prepare_channels, Lp >= (Kp-1)*step+wl
  *   window_dev  wl window values in the precision's real type
  *   fft_scale   1, 1/wl or 1/sqrt(wl): the rfft norm of enums.py:53-75
- *   X_out_dev   spectra [wl/2+1][M][Kp] complex (k contiguous); frames >= nframes are
- *               written as zeros so the rank-K update may run over whole tiles. */
+ *   X_out_dev   spectra, Kp * (wl/2+1) * M complex values laid out
+ *               [Kp/16 frame chunks][wl/2+1 bins][M channels][16 frames]; frames >= nframes
+ *               are written as zeros so the rank-K update may run over whole chunks. */
 int b2_welch_rfft(const void *xc_dev, int64_t Lp, int M, int wl, int step, int64_t nframes,
                   const void *window_dev, const void *twiddle_dev, int detrend,
                   double fft_scale, void *X_out_dev, int64_t Kp, int precision, void *stream);
@@ -89,7 +90,7 @@ int b2_welch_rfft(const void *xc_dev, int64_t Lp, int M, int wl, int step, int64
  * Replaces the M(M+1)/2 `_welch` calls of _csm_welch (_spectral_methods.py:351-369) and the
  * frame sum of np.mean (:152); the division by the frame count happens in b2_csm_finalize
  * so partial sums of frame shards can be all-reduced first.
- *   X_dev   [nb][M][Kp] complex spectra (precision's complex type)
+ *   X_dev   spectra in the [Kp/16][nb][M][16] layout written by b2_welch_rfft
  *   S_dev   [nb][M][M] complex128 sums; entries with row >= col are valid on return
  *   accumulate  0: overwrite, 1: add to the existing sums */
 int b2_csm_herk(const void *X_dev, int M, int64_t Kp, int nb, void *S_dev, int accumulate,

@@ -36,7 +36,9 @@ def run_k0_k1(x, wl, step, window, detrend, scale, prec, transposed_storage=Fals
     N.check(lib.b2_welch_rfft(N.ptr(xc), Lp, M, wl, step, K, N.ptr(win), N.ptr(tw), int(detrend), scale,
                               N.ptr(X), Kp, prec, st))
     torch.cuda.synchronize()
-    return xc.cpu().numpy(), X.cpu().numpy(), K, tw.cpu().numpy()
+    # device layout [Kp/16][nb][M][16] -> (nb, M, Kp)
+    Xn = X.cpu().numpy().reshape(Kp // 16, wl // 2 + 1, M, 16).transpose(1, 2, 0, 3).reshape(wl // 2 + 1, M, Kp)
+    return xc.cpu().numpy(), Xn, K, tw.cpu().numpy()
 
 
 @pytest.mark.parametrize("wl", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
