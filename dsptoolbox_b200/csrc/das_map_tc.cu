@@ -1,16 +1,509 @@
-// Tensor-core (tcgen05) variants of the delay-and-sum map -- placeholder until the kernel lands.
+// K3 on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces the G x F np.linalg.multi_dot loop of BeamformerDASFrequency.get_beamformer_map
+// (beamforming/beamforming.py:863-868) with the dense steering array of :858 never stored.
+//
+// Per CTA: a tile of 128 grid points (UMMA M = 128, one TMEM lane per grid point).  For every
+// bin f and every block of NB matrix columns n:
+//
+//     T[g, n] = sum_{m >= n} conj(H[g, m]) L_f[m, n]            (L = 2*tril(C,-1) + diag(C))
+//
+// is a real GEMM  D[128 x 2NB] = A[128 x 2M] * B^T  with
+//     A[g, 2m+{0,1}]   = (Re, Im) of H[g, m] = a_gm exp(-i k_f r_gm)   synthesised by 4 warps
+//                        straight into the 128B-swizzled K-major shared-memory operand tile,
+//     B[n,      2m+{0,1}] = ( Re L[m,n],  Im L[m,n])                    -> D[:, n]      = Re T
+//     B[NB + n, 2m+{0,1}] = ( Im L[m,n], -Re L[m,n])                    -> D[:, NB + n] = Im T
+// (operand images pre-swizzled by b2_das_prepare and streamed with cp.async.bulk), accumulated
+// in TMEM as fp32.  K chunks (16 microphones) that lie entirely above the diagonal are skipped.
+// The epilogue warps read D back with tcgen05.ld, re-synthesise H[g, n] and reduce
+//     P[g, f] = sum_n Re(T[g, n] H[g, n]),   clamp,   map[g] += w_f P[g, f]
+// while the next column block accumulates into the second TMEM buffer.
+// Split-TF32 (PASSES = 3): every operand is split x = hi + lo (both TF32-exact) and
+// hi*hi + lo*hi + hi*lo is accumulated, which restores ~fp32 accuracy.
+//
+// Warp roles (320 threads): 0-3 steering synthesis, 4-7 epilogue, 8 MMA issue + TMEM
+// allocation, 9 operand loader.  Pipelines: smem ring full/empty mbarriers (loader + synthesis ->
+// MMA -> tcgen05.commit), TMEM full/empty mbarriers (MMA -> epilogue).
 #include "common.cuh"
+#include "das_common.cuh"
 
-int64_t b2_das_tc_operand_bytes(int, int, int) {
-    b2_set_error("tensor-core map kernel not built");
-    return B2_EUNSUPPORTED;
+namespace {
+
+constexpr int TILE_G = 128;
+constexpr int KCH = 16;                       // microphones per K chunk = 32 reals = one 128 B row
+constexpr int A_TILE = TILE_G * 128;          // bytes of one A operand image
+constexpr int TC_THREADS = 320;
+constexpr int MAX_MICS = 1024;
+
+__host__ __device__ constexpr int tc_nb(int M) { return M <= 32 ? 32 : (M <= 64 ? 64 : 128); }
+
+template <int NB, int PASSES> struct TcCfg {
+    static constexpr int UMMA_N = 2 * NB;
+    static constexpr int B_TILE = UMMA_N * 128;
+    static constexpr int NSPLIT = PASSES == 3 ? 2 : 1;                 // operand images per stage (hi[, lo])
+    static constexpr int STAGE = NSPLIT * (A_TILE + B_TILE);
+    static constexpr int NSTAGE_RAW = (192 * 1024) / STAGE;
+    static constexpr int NSTAGE = NSTAGE_RAW > 6 ? 6 : NSTAGE_RAW;
+    static constexpr int TMEM_COLS = 2 * UMMA_N;                       // two accumulator buffers
+    static constexpr int SMEM = 1024 /*align slack*/ + NSTAGE * STAGE + 3 * MAX_MICS * 4 + 256;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-int b2_das_tc_prepare(const void *, int, int, int, int, int, void *, int, cudaStream_t) {
-    b2_set_error("tensor-core map kernel not built");
-    return B2_EUNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
-int b2_das_tc_map(const void *, int, int, const void *, const void *, double, const void *, const double *,
-                  const void *, int64_t, int, int, void *, void *, int, cudaStream_t) {
-    b2_set_error("tensor-core map kernel not built");
-    return B2_EUNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 | LBO(=1)<<16 | SBO(=1024B>>4)<<32 | version(=1)<<46 | layout SWIZZLE_128B(=2)<<61
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(64) << 32) | (uint64_t(1) << 46) |
+           (uint64_t(2) << 61);
+}
+// kind::tf32 instruction descriptor: fp32 accumulate, TF32 x TF32, both operands K-major
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+// byte offset of the 16-byte chunk j (0..7) of row r inside a 128B-swizzled K-major tile
+__host__ __device__ __forceinline__ int sw128_offset(int r, int j) { return (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4); }
+
+// ---------------------------------------------------------------- per-row geometry
+struct RowGeo {
+    float gx, gy, gz;     // grid point relative to the reference microphone
+    float c0, c1, c2;     // |h| = c0 + c1 / r + c2 * r   (formulations of beamforming.py:1515-1703)
+};
+
+__device__ __forceinline__ RowGeo row_setup(int64_t g, int64_t G, const double *__restrict__ grid,
+                                            const double *__restrict__ mic, int M, double cx0, double cy0,
+                                            double cz0, int steering) {
+    RowGeo rg;
+    rg.gx = rg.gy = rg.gz = 0.f;
+    rg.c0 = rg.c1 = rg.c2 = 0.f;
+    if (g >= G) { rg.gz = 1.0f; return rg; }               // inactive row: amplitude 0
+    const double x = grid[3 * g], y = grid[3 * g + 1], z = grid[3 * g + 2];
+    double s = 0.0;
+    for (int m = 0; m < M; ++m) {
+        const double dx = x - mic[3 * m], dy = y - mic[3 * m + 1], dz = z - mic[3 * m + 2];
+        s += 1.0 / (dx * dx + dy * dy + dz * dz);
+    }
+    const double r0 = das_distance(x, y, z, cx0, cy0, cz0);
+    switch (steering) {
+    case B2_STEER_CLASSIC: rg.c0 = float(1.0 / double(M)); break;
+    case B2_STEER_INVERSE: rg.c2 = float(1.0 / (double(M) * r0)); break;
+    case B2_STEER_TRUE_POWER: rg.c1 = float(1.0 / (r0 * s)); break;
+    default: rg.c1 = float(1.0 / sqrt(double(M) * s)); break;
+    }
+    rg.gx = float(x - cx0); rg.gy = float(y - cy0); rg.gz = float(z - cz0);
+    return rg;
+}
+
+struct BinF {               // frequency / c as compensated floats:  f/c = q_hi + q_lo  (cycles per metre)
+    float q_hi, q_lo;
+};
+
+// H[g, m] = a exp(-i 2 pi (f/c) r): returns (Re, Im)
+__device__ __forceinline__ float2 steer(const RowGeo &rg, float mx, float my, float mz, BinF b) {
+    const float dx = rg.gx - mx, dy = rg.gy - my, dz = rg.gz - mz;
+    const float d2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-30f);
+    const float rs = rsqrtf(d2);
+    float r = d2 * rs;
+    r = fmaf(0.5f * rs, fmaf(-r, r, d2), r);                  // one Newton step: r = sqrt(d2) to ~0.5 ulp
+    const float a = fmaf(rg.c2, r, fmaf(rg.c1, rs, rg.c0));
+    // cycles = (q_hi + q_lo) * r, fractional part kept to full fp32 accuracy
+    const float p = b.q_hi * r;
+    const float e = fmaf(b.q_hi, r, -p) + b.q_lo * r;
+    const float fr = (p - rintf(p)) + e;
+    float sn, cs;
+    __sincosf(6.28318530717958647692f * fr, &sn, &cs);
+    return make_float2(a * cs, -a * sn);
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int NB, int PASSES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+das_map_tc_kernel(const unsigned char *__restrict__ op, int M, int nbins, const double *__restrict__ freqs,
+                  const double *__restrict__ weights, double inv_c, const double *__restrict__ mic, double cx0,
+                  double cy0, double cz0, const double *__restrict__ grid, int64_t G, int steering,
+                  int clamp_negative, double *__restrict__ map_out, double *__restrict__ per_bin, int ntiles) {
+    using CF = TcCfg<NB, PASSES>;
+    constexpr int UMMA_N = CF::UMMA_N, NSTAGE = CF::NSTAGE;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float *micf = reinterpret_cast<float *>(smem + NSTAGE * CF::STAGE);               // [3][MAX_MICS]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(micf + 3 * MAX_MICS);
+    uint64_t *full = bars, *empty = bars + NSTAGE, *tfull = bars + 2 * NSTAGE, *tempty = bars + 2 * NSTAGE + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGE + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NKC = (M + KCH - 1) / KCH;          // K chunks
+    const int NBLK = (M + NB - 1) / NB;           // column blocks
+
+    // stage s: [A_hi][A_lo?][B_hi][B_lo?]
+    auto a_tile = [&](int s, int split) { return smem + s * CF::STAGE + split * A_TILE; };
+    auto b_tile = [&](int s, int split) { return smem + s * CF::STAGE + CF::NSPLIT * A_TILE + split * CF::B_TILE; };
+
+    for (int i = tid; i < 3 * MAX_MICS; i += TC_THREADS) {
+        const int c = i / MAX_MICS, m = i - c * MAX_MICS;
+        const double ctr = c == 0 ? cx0 : (c == 1 ? cy0 : cz0);
+        micf[i] = m < M ? float(mic[3 * m + c] - ctr) : 0.f;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 128 + 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, CF::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // =========================== steering synthesis -> A operand tiles ===========================
+        const int r = tid;                                   // row of the tile = TMEM lane
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const RowGeo rg = row_setup(int64_t(tile) * TILE_G + r, G, grid, mic, M, cx0, cy0, cz0, steering);
+            for (int fi = 0; fi < nbins; ++fi) {
+                const double q = freqs[fi] * inv_c;
+                BinF bf;
+                bf.q_hi = float(q);
+                bf.q_lo = float(q - double(bf.q_hi));
+                for (int nbk = 0; nbk < NBLK; ++nbk) {
+                    for (int kc = (nbk * NB) / KCH; kc < NKC; ++kc, ++it) {
+                        const int s = it % NSTAGE;
+                        mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
+                        unsigned char *ahi = a_tile(s, 0);
+                        unsigned char *alo = a_tile(s, CF::NSPLIT - 1);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int m0 = kc * KCH + 2 * j;
+                            float2 h0 = make_float2(0.f, 0.f), h1 = make_float2(0.f, 0.f);
+                            if (m0 < M) h0 = steer(rg, micf[m0], micf[MAX_MICS + m0], micf[2 * MAX_MICS + m0], bf);
+                            if (m0 + 1 < M) h1 = steer(rg, micf[m0 + 1], micf[MAX_MICS + m0 + 1], micf[2 * MAX_MICS + m0 + 1], bf);
+                            float4 hi4 = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
+                            const int off = sw128_offset(r, j);
+                            *reinterpret_cast<float4 *>(ahi + off) = hi4;
+                            if (PASSES == 3) {
+                                float4 lo4 = make_float4(to_tf32(h0.x - hi4.x), to_tf32(h0.y - hi4.y),
+                                                         to_tf32(h1.x - hi4.z), to_tf32(h1.y - hi4.w));
+                                *reinterpret_cast<float4 *>(alo + off) = lo4;
+                            }
+                        }
+                        fence_proxy_async();                 // generic-proxy writes -> visible to the MMA (async proxy)
+                        mbar_arrive(&full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp < 8) {
+        // =========================== epilogue: TMEM -> P[g,f] -> map ===========================
+        const int r = tid - 128;
+        const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+        uint32_t acc_it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t g = int64_t(tile) * TILE_G + r;
+            const RowGeo rg = row_setup(g, G, grid, mic, M, cx0, cy0, cz0, steering);
+            double acc_map = 0.0;
+            for (int fi = 0; fi < nbins; ++fi) {
+                const double q = freqs[fi] * inv_c;
+                BinF bf;
+                bf.q_hi = float(q);
+                bf.q_lo = float(q - double(bf.q_hi));
+                float p0 = 0.f, p1 = 0.f;
+                for (int nbk = 0; nbk < NBLK; ++nbk, ++acc_it) {
+                    const int buf = acc_it & 1;
+                    mbar_wait(&tfull[buf], (acc_it >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N;
+#pragma unroll 1
+                    for (int cg = 0; cg < NB / 32; ++cg) {
+                        const int n0 = nbk * NB + cg * 32;
+                        if (n0 >= M) break;
+                        float tr[32], ti[32];
+                        tmem_ld32(tcol + cg * 32, tr);
+                        tmem_ld32(tcol + NB + cg * 32, ti);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const int n = n0 + j;
+                            if (n < M) {
+                                const float2 h = steer(rg, micf[n], micf[MAX_MICS + n], micf[2 * MAX_MICS + n], bf);
+                                p0 = fmaf(tr[j], h.x, p0);
+                                p0 = fmaf(-ti[j], h.y, p0);
+                            }
+                            if (n + 1 < M) {
+                                const float2 h = steer(rg, micf[n + 1], micf[MAX_MICS + n + 1], micf[2 * MAX_MICS + n + 1], bf);
+                                p1 = fmaf(tr[j + 1], h.x, p1);
+                                p1 = fmaf(-ti[j + 1], h.y, p1);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&tempty[buf]);
+                }
+                double p = double(p0) + double(p1);
+                if (clamp_negative && p < 0.0) p = 0.0;                         // beamforming.py:871-872
+                acc_map += weights[fi] * p;                                       // :875-876
+                if (per_bin != nullptr && g < G) per_bin[g * nbins + fi] = p;
+            }
+            if (g < G) map_out[g] = acc_map;
+        }
+    } else if (warp == 8) {
+        // =========================== MMA issue (one thread) ===========================
+        if (lane == 0) {
+            constexpr uint32_t IDESC = idesc_tf32(TILE_G, UMMA_N);
+            uint32_t it = 0, acc_it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int fi = 0; fi < nbins; ++fi) {
+                    for (int nbk = 0; nbk < NBLK; ++nbk, ++acc_it) {
+                        const int buf = acc_it & 1;
+                        mbar_wait(&tempty[buf], ((acc_it >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + buf * UMMA_N;
+                        const int kc0 = (nbk * NB) / KCH;
+                        for (int kc = kc0; kc < NKC; ++kc, ++it) {
+                            const int s = it % NSTAGE;
+                            mbar_wait(&full[s], (it / NSTAGE) & 1);
+                            tc_fence_after();
+                            const uint64_t a_hi = smem_desc_sw128(smem_u32(a_tile(s, 0)));
+                            const uint64_t b_hi = smem_desc_sw128(smem_u32(b_tile(s, 0)));
+                            const uint64_t a_lo = smem_desc_sw128(smem_u32(a_tile(s, CF::NSPLIT - 1)));
+                            const uint64_t b_lo = smem_desc_sw128(smem_u32(b_tile(s, CF::NSPLIT - 1)));
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {              // UMMA K = 8 tf32 = 32 bytes
+                                const uint64_t adv = uint64_t(ks * 2);    // (32 B) >> 4
+                                umma_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kc > kc0 || ks > 0) ? 1u : 0u);
+                                if (PASSES == 3) {
+                                    umma_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1u);
+                                    umma_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+                                }
+                            }
+                            umma_commit(&empty[s]);                       // frees the stage when the MMAs retire
+                        }
+                        umma_commit(&tfull[buf]);                         // accumulator complete -> epilogue
+                    }
+                }
+            }
+        }
+    } else {
+        // =========================== B operand loader (one thread) ===========================
+        if (lane == 0) {
+            uint32_t it = 0;
+            const size_t bin_bytes = size_t(NBLK) * NKC * CF::NSPLIT * CF::B_TILE;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int fi = 0; fi < nbins; ++fi) {
+                    for (int nbk = 0; nbk < NBLK; ++nbk) {
+                        for (int kc = (nbk * NB) / KCH; kc < NKC; ++kc, ++it) {
+                            const int s = it % NSTAGE;
+                            mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
+                            const unsigned char *src = op + size_t(fi) * bin_bytes + (size_t(nbk) * NKC + kc) * (CF::NSPLIT * CF::B_TILE);
+                            mbar_arrive_expect_tx(&full[s], CF::NSPLIT * CF::B_TILE);
+                            bulk_g2s(b_tile(s, 0), src, CF::NSPLIT * CF::B_TILE, &full[s]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 8) tmem_dealloc(tmem_base, CF::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------- K3a for the tensor-core path
+// One thread per 16-byte chunk of an operand image: (bin, column block, K chunk, row, chunk j).
+template <int NB, int PASSES>
+__global__ void das_prepare_tc_kernel(const double2 *__restrict__ csm, int M, int bin0, double gain, int remove_diag,
+                                      unsigned char *__restrict__ op, int NKC, int NBLK) {
+    using CF = TcCfg<NB, PASSES>;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;       // 0 .. 2NB-1
+    if (row >= CF::UMMA_N) return;
+    const int kc = blockIdx.y % NKC, nbk = blockIdx.y / NKC;
+    const int fi = blockIdx.z;
+    const bool imag_row = row >= NB;
+    const int n = nbk * NB + (imag_row ? row - NB : row);
+    unsigned char *tile = op + ((size_t(fi) * NBLK + nbk) * NKC + kc) * size_t(CF::NSPLIT * CF::B_TILE);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int m = kc * KCH + 2 * j + e;
+            double lr = 0.0, li = 0.0;
+            if (m < M && n < M && n <= m) {
+                const double2 c = csm[(int64_t(bin0 + fi) * M + m) * M + n];
+                if (n == m) { lr = remove_diag ? 0.0 : gain * c.x; }
+                else { lr = 2.0 * gain * c.x; li = 2.0 * gain * c.y; }
+            }
+            // real rows: (Re L, Im L) ; imaginary rows: (Im L, -Re L)
+            v[2 * e] = float(imag_row ? li : lr);
+            v[2 * e + 1] = float(imag_row ? -lr : li);
+        }
+        const int off = sw128_offset(row, j);
+        const float4 hi = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+        *reinterpret_cast<float4 *>(tile + off) = hi;
+        if (PASSES == 3) {
+            const float4 lo = make_float4(to_tf32(v[0] - hi.x), to_tf32(v[1] - hi.y), to_tf32(v[2] - hi.z), to_tf32(v[3] - hi.w));
+            *reinterpret_cast<float4 *>(tile + CF::B_TILE + off) = lo;
+        }
+    }
+}
+
+template <int NB, int PASSES>
+int launch_prepare(const void *csm, int M, int bin0, int nbins, int remove_diag, void *op, cudaStream_t st) {
+    using CF = TcCfg<NB, PASSES>;
+    const int NKC = (M + KCH - 1) / KCH, NBLK = (M + NB - 1) / NB;
+    const double gain = remove_diag ? double(M) / double(M - 1) : 1.0;
+    dim3 grid((CF::UMMA_N + 127) / 128, NKC * NBLK, nbins);
+    das_prepare_tc_kernel<NB, PASSES><<<grid, 128, 0, st>>>((const double2 *)csm, M, bin0, gain, remove_diag,
+                                                            (unsigned char *)op, NKC, NBLK);
+    B2_LAUNCH_OK("b2_das_prepare(tc)");
+    return B2_OK;
+}
+
+template <int NB, int PASSES>
+int launch_map(const void *op, int M, int nbins, const void *freqs, const void *weights, double c, const void *mic,
+               const double *center, const void *grid, int64_t G, int steering, int clamp_negative, void *map_out,
+               void *per_bin, cudaStream_t st) {
+    using CF = TcCfg<NB, PASSES>;
+    auto kern = das_map_tc_kernel<NB, PASSES>;
+    static bool attr_done = false;
+    static int num_sms = 0;
+    if (!attr_done) {
+        B2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
+        int dev = 0;
+        B2_CUDA_OK(cudaGetDevice(&dev));
+        B2_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        attr_done = true;
+    }
+    const int64_t ntiles = (G + TILE_G - 1) / TILE_G;
+    B2_REQUIRE(ntiles <= 0x7fffffff, B2_EINVAL, "b2_das_map: too many grid points");
+    const int nblocks = int(ntiles < num_sms ? ntiles : num_sms);      // persistent: one CTA per SM
+    kern<<<nblocks, TC_THREADS, CF::SMEM, st>>>((const unsigned char *)op, M, nbins, (const double *)freqs,
+                                                (const double *)weights, 1.0 / c, (const double *)mic, center[0],
+                                                center[1], center[2], (const double *)grid, G, steering,
+                                                clamp_negative, (double *)map_out, (double *)per_bin, int(ntiles));
+    B2_LAUNCH_OK("b2_das_map(tc)");
+    return B2_OK;
+}
+
+template <int PASSES> int64_t operand_bytes(int M, int nbins) {
+    const int NKC = (M + KCH - 1) / KCH;
+    const int nb = tc_nb(M), NBLK = (M + nb - 1) / nb;
+    const int64_t btile = 2 * nb * 128;
+    return int64_t(nbins) * NBLK * NKC * (PASSES == 3 ? 2 : 1) * btile;
+}
+
+}  // namespace
+
+int64_t b2_das_tc_operand_bytes(int M, int nbins, int mode) {
+    if (M > MAX_MICS) { b2_set_error("tensor-core map kernel supports at most %d microphones", MAX_MICS); return B2_EUNSUPPORTED; }
+    return mode == B2_MAP_TC_TF32X3 ? operand_bytes<3>(M, nbins) : operand_bytes<1>(M, nbins);
+}
+
+#define B2_TC_DISPATCH(FN, ...)                                                      \
+    do {                                                                             \
+        const int nb_ = tc_nb(M);                                                    \
+        if (mode == B2_MAP_TC_TF32X3) {                                              \
+            if (nb_ == 32) return FN<32, 3>(__VA_ARGS__);                            \
+            if (nb_ == 64) return FN<64, 3>(__VA_ARGS__);                            \
+            return FN<128, 3>(__VA_ARGS__);                                          \
+        } else {                                                                     \
+            if (nb_ == 32) return FN<32, 1>(__VA_ARGS__);                            \
+            if (nb_ == 64) return FN<64, 1>(__VA_ARGS__);                            \
+            return FN<128, 1>(__VA_ARGS__);                                          \
+        }                                                                            \
+    } while (0)
+
+int b2_das_tc_prepare(const void *csm_dev, int M, int nb, int bin0, int nbins, int remove_diag, void *op_dev,
+                      int mode, cudaStream_t st) {
+    (void)nb;
+    B2_REQUIRE(M <= MAX_MICS, B2_EUNSUPPORTED, "tensor-core map kernel supports at most %d microphones", MAX_MICS);
+    B2_TC_DISPATCH(launch_prepare, csm_dev, M, bin0, nbins, remove_diag, op_dev, st);
+}
+
+int b2_das_tc_map(const void *op_dev, int M, int nbins, const void *freqs_dev, const void *weights_dev, double c,
+                  const void *mic_xyz_dev, const double *center_xyz, const void *grid_xyz_dev, int64_t G,
+                  int steering, int clamp_negative, void *map_out_dev, void *per_bin_out_dev, int mode,
+                  cudaStream_t st) {
+    B2_REQUIRE(M <= MAX_MICS, B2_EUNSUPPORTED, "tensor-core map kernel supports at most %d microphones", MAX_MICS);
+    B2_TC_DISPATCH(launch_map, op_dev, M, nbins, freqs_dev, weights_dev, c, mic_xyz_dev, center_xyz, grid_xyz_dev, G,
+                   steering, clamp_negative, map_out_dev, per_bin_out_dev, st);
 }

@@ -22,7 +22,7 @@ template <typename T, int LOG2NC> struct Geo {
     static constexpr int NCP = NC + (NC >> 3);          // 1 pad slot per 8 points
     static constexpr int PITCH = NCP + 1;               // per-frame pitch (staggers frames)
     static constexpr int CXB = int(sizeof(cx<T>));
-    static constexpr int frames_fit(int fr) { return fr * PITCH * CXB <= 72 * 1024; }
+    static constexpr int frames_fit(int fr) { return fr * PITCH * CXB <= 74 * 1024; }   // 3 CTAs per SM
     static constexpr int FR = frames_fit(16) ? 16 : frames_fit(8) ? 8 : frames_fit(4) ? 4 : frames_fit(2) ? 2 : 1;
     static constexpr int VPT = sizeof(T) == 8 ? 16 : 32;  // complex values held per thread
     static constexpr int NT_RAW = FR * NC / VPT;
@@ -80,9 +80,25 @@ __device__ __forceinline__ void stockham_pass(cx<T> *s, const cx<T> *__restrict_
 #pragma unroll
             for (int r = 0; r < R; ++r) v[it][r] = base[padidx(j + r * J)];
             if constexpr (NS > 1) {
+                // twiddles w^r, w = exp(-2 pi i k / (NS R)): one table read, powers by products
+                // (depth <= 3 multiplications, so the error stays at a few ulp)
                 constexpr int TSTEP = G::N / (NS * R);
-#pragma unroll
-                for (int r = 1; r < R; ++r) v[it][r] = cmul(v[it][r], tw[k * r * TSTEP]);
+                const cx<T> w1 = __ldg(tw + k * TSTEP);
+                if constexpr (R == 2) {
+                    v[it][1] = cmul(v[it][1], w1);
+                } else {
+                    const cx<T> w2 = cmul(w1, w1), w3 = cmul(w1, w2);
+                    v[it][1] = cmul(v[it][1], w1);
+                    v[it][2] = cmul(v[it][2], w2);
+                    v[it][3] = cmul(v[it][3], w3);
+                    if constexpr (R == 8) {
+                        const cx<T> w4 = cmul(w2, w2);
+                        v[it][4] = cmul(v[it][4], w4);
+                        v[it][5] = cmul(v[it][5], cmul(w4, w1));
+                        v[it][6] = cmul(v[it][6], cmul(w4, w2));
+                        v[it][7] = cmul(v[it][7], cmul(w4, w3));
+                    }
+                }
             }
             dftR<T, R>(v[it]);
         }
@@ -146,9 +162,21 @@ welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframe
             if (vec_ok) {
                 const C *src2 = reinterpret_cast<const C *>(src);
                 const C *w2 = reinterpret_cast<const C *>(window);
-                for (int n = tid; n < NC; n += NT) {
-                    C x = __ldg(src2 + n), w = __ldg(w2 + n);
-                    base[padidx(n)] = mk<T>(x.x * w.x, x.y * w.y);
+                constexpr int PER = (NC + NT - 1) / NT;
+                constexpr int UN = PER < 8 ? PER : 8;
+                // issue UN independent loads before touching shared memory (memory-level parallelism)
+                for (int n0 = tid; n0 < NC; n0 += NT * UN) {
+                    C xv[UN], wv[UN];
+#pragma unroll
+                    for (int u = 0; u < UN; ++u) {
+                        const int n = n0 + u * NT;
+                        if (n < NC) { xv[u] = __ldg(src2 + n); wv[u] = __ldg(w2 + n); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UN; ++u) {
+                        const int n = n0 + u * NT;
+                        if (n < NC) base[padidx(n)] = mk<T>(xv[u].x * wv[u].x, xv[u].y * wv[u].y);
+                    }
                 }
             } else {
                 for (int n = tid; n < NC; n += NT)
