@@ -21,9 +21,13 @@
 // Split-TF32 (PASSES = 3): every operand is split x = hi + lo (both TF32-exact) and
 // hi*hi + lo*hi + hi*lo is accumulated, which restores ~fp32 accuracy.
 //
-// Warp roles (320 threads): 0-3 steering synthesis, 4-7 epilogue, 8 MMA issue + TMEM
-// allocation, 9 operand loader.  Pipelines: smem ring full/empty mbarriers (loader + synthesis ->
-// MMA -> tcgen05.commit), TMEM full/empty mbarriers (MMA -> epilogue).
+// Warp roles (576 threads): 0-7 steering synthesis (two threads per grid point), 8-15 epilogue
+// (two warps per TMEM lane quadrant), 16 MMA issue + TMEM allocation, 17 operand loader.
+// Pipelines: smem ring full/empty mbarriers (loader + synthesis -> MMA -> tcgen05.commit), TMEM
+// full/empty mbarriers (MMA -> epilogue).  The bin-independent part of the steering vector
+// (distance r and amplitude a of every (grid point, microphone) pair of the tile) is computed
+// once per tile in fp64 and parked in an L2-resident scratch table, so the per-bin work is one
+// compensated phase product, one sincos and the TF32 split.
 #include "common.cuh"
 #include "das_common.cuh"
 
@@ -32,7 +36,10 @@ namespace {
 constexpr int TILE_G = 128;
 constexpr int KCH = 16;                       // microphones per K chunk = 32 reals = one 128 B row
 constexpr int A_TILE = TILE_G * 128;          // bytes of one A operand image
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 576;
+constexpr int NGEN = 256;                     // synthesis threads
+constexpr int NEPI = 256;                     // epilogue threads
+constexpr int MAX_CTAS = 160;                 // scratch tables are sized for this many persistent CTAs
 constexpr int MAX_MICS = 1024;
 
 __host__ __device__ constexpr int tc_nb(int M) { return M <= 32 ? 32 : (M <= 64 ? 64 : 128); }
@@ -42,10 +49,10 @@ template <int NB, int PASSES> struct TcCfg {
     static constexpr int B_TILE = UMMA_N * 128;
     static constexpr int NSPLIT = PASSES == 3 ? 2 : 1;                 // operand images per stage (hi[, lo])
     static constexpr int STAGE = NSPLIT * (A_TILE + B_TILE);
-    static constexpr int NSTAGE_RAW = (192 * 1024) / STAGE;
+    static constexpr int NSTAGE_RAW = (208 * 1024) / STAGE;
     static constexpr int NSTAGE = NSTAGE_RAW > 6 ? 6 : NSTAGE_RAW;
     static constexpr int TMEM_COLS = 2 * UMMA_N;                       // two accumulator buffers
-    static constexpr int SMEM = 1024 /*align slack*/ + NSTAGE * STAGE + 3 * MAX_MICS * 4 + 256;
+    static constexpr int SMEM = 1024 /*align slack*/ + NSTAGE * STAGE + 2 * TILE_G * 4 + 256;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -120,6 +127,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float to_tf32(float x) {
@@ -141,103 +159,102 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
 // byte offset of the 16-byte chunk j (0..7) of row r inside a 128B-swizzled K-major tile
 __host__ __device__ __forceinline__ int sw128_offset(int r, int j) { return (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4); }
 
-// ---------------------------------------------------------------- per-row geometry
-struct RowGeo {
-    float gx, gy, gz;     // grid point relative to the reference microphone
-    float c0, c1, c2;     // |h| = c0 + c1 / r + c2 * r   (formulations of beamforming.py:1515-1703)
-};
+// ---------------------------------------------------------------- per-tile geometry table
+// tab[((kc*2 + half)*128 + row)*8 + i] = (r, a) of microphone m = kc*16 + half*8 + i for grid
+// point `row` of the tile: r = |grid - mic| and a = |h| of beamforming.py:1515-1703.
+__device__ __forceinline__ int tab_index(int m, int row) { return (((m >> 3) * TILE_G) + row) * 8 + (m & 7); }
 
-__device__ __forceinline__ RowGeo row_setup(int64_t g, int64_t G, const double *__restrict__ grid,
-                                            const double *__restrict__ mic, int M, double cx0, double cy0,
-                                            double cz0, int steering) {
-    RowGeo rg;
-    rg.gx = rg.gy = rg.gz = 0.f;
-    rg.c0 = rg.c1 = rg.c2 = 0.f;
-    if (g >= G) { rg.gz = 1.0f; return rg; }               // inactive row: amplitude 0
-    const double x = grid[3 * g], y = grid[3 * g + 1], z = grid[3 * g + 2];
-    double s = 0.0;
-    for (int m = 0; m < M; ++m) {
-        const double dx = x - mic[3 * m], dy = y - mic[3 * m + 1], dz = z - mic[3 * m + 2];
-        s += 1.0 / (dx * dx + dy * dy + dz * dz);
+// Fill the (r, a) entries of microphones with ((m >> 3) & 1) == half for one grid point.
+__device__ __forceinline__ void row_table(float2 *__restrict__ tab, int row, int half, int64_t g, int64_t G,
+                                          const double *__restrict__ grid, const double *__restrict__ mic, int M,
+                                          int Mk, double cx0, double cy0, double cz0, int steering) {
+    const bool valid = g < G;
+    double x = 0, y = 0, z = 0, s = 0.0, r0 = 1.0;
+    if (valid) {
+        x = grid[3 * g]; y = grid[3 * g + 1]; z = grid[3 * g + 2];
+        for (int m = 0; m < M; ++m) {
+            const double dx = x - mic[3 * m], dy = y - mic[3 * m + 1], dz = z - mic[3 * m + 2];
+            s += 1.0 / (dx * dx + dy * dy + dz * dz);
+        }
+        r0 = das_distance(x, y, z, cx0, cy0, cz0);
     }
-    const double r0 = das_distance(x, y, z, cx0, cy0, cz0);
-    switch (steering) {
-    case B2_STEER_CLASSIC: rg.c0 = float(1.0 / double(M)); break;
-    case B2_STEER_INVERSE: rg.c2 = float(1.0 / (double(M) * r0)); break;
-    case B2_STEER_TRUE_POWER: rg.c1 = float(1.0 / (r0 * s)); break;
-    default: rg.c1 = float(1.0 / sqrt(double(M) * s)); break;
+    for (int m8 = half * 8; m8 < Mk; m8 += 16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m8 + i;
+            float2 v = make_float2(1.0f, 0.0f);
+            if (valid && m < M) {
+                const double r = das_distance(x, y, z, mic[3 * m], mic[3 * m + 1], mic[3 * m + 2]);
+                v = make_float2(float(r), float(das_amplitude(steering, r, r0, s, M)));
+            }
+            tab[tab_index(m, row)] = v;
+        }
     }
-    rg.gx = float(x - cx0); rg.gy = float(y - cy0); rg.gz = float(z - cz0);
-    return rg;
 }
 
 struct BinF {               // frequency / c as compensated floats:  f/c = q_hi + q_lo  (cycles per metre)
     float q_hi, q_lo;
 };
 
-// H[g, m] = a exp(-i 2 pi (f/c) r): returns (Re, Im)
-__device__ __forceinline__ float2 steer(const RowGeo &rg, float mx, float my, float mz, BinF b) {
-    const float dx = rg.gx - mx, dy = rg.gy - my, dz = rg.gz - mz;
-    const float d2 = fmaxf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)), 1e-30f);
-    const float rs = rsqrtf(d2);
-    float r = d2 * rs;
-    r = fmaf(0.5f * rs, fmaf(-r, r, d2), r);                  // one Newton step: r = sqrt(d2) to ~0.5 ulp
-    const float a = fmaf(rg.c2, r, fmaf(rg.c1, rs, rg.c0));
-    // cycles = (q_hi + q_lo) * r, fractional part kept to full fp32 accuracy
+// H[g, m] = a exp(-i 2 pi (f/c) r): returns (Re, Im); the phase (in cycles) is reduced exactly.
+__device__ __forceinline__ float2 steer(float2 ra, BinF b) {
+    const float r = ra.x;
     const float p = b.q_hi * r;
-    const float e = fmaf(b.q_hi, r, -p) + b.q_lo * r;
+    const float e = fmaf(b.q_lo, r, fmaf(b.q_hi, r, -p));
     const float fr = (p - rintf(p)) + e;
     float sn, cs;
     __sincosf(6.28318530717958647692f * fr, &sn, &cs);
-    return make_float2(a * cs, -a * sn);
+    return make_float2(ra.y * cs, -ra.y * sn);
 }
 
 // ---------------------------------------------------------------- the kernel
 template <int NB, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-das_map_tc_kernel(const unsigned char *__restrict__ op, int M, int nbins, const double *__restrict__ freqs,
-                  const double *__restrict__ weights, double inv_c, const double *__restrict__ mic, double cx0,
-                  double cy0, double cz0, const double *__restrict__ grid, int64_t G, int steering,
-                  int clamp_negative, double *__restrict__ map_out, double *__restrict__ per_bin, int ntiles) {
+das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scratch, int M, int nbins,
+                  const double *__restrict__ freqs, const double *__restrict__ weights, double inv_c,
+                  const double *__restrict__ mic, double cx0, double cy0, double cz0,
+                  const double *__restrict__ grid, int64_t G, int steering, int clamp_negative,
+                  double *__restrict__ map_out, double *__restrict__ per_bin, int ntiles) {
     using CF = TcCfg<NB, PASSES>;
     constexpr int UMMA_N = CF::UMMA_N, NSTAGE = CF::NSTAGE;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float *micf = reinterpret_cast<float *>(smem + NSTAGE * CF::STAGE);               // [3][MAX_MICS]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(micf + 3 * MAX_MICS);
+    float *part = reinterpret_cast<float *>(smem + NSTAGE * CF::STAGE);                // [2][128] epilogue partials
+    uint64_t *bars = reinterpret_cast<uint64_t *>(part + 2 * TILE_G);
     uint64_t *full = bars, *empty = bars + NSTAGE, *tfull = bars + 2 * NSTAGE, *tempty = bars + 2 * NSTAGE + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGE + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NKC = (M + KCH - 1) / KCH;          // K chunks
+    const int Mk = NKC * KCH;
     const int NBLK = (M + NB - 1) / NB;           // column blocks
+    float2 *tab = scratch + size_t(blockIdx.x) * TILE_G * Mk;
 
     // stage s: [A_hi][A_lo?][B_hi][B_lo?]
     auto a_tile = [&](int s, int split) { return smem + s * CF::STAGE + split * A_TILE; };
     auto b_tile = [&](int s, int split) { return smem + s * CF::STAGE + CF::NSPLIT * A_TILE + split * CF::B_TILE; };
 
-    for (int i = tid; i < 3 * MAX_MICS; i += TC_THREADS) {
-        const int c = i / MAX_MICS, m = i - c * MAX_MICS;
-        const double ctr = c == 0 ? cx0 : (c == 1 ? cy0 : cz0);
-        micf[i] = m < M ? float(mic[3 * m + c] - ctr) : 0.f;
-    }
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 128 + 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 128); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], NGEN + 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEPI); }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, CF::TMEM_COLS);
+    if (warp == 16) tmem_alloc(tmem_slot, CF::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // =========================== steering synthesis -> A operand tiles ===========================
-        const int r = tid;                                   // row of the tile = TMEM lane
+        const int r = tid & 127, half = tid >> 7;            // row of the tile, which 8 of a chunk's 16 mics
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const RowGeo rg = row_setup(int64_t(tile) * TILE_G + r, G, grid, mic, M, cx0, cy0, cz0, steering);
+            // the epilogue warps are done with the previous tile's table before it is overwritten
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            row_table(tab, r, half, int64_t(tile) * TILE_G + r, G, grid, mic, M, Mk, cx0, cy0, cz0, steering);
+            __threadfence_block();
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             for (int fi = 0; fi < nbins; ++fi) {
                 const double q = freqs[fi] * inv_c;
                 BinF bf;
@@ -246,23 +263,29 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, int M, int nbins, const 
                 for (int nbk = 0; nbk < NBLK; ++nbk) {
                     for (int kc = (nbk * NB) / KCH; kc < NKC; ++kc, ++it) {
                         const int s = it % NSTAGE;
+                        // (r, a) of this thread's 8 microphones: 64 contiguous bytes, coalesced over rows
+                        const float4 *src = reinterpret_cast<const float4 *>(tab + tab_index(kc * KCH + half * 8, r));
+                        float4 ra[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ra[j] = __ldcg(src + j);
+                        float4 hi4[4], lo4[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 h0 = steer(make_float2(ra[j].x, ra[j].y), bf);
+                            const float2 h1 = steer(make_float2(ra[j].z, ra[j].w), bf);
+                            hi4[j] = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
+                            if (PASSES == 3)
+                                lo4[j] = make_float4(to_tf32(h0.x - hi4[j].x), to_tf32(h0.y - hi4[j].y),
+                                                     to_tf32(h1.x - hi4[j].z), to_tf32(h1.y - hi4[j].w));
+                        }
                         mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
                         unsigned char *ahi = a_tile(s, 0);
                         unsigned char *alo = a_tile(s, CF::NSPLIT - 1);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int m0 = kc * KCH + 2 * j;
-                            float2 h0 = make_float2(0.f, 0.f), h1 = make_float2(0.f, 0.f);
-                            if (m0 < M) h0 = steer(rg, micf[m0], micf[MAX_MICS + m0], micf[2 * MAX_MICS + m0], bf);
-                            if (m0 + 1 < M) h1 = steer(rg, micf[m0 + 1], micf[MAX_MICS + m0 + 1], micf[2 * MAX_MICS + m0 + 1], bf);
-                            float4 hi4 = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
-                            const int off = sw128_offset(r, j);
-                            *reinterpret_cast<float4 *>(ahi + off) = hi4;
-                            if (PASSES == 3) {
-                                float4 lo4 = make_float4(to_tf32(h0.x - hi4.x), to_tf32(h0.y - hi4.y),
-                                                         to_tf32(h1.x - hi4.z), to_tf32(h1.y - hi4.w));
-                                *reinterpret_cast<float4 *>(alo + off) = lo4;
-                            }
+                        for (int j = 0; j < 4; ++j) {
+                            const int off = sw128_offset(r, half * 4 + j);
+                            *reinterpret_cast<float4 *>(ahi + off) = hi4[j];
+                            if (PASSES == 3) *reinterpret_cast<float4 *>(alo + off) = lo4[j];
                         }
                         fence_proxy_async();                 // generic-proxy writes -> visible to the MMA (async proxy)
                         mbar_arrive(&full[s]);
@@ -270,14 +293,18 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, int M, int nbins, const 
                 }
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < 16) {
         // =========================== epilogue: TMEM -> P[g,f] -> map ===========================
-        const int r = tid - 128;
-        const uint32_t lane_base = uint32_t((warp & 3) * 32) << 16;
+        const int ew = warp - 8;
+        const int quad = ew & 3, half = ew >> 2;             // TMEM lane quadrant, which half of the columns
+        const int r = quad * 32 + lane;
+        const uint32_t lane_base = uint32_t(quad * 32) << 16;
+        constexpr int CG_PER_HALF = (NB / 32 + 1) / 2;       // 32-column groups per epilogue half
         uint32_t acc_it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t g = int64_t(tile) * TILE_G + r;
-            const RowGeo rg = row_setup(g, G, grid, mic, M, cx0, cy0, cz0, steering);
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");   // table of this tile is complete
             double acc_map = 0.0;
             for (int fi = 0; fi < nbins; ++fi) {
                 const double q = freqs[fi] * inv_c;
@@ -291,39 +318,50 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, int M, int nbins, const 
                     tc_fence_after();
                     const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N;
 #pragma unroll 1
-                    for (int cg = 0; cg < NB / 32; ++cg) {
-                        const int n0 = nbk * NB + cg * 32;
-                        if (n0 >= M) break;
-                        float tr[32], ti[32];
-                        tmem_ld32(tcol + cg * 32, tr);
-                        tmem_ld32(tcol + NB + cg * 32, ti);
+                    for (int c = 0; c < 2 * CG_PER_HALF; ++c) {          // 16 columns (microphones) at a time
+                        const int col = half * CG_PER_HALF * 32 + c * 16;
+                        const int n0 = nbk * NB + col;
+                        if (col >= NB || n0 >= Mk) break;
+                        float tr[16], ti[16];
+                        tmem_ld16(tcol + col, tr);
+                        tmem_ld16(tcol + NB + col, ti);
+                        // (r, a) of the 16 microphones n0 .. n0+15 of this row (two 64-byte runs)
+                        float4 ra[8];
+#pragma unroll
+                        for (int k8 = 0; k8 < 2; ++k8) {
+                            const float4 *src = reinterpret_cast<const float4 *>(tab + tab_index(n0 + 8 * k8, r));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) ra[k8 * 4 + j] = __ldcg(src + j);
+                        }
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            const int n = n0 + j;
-                            if (n < M) {
-                                const float2 h = steer(rg, micf[n], micf[MAX_MICS + n], micf[2 * MAX_MICS + n], bf);
-                                p0 = fmaf(tr[j], h.x, p0);
-                                p0 = fmaf(-ti[j], h.y, p0);
-                            }
-                            if (n + 1 < M) {
-                                const float2 h = steer(rg, micf[n + 1], micf[MAX_MICS + n + 1], micf[2 * MAX_MICS + n + 1], bf);
-                                p1 = fmaf(tr[j + 1], h.x, p1);
-                                p1 = fmaf(-ti[j + 1], h.y, p1);
-                            }
+                        for (int j = 0; j < 8; ++j) {
+                            // padded microphones carry amplitude 0, so no bounds test is needed
+                            const float2 h0 = steer(make_float2(ra[j].x, ra[j].y), bf);
+                            const float2 h1 = steer(make_float2(ra[j].z, ra[j].w), bf);
+                            p0 = fmaf(tr[2 * j], h0.x, p0);
+                            p0 = fmaf(-ti[2 * j], h0.y, p0);
+                            p1 = fmaf(tr[2 * j + 1], h1.x, p1);
+                            p1 = fmaf(-ti[2 * j + 1], h1.y, p1);
                         }
                     }
                     tc_fence_before();
                     mbar_arrive(&tempty[buf]);
                 }
-                double p = double(p0) + double(p1);
-                if (clamp_negative && p < 0.0) p = 0.0;                         // beamforming.py:871-872
-                acc_map += weights[fi] * p;                                       // :875-876
-                if (per_bin != nullptr && g < G) per_bin[g * nbins + fi] = p;
+                // combine the two column halves of this row
+                float *pp = part + (fi & 1) * TILE_G;
+                if (half == 1) pp[r] = p0 + p1;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (half == 0) {
+                    double p = double(p0 + p1) + double(pp[r]);
+                    if (clamp_negative && p < 0.0) p = 0.0;                         // beamforming.py:871-872
+                    acc_map += weights[fi] * p;                                       // :875-876
+                    if (per_bin != nullptr && g < G) per_bin[g * nbins + fi] = p;
+                }
             }
-            if (g < G) map_out[g] = acc_map;
+            if (half == 0 && g < G) map_out[g] = acc_map;
         }
-    } else if (warp == 8) {
+    } else if (warp == 16) {
         // =========================== MMA issue (one thread) ===========================
         if (lane == 0) {
             constexpr uint32_t IDESC = idesc_tf32(TILE_G, UMMA_N);
@@ -384,7 +422,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, int M, int nbins, const 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 8) tmem_dealloc(tmem_base, CF::TMEM_COLS);
+    if (warp == 16) tmem_dealloc(tmem_base, CF::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------- K3a for the tensor-core path
@@ -426,6 +464,13 @@ __global__ void das_prepare_tc_kernel(const double2 *__restrict__ csm, int M, in
     }
 }
 
+template <int PASSES> int64_t images_bytes(int M, int nbins) {
+    const int NKC = (M + KCH - 1) / KCH;
+    const int nb = tc_nb(M), NBLK = (M + nb - 1) / nb;
+    const int64_t btile = 2 * nb * 128;
+    return int64_t(nbins) * NBLK * NKC * (PASSES == 3 ? 2 : 1) * btile;
+}
+
 template <int NB, int PASSES>
 int launch_prepare(const void *csm, int M, int bin0, int nbins, int remove_diag, void *op, cudaStream_t st) {
     using CF = TcCfg<NB, PASSES>;
@@ -455,8 +500,10 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
     }
     const int64_t ntiles = (G + TILE_G - 1) / TILE_G;
     B2_REQUIRE(ntiles <= 0x7fffffff, B2_EINVAL, "b2_das_map: too many grid points");
-    const int nblocks = int(ntiles < num_sms ? ntiles : num_sms);      // persistent: one CTA per SM
-    kern<<<nblocks, TC_THREADS, CF::SMEM, st>>>((const unsigned char *)op, M, nbins, (const double *)freqs,
+    int nblocks = int(ntiles < num_sms ? ntiles : num_sms);            // persistent: one CTA per SM
+    if (nblocks > MAX_CTAS) nblocks = MAX_CTAS;
+    float2 *scratch = reinterpret_cast<float2 *>((unsigned char *)op + images_bytes<PASSES>(M, nbins));
+    kern<<<nblocks, TC_THREADS, CF::SMEM, st>>>((const unsigned char *)op, scratch, M, nbins, (const double *)freqs,
                                                 (const double *)weights, 1.0 / c, (const double *)mic, center[0],
                                                 center[1], center[2], (const double *)grid, G, steering,
                                                 clamp_negative, (double *)map_out, (double *)per_bin, int(ntiles));
@@ -466,9 +513,8 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
 
 template <int PASSES> int64_t operand_bytes(int M, int nbins) {
     const int NKC = (M + KCH - 1) / KCH;
-    const int nb = tc_nb(M), NBLK = (M + nb - 1) / nb;
-    const int64_t btile = 2 * nb * 128;
-    return int64_t(nbins) * NBLK * NKC * (PASSES == 3 ? 2 : 1) * btile;
+    // operand images + one (r, a) table of 128 x Mk float2 per persistent CTA
+    return images_bytes<PASSES>(M, nbins) + int64_t(MAX_CTAS) * TILE_G * NKC * KCH * 8;
 }
 
 }  // namespace
