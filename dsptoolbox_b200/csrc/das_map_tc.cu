@@ -11,10 +11,14 @@
 // is a real GEMM  D[128 x 2NB] = A[128 x 2M] * B^T  with
 //     A[g, 2m+{0,1}]   = (Re, Im) of H[g, m] = a_gm exp(-i k_f r_gm)   synthesised by 4 warps
 //                        straight into the 128B-swizzled K-major shared-memory operand tile,
-//     B[n,      2m+{0,1}] = ( Re L[m,n],  Im L[m,n])                    -> D[:, n]      = Re T
-//     B[NB + n, 2m+{0,1}] = ( Im L[m,n], -Re L[m,n])                    -> D[:, NB + n] = Im T
+//     B[2n,     2m+{0,1}] = ( Re L[m,n],  Im L[m,n])                    -> D[:, 2n]     = Re T
+//     B[2n + 1, 2m+{0,1}] = ( Im L[m,n], -Re L[m,n])                    -> D[:, 2n + 1] = Im T
 // (operand images pre-swizzled by b2_das_prepare and streamed with cp.async.bulk), accumulated
-// in TMEM as fp32.  K chunks (16 microphones) that lie entirely above the diagonal are skipped.
+// in TMEM as fp32.  L is lower triangular: K chunks (16 microphones) entirely above the diagonal
+// are skipped, and a chunk that straddles it only touches its first w = 16, 32, ... columns, so
+// the MMA is issued with N = 2w and only the first 2w operand rows are fetched.  Chunks are
+// walked from the last one down so that the first MMA of an accumulator (the one that
+// overwrites instead of accumulating) is the widest.
 // The epilogue warps read D back with tcgen05.ld, re-synthesise H[g, n] and reduce
 //     P[g, f] = sum_n Re(T[g, n] H[g, n]),   clamp,   map[g] += w_f P[g, f]
 // while the next column block accumulates into the second TMEM buffer.
@@ -261,7 +265,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scr
                 bf.q_hi = float(q);
                 bf.q_lo = float(q - double(bf.q_hi));
                 for (int nbk = 0; nbk < NBLK; ++nbk) {
-                    for (int kc = (nbk * NB) / KCH; kc < NKC; ++kc, ++it) {
+                    for (int kc = NKC - 1; kc >= (nbk * NB) / KCH; --kc, ++it) {
                         const int s = it % NSTAGE;
                         // (r, a) of this thread's 8 microphones: 64 contiguous bytes, coalesced over rows
                         const float4 *src = reinterpret_cast<const float4 *>(tab + tab_index(kc * KCH + half * 8, r));
@@ -322,9 +326,8 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scr
                         const int col = half * CG_PER_HALF * 32 + c * 16;
                         const int n0 = nbk * NB + col;
                         if (col >= NB || n0 >= Mk) break;
-                        float tr[16], ti[16];
-                        tmem_ld16(tcol + col, tr);
-                        tmem_ld16(tcol + NB + col, ti);
+                        float t[32];                                     // (Re T, Im T) of 16 columns n
+                        tmem_ld32(tcol + 2 * col, t);
                         // (r, a) of the 16 microphones n0 .. n0+15 of this row (two 64-byte runs)
                         float4 ra[8];
 #pragma unroll
@@ -339,10 +342,10 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scr
                             // padded microphones carry amplitude 0, so no bounds test is needed
                             const float2 h0 = steer(make_float2(ra[j].x, ra[j].y), bf);
                             const float2 h1 = steer(make_float2(ra[j].z, ra[j].w), bf);
-                            p0 = fmaf(tr[2 * j], h0.x, p0);
-                            p0 = fmaf(-ti[2 * j], h0.y, p0);
-                            p1 = fmaf(tr[2 * j + 1], h1.x, p1);
-                            p1 = fmaf(-ti[2 * j + 1], h1.y, p1);
+                            p0 = fmaf(t[4 * j], h0.x, p0);
+                            p0 = fmaf(-t[4 * j + 1], h0.y, p0);
+                            p1 = fmaf(t[4 * j + 2], h1.x, p1);
+                            p1 = fmaf(-t[4 * j + 3], h1.y, p1);
                         }
                     }
                     tc_fence_before();
@@ -364,7 +367,6 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scr
     } else if (warp == 16) {
         // =========================== MMA issue (one thread) ===========================
         if (lane == 0) {
-            constexpr uint32_t IDESC = idesc_tf32(TILE_G, UMMA_N);
             uint32_t it = 0, acc_it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int fi = 0; fi < nbins; ++fi) {
@@ -374,8 +376,11 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scr
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + buf * UMMA_N;
                         const int kc0 = (nbk * NB) / KCH;
-                        for (int kc = kc0; kc < NKC; ++kc, ++it) {
+                        for (int kc = NKC - 1; kc >= kc0; --kc, ++it) {
                             const int s = it % NSTAGE;
+                            // columns of this block that chunk kc can reach (lower triangle): w, N = 2w
+                            const int w = min(NB, KCH * (kc - kc0 + 1));
+                            const uint32_t idesc = idesc_tf32(TILE_G, 2 * w);
                             mbar_wait(&full[s], (it / NSTAGE) & 1);
                             tc_fence_after();
                             const uint64_t a_hi = smem_desc_sw128(smem_u32(a_tile(s, 0)));
@@ -385,10 +390,10 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scr
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {              // UMMA K = 8 tf32 = 32 bytes
                                 const uint64_t adv = uint64_t(ks * 2);    // (32 B) >> 4
-                                umma_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC, (kc > kc0 || ks > 0) ? 1u : 0u);
+                                umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kc < NKC - 1 || ks > 0) ? 1u : 0u);
                                 if (PASSES == 3) {
-                                    umma_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC, 1u);
-                                    umma_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+                                    umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                                    umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
                                 }
                             }
                             umma_commit(&empty[s]);                       // frees the stage when the MMAs retire
@@ -406,12 +411,16 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scr
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int fi = 0; fi < nbins; ++fi) {
                     for (int nbk = 0; nbk < NBLK; ++nbk) {
-                        for (int kc = (nbk * NB) / KCH; kc < NKC; ++kc, ++it) {
+                        const int kc0 = (nbk * NB) / KCH;
+                        for (int kc = NKC - 1; kc >= kc0; --kc, ++it) {
                             const int s = it % NSTAGE;
+                            const int w = min(NB, KCH * (kc - kc0 + 1));
+                            const uint32_t bytes = uint32_t(2 * w) * 128;          // first 2w rows of each image
                             mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
                             const unsigned char *src = op + size_t(fi) * bin_bytes + (size_t(nbk) * NKC + kc) * (CF::NSPLIT * CF::B_TILE);
-                            mbar_arrive_expect_tx(&full[s], CF::NSPLIT * CF::B_TILE);
-                            bulk_g2s(b_tile(s, 0), src, CF::NSPLIT * CF::B_TILE, &full[s]);
+                            mbar_arrive_expect_tx(&full[s], CF::NSPLIT * bytes);
+                            bulk_g2s(b_tile(s, 0), src, bytes, &full[s]);
+                            if (PASSES == 3) bulk_g2s(b_tile(s, 1), src + CF::B_TILE, bytes, &full[s]);
                         }
                     }
                 }
@@ -435,8 +444,8 @@ __global__ void das_prepare_tc_kernel(const double2 *__restrict__ csm, int M, in
     if (row >= CF::UMMA_N) return;
     const int kc = blockIdx.y % NKC, nbk = blockIdx.y / NKC;
     const int fi = blockIdx.z;
-    const bool imag_row = row >= NB;
-    const int n = nbk * NB + (imag_row ? row - NB : row);
+    const bool imag_row = row & 1;                                // rows alternate Re T / Im T of column n
+    const int n = nbk * NB + (row >> 1);
     unsigned char *tile = op + ((size_t(fi) * NBLK + nbk) * NKC + kc) * size_t(CF::NSPLIT * CF::B_TILE);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
