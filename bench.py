@@ -207,9 +207,10 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------- B200 arm
-def tf32_peak(torch):
-    """cuBLAS TF32 GEMM throughput (8192^3, best of 5) -- the tensor roofline denominator that
-    MEASURED_PEAKS.json (bf16 only) does not carry."""
+def tf32_peak(torch, sustained_seconds=2.5):
+    """cuBLAS TF32 GEMM throughput (8192^3): best of 5 (burst) and a back-to-back loop of
+    `sustained_seconds` (sustained, under the power cap) -- the tensor roofline denominators that
+    MEASURED_PEAKS.json (bf16 only) does not carry.  Returns (burst, sustained) in TFLOP/s."""
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     a = torch.randn(8192, 8192, device="cuda"); b = torch.randn(8192, 8192, device="cuda")
@@ -220,9 +221,16 @@ def tf32_peak(torch):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); a @ b; e.record(); torch.cuda.synchronize()
         best = min(best, s.elapsed_time(e))
+    n = max(8, int(sustained_seconds * 1e3 / best))
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n):
+        a @ b
+    e.record(); torch.cuda.synchronize()
+    sustained = 2 * 8192 ** 3 * n / s.elapsed_time(e) / 1e9
     torch.backends.cuda.matmul.allow_tf32 = prev
     del a, b
-    return 2 * 8192 ** 3 / best / 1e9
+    return 2 * 8192 ** 3 / best / 1e9, sustained
 
 
 def run_b200(args):
@@ -424,7 +432,10 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    peak_tf32 = tf32_peak(torch)
+    peak_tf32_burst, peak_tf32_sustained = tf32_peak(torch)
+    # the map kernel runs for seconds under the 1 kW cap: the sustained figure is its denominator;
+    # a kernel shorter than ~0.5 s is compared with the burst figure
+    peak_tf32 = peak_tf32_sustained if ms_map_kernel > 500.0 else peak_tf32_burst
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -439,7 +450,7 @@ def run_b200(args):
     roofline = {"kernel": f"das_map[{mode_name}]", "bound": "tensor", "achieved": achieved, "peak": tensor_peak,
                 "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": None,
                 "algorithmic_flops_per_launch": alg_flops, "kernel_ms": ms_map_kernel,
-                "peak_source": f"cuBLAS TF32 8192^3 measured in this run = {peak_tf32:.1f} TFLOP/s"
+                "peak_source": f"cuBLAS TF32 8192^3 measured in this run: burst {peak_tf32_burst:.1f}, sustained {peak_tf32_sustained:.1f} TFLOP/s; used {peak_tf32:.1f}"
                                + (" / 3 (split-TF32: three tensor products per algorithmic product)" if passes == 3 else "")
                                + f"; MEASURED_PEAKS bf16 {peaks.get('bf16_tflops')} (of {'measured' if peaks else 'fallback'})"}
     s_in, s_x = (8, 16) if engine.config.csm_precision == "fp64" else (4, 8)

@@ -164,36 +164,50 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
 __host__ __device__ __forceinline__ int sw128_offset(int r, int j) { return (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4); }
 
 // ---------------------------------------------------------------- per-tile geometry table
-// tab[((kc*2 + half)*128 + row)*8 + i] = (r, a) of microphone m = kc*16 + half*8 + i for grid
-// point `row` of the tile: r = |grid - mic| and a = |h| of beamforming.py:1515-1703.
+// tab[((m >> 3) * 128 + row) * 8 + (m & 7)] = r = |grid_row - mic_m| (fp32 of an fp64 result): the
+// bin-independent part of the steering phase.  The amplitude follows from r and three per-row
+// constants, |h| = c0 + c1 / r + c2 * r  (the four formulations of beamforming.py:1515-1703).
 __device__ __forceinline__ int tab_index(int m, int row) { return (((m >> 3) * TILE_G) + row) * 8 + (m & 7); }
 
-// Fill the (r, a) entries of microphones with ((m >> 3) & 1) == half for one grid point.
-__device__ __forceinline__ void row_table(float2 *__restrict__ tab, int row, int half, int64_t g, int64_t G,
-                                          const double *__restrict__ grid, const double *__restrict__ mic, int M,
-                                          int Mk, double cx0, double cy0, double cz0, int steering) {
+struct RowAmp { float c0, c1, c2; };
+
+// Fill r for the microphones with ((m >> 3) & 1) == half of one grid point; returns the row's
+// amplitude constants.  Padded microphones get r = 1 (their operand columns are zero anyway).
+__device__ __forceinline__ RowAmp row_table(float *__restrict__ tab, int row, int half, bool write, int64_t g,
+                                            int64_t G, const double *__restrict__ grid,
+                                            const double *__restrict__ mic, int M, int Mk, double cx0, double cy0,
+                                            double cz0, int steering) {
+    RowAmp ra;
+    ra.c0 = ra.c1 = ra.c2 = 0.f;
     const bool valid = g < G;
-    double x = 0, y = 0, z = 0, s = 0.0, r0 = 1.0;
+    double x = 0, y = 0, z = 0;
     if (valid) {
         x = grid[3 * g]; y = grid[3 * g + 1]; z = grid[3 * g + 2];
+        double s = 0.0;
         for (int m = 0; m < M; ++m) {
             const double dx = x - mic[3 * m], dy = y - mic[3 * m + 1], dz = z - mic[3 * m + 2];
             s += 1.0 / (dx * dx + dy * dy + dz * dz);
         }
-        r0 = das_distance(x, y, z, cx0, cy0, cz0);
-    }
-    for (int m8 = half * 8; m8 < Mk; m8 += 16) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = m8 + i;
-            float2 v = make_float2(1.0f, 0.0f);
-            if (valid && m < M) {
-                const double r = das_distance(x, y, z, mic[3 * m], mic[3 * m + 1], mic[3 * m + 2]);
-                v = make_float2(float(r), float(das_amplitude(steering, r, r0, s, M)));
-            }
-            tab[tab_index(m, row)] = v;
+        const double r0 = das_distance(x, y, z, cx0, cy0, cz0);
+        switch (steering) {
+        case B2_STEER_CLASSIC: ra.c0 = float(1.0 / double(M)); break;
+        case B2_STEER_INVERSE: ra.c2 = float(1.0 / (double(M) * r0)); break;
+        case B2_STEER_TRUE_POWER: ra.c1 = float(1.0 / (r0 * s)); break;
+        default: ra.c1 = float(1.0 / sqrt(double(M) * s)); break;
         }
     }
+    if (write) {
+        for (int m8 = half * 8; m8 < Mk; m8 += 16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m8 + i;
+                float v = 1.0f;
+                if (valid && m < M) v = float(das_distance(x, y, z, mic[3 * m], mic[3 * m + 1], mic[3 * m + 2]));
+                tab[tab_index(m, row)] = v;
+            }
+        }
+    }
+    return ra;
 }
 
 struct BinF {               // frequency / c as compensated floats:  f/c = q_hi + q_lo  (cycles per metre)
@@ -201,20 +215,27 @@ struct BinF {               // frequency / c as compensated floats:  f/c = q_hi 
 };
 
 // H[g, m] = a exp(-i 2 pi (f/c) r): returns (Re, Im); the phase (in cycles) is reduced exactly.
-__device__ __forceinline__ float2 steer(float2 ra, BinF b) {
-    const float r = ra.x;
+__device__ __forceinline__ float2 steer(float r, const RowAmp &amp, BinF b) {
     const float p = b.q_hi * r;
     const float e = fmaf(b.q_lo, r, fmaf(b.q_hi, r, -p));
-    const float fr = (p - rintf(p)) + e;
+    const float rn = (p + 12582912.0f) - 12582912.0f;         // round to nearest integer (|p| < 2^22)
+    const float fr = (p - rn) + e;
     float sn, cs;
     __sincosf(6.28318530717958647692f * fr, &sn, &cs);
-    return make_float2(ra.y * cs, -ra.y * sn);
+    float rinv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r));
+    const float a = fmaf(amp.c2, r, fmaf(amp.c1, rinv, amp.c0));
+    return make_float2(a * cs, -a * sn);
+}
+
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // ---------------------------------------------------------------- the kernel
 template <int NB, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scratch, int M, int nbins,
+das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scratch, int M, int nbins,
                   const double *__restrict__ freqs, const double *__restrict__ weights, double inv_c,
                   const double *__restrict__ mic, double cx0, double cy0, double cz0,
                   const double *__restrict__ grid, int64_t G, int steering, int clamp_negative,
@@ -232,7 +253,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scr
     const int NKC = (M + KCH - 1) / KCH;          // K chunks
     const int Mk = NKC * KCH;
     const int NBLK = (M + NB - 1) / NB;           // column blocks
-    float2 *tab = scratch + size_t(blockIdx.x) * TILE_G * Mk;
+    float *tab = scratch + size_t(blockIdx.x) * TILE_G * Mk;
 
     // stage s: [A_hi][A_lo?][B_hi][B_lo?]
     auto a_tile = [&](int s, int split) { return smem + s * CF::STAGE + split * A_TILE; };
@@ -252,44 +273,54 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scr
     if (warp < 8) {
         // =========================== steering synthesis -> A operand tiles ===========================
         const int r = tid & 127, half = tid >> 7;            // row of the tile, which 8 of a chunk's 16 mics
+        const uint32_t a_base = smem_u32(smem);
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             // the epilogue warps are done with the previous tile's table before it is overwritten
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            row_table(tab, r, half, int64_t(tile) * TILE_G + r, G, grid, mic, M, Mk, cx0, cy0, cz0, steering);
+            const RowAmp amp = row_table(tab, r, half, true, int64_t(tile) * TILE_G + r, G, grid, mic, M, Mk, cx0, cy0,
+                                         cz0, steering);
             __threadfence_block();
             asm volatile("bar.sync 1, 512;" ::: "memory");
+            // distances of this thread's 8 microphones of a chunk: 32 contiguous bytes, coalesced over rows
+            auto load_r = [&](int kc, float4 &lo, float4 &hi) {
+                const float4 *src = reinterpret_cast<const float4 *>(tab + tab_index(kc * KCH + half * 8, r));
+                lo = __ldcg(src);
+                hi = __ldcg(src + 1);
+            };
+            float4 r_lo, r_hi;
+            load_r(NKC - 1, r_lo, r_hi);
             for (int fi = 0; fi < nbins; ++fi) {
                 const double q = freqs[fi] * inv_c;
                 BinF bf;
                 bf.q_hi = float(q);
                 bf.q_lo = float(q - double(bf.q_hi));
                 for (int nbk = 0; nbk < NBLK; ++nbk) {
-                    for (int kc = NKC - 1; kc >= (nbk * NB) / KCH; --kc, ++it) {
+                    const int kc0 = (nbk * NB) / KCH;
+                    for (int kc = NKC - 1; kc >= kc0; --kc, ++it) {
                         const int s = it % NSTAGE;
-                        // (r, a) of this thread's 8 microphones: 64 contiguous bytes, coalesced over rows
-                        const float4 *src = reinterpret_cast<const float4 *>(tab + tab_index(kc * KCH + half * 8, r));
-                        float4 ra[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) ra[j] = __ldcg(src + j);
+                        const float rr[8] = {r_lo.x, r_lo.y, r_lo.z, r_lo.w, r_hi.x, r_hi.y, r_hi.z, r_hi.w};
+                        // prefetch the next chunk's distances (the walk only depends on kc)
+                        int kn = kc - 1;
+                        if (kn < kc0) kn = NKC - 1;
+                        load_r(kn, r_lo, r_hi);
                         float4 hi4[4], lo4[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float2 h0 = steer(make_float2(ra[j].x, ra[j].y), bf);
-                            const float2 h1 = steer(make_float2(ra[j].z, ra[j].w), bf);
+                            const float2 h0 = steer(rr[2 * j], amp, bf);
+                            const float2 h1 = steer(rr[2 * j + 1], amp, bf);
                             hi4[j] = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
-                            if (PASSES == 3)
-                                lo4[j] = make_float4(to_tf32(h0.x - hi4[j].x), to_tf32(h0.y - hi4[j].y),
-                                                     to_tf32(h1.x - hi4[j].z), to_tf32(h1.y - hi4[j].w));
+                            if (PASSES == 3)   // residuals are exact in fp32; the tensor core keeps their top 11 bits
+                                lo4[j] = make_float4(h0.x - hi4[j].x, h0.y - hi4[j].y, h1.x - hi4[j].z, h1.y - hi4[j].w);
                         }
                         mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
-                        unsigned char *ahi = a_tile(s, 0);
-                        unsigned char *alo = a_tile(s, CF::NSPLIT - 1);
+                        const uint32_t ahi = a_base + s * CF::STAGE;
+                        const uint32_t alo = ahi + (CF::NSPLIT - 1) * A_TILE;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int off = sw128_offset(r, half * 4 + j);
-                            *reinterpret_cast<float4 *>(ahi + off) = hi4[j];
-                            if (PASSES == 3) *reinterpret_cast<float4 *>(alo + off) = lo4[j];
+                            sts128(ahi + off, hi4[j]);
+                            if (PASSES == 3) sts128(alo + off, lo4[j]);
                         }
                         fence_proxy_async();                 // generic-proxy writes -> visible to the MMA (async proxy)
                         mbar_arrive(&full[s]);
@@ -308,6 +339,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scr
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t g = int64_t(tile) * TILE_G + r;
             asm volatile("bar.sync 1, 512;" ::: "memory");
+            const RowAmp amp = row_table(tab, r, 0, false, g, G, grid, mic, M, Mk, cx0, cy0, cz0, steering);
             asm volatile("bar.sync 1, 512;" ::: "memory");   // table of this tile is complete
             double acc_map = 0.0;
             for (int fi = 0; fi < nbins; ++fi) {
@@ -328,24 +360,28 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float2 *__restrict__ scr
                         if (col >= NB || n0 >= Mk) break;
                         float t[32];                                     // (Re T, Im T) of 16 columns n
                         tmem_ld32(tcol + 2 * col, t);
-                        // (r, a) of the 16 microphones n0 .. n0+15 of this row (two 64-byte runs)
-                        float4 ra[8];
+                        // distances of the 16 microphones n0 .. n0+15 of this row (two 32-byte runs)
+                        float4 rq[4];
 #pragma unroll
                         for (int k8 = 0; k8 < 2; ++k8) {
                             const float4 *src = reinterpret_cast<const float4 *>(tab + tab_index(n0 + 8 * k8, r));
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) ra[k8 * 4 + j] = __ldcg(src + j);
+                            rq[2 * k8] = __ldcg(src);
+                            rq[2 * k8 + 1] = __ldcg(src + 1);
                         }
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            // padded microphones carry amplitude 0, so no bounds test is needed
-                            const float2 h0 = steer(make_float2(ra[j].x, ra[j].y), bf);
-                            const float2 h1 = steer(make_float2(ra[j].z, ra[j].w), bf);
-                            p0 = fmaf(t[4 * j], h0.x, p0);
-                            p0 = fmaf(-t[4 * j + 1], h0.y, p0);
-                            p1 = fmaf(t[4 * j + 2], h1.x, p1);
-                            p1 = fmaf(-t[4 * j + 3], h1.y, p1);
+                        for (int j = 0; j < 4; ++j) {
+                            // padded microphones have all-zero operand rows, so T is 0 there: no bounds test
+                            const float2 h0 = steer(rq[j].x, amp, bf), h1 = steer(rq[j].y, amp, bf);
+                            const float2 h2 = steer(rq[j].z, amp, bf), h3 = steer(rq[j].w, amp, bf);
+                            p0 = fmaf(t[8 * j], h0.x, p0);
+                            p0 = fmaf(-t[8 * j + 1], h0.y, p0);
+                            p1 = fmaf(t[8 * j + 2], h1.x, p1);
+                            p1 = fmaf(-t[8 * j + 3], h1.y, p1);
+                            p0 = fmaf(t[8 * j + 4], h2.x, p0);
+                            p0 = fmaf(-t[8 * j + 5], h2.y, p0);
+                            p1 = fmaf(t[8 * j + 6], h3.x, p1);
+                            p1 = fmaf(-t[8 * j + 7], h3.y, p1);
                         }
                     }
                     tc_fence_before();
@@ -511,7 +547,7 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
     B2_REQUIRE(ntiles <= 0x7fffffff, B2_EINVAL, "b2_das_map: too many grid points");
     int nblocks = int(ntiles < num_sms ? ntiles : num_sms);            // persistent: one CTA per SM
     if (nblocks > MAX_CTAS) nblocks = MAX_CTAS;
-    float2 *scratch = reinterpret_cast<float2 *>((unsigned char *)op + images_bytes<PASSES>(M, nbins));
+    float *scratch = reinterpret_cast<float *>((unsigned char *)op + images_bytes<PASSES>(M, nbins));
     kern<<<nblocks, TC_THREADS, CF::SMEM, st>>>((const unsigned char *)op, scratch, M, nbins, (const double *)freqs,
                                                 (const double *)weights, 1.0 / c, (const double *)mic, center[0],
                                                 center[1], center[2], (const double *)grid, G, steering,
@@ -522,8 +558,8 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
 
 template <int PASSES> int64_t operand_bytes(int M, int nbins) {
     const int NKC = (M + KCH - 1) / KCH;
-    // operand images + one (r, a) table of 128 x Mk float2 per persistent CTA
-    return images_bytes<PASSES>(M, nbins) + int64_t(MAX_CTAS) * TILE_G * NKC * KCH * 8;
+    // operand images + one distance table of 128 x Mk floats per persistent CTA
+    return images_bytes<PASSES>(M, nbins) + int64_t(MAX_CTAS) * TILE_G * NKC * KCH * 4;
 }
 
 }  // namespace
