@@ -119,6 +119,57 @@ __device__ __forceinline__ void stockham_pass(cx<T> *s, const cx<T> *__restrict_
     __syncthreads();
 }
 
+// First pass fused with the load: every butterfly reads its R inputs straight from global memory
+// (frame samples x window, packed as complex pairs; coalesced because consecutive butterflies read
+// consecutive pairs), so the time-domain frame never makes a round trip through shared memory.
+template <typename T, int LOG2NC, int R>
+__device__ __forceinline__ void first_pass_from_global(cx<T> *s, const T *__restrict__ xrow, int step, int64_t k0,
+                                                       int64_t nframes, const T *__restrict__ window, int vec_ok,
+                                                       int tid) {
+    using G = Geo<T, LOG2NC>;
+    using C = cx<T>;
+    constexpr int NC = G::NC, J = NC / R;
+    constexpr int TOTAL = G::FR * J;
+    constexpr int ITEMS = (TOTAL + G::NT - 1) / G::NT;
+    C v[ITEMS][R];
+    const C *w2 = reinterpret_cast<const C *>(window);
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int item = tid + it * G::NT;
+        if (item < TOTAL) {
+            const int fr = item / J, j = item - fr * J;
+            const int64_t k = k0 + fr;
+            if (k < nframes) {
+                const T *src = xrow + k * int64_t(step);
+                if (vec_ok) {
+                    const C *src2 = reinterpret_cast<const C *>(src);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) v[it][r] = __ldg(src2 + j + r * J);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const C w = __ldg(w2 + j + r * J);
+                        v[it][r] = mk<T>(v[it][r].x * w.x, v[it][r].y * w.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int n = j + r * J;
+                        v[it][r] = mk<T>(src[2 * n] * window[2 * n], src[2 * n + 1] * window[2 * n + 1]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) v[it][r] = mk<T>(T(0), T(0));
+            }
+            dftR<T, R>(v[it]);
+            C *base = s + fr * G::PITCH;
+#pragma unroll
+            for (int r = 0; r < R; ++r) base[padidx(j * R + r)] = v[it][r];
+        }
+    }
+    __syncthreads();
+}
+
 // Run all passes: radix 8 while >= 8 points remain, then one radix 4 / 2 pass.
 template <typename T, int LOG2NC, int NS>
 __device__ __forceinline__ void stockham_all(cx<T> *s, const cx<T> *__restrict__ tw, int tid) {
@@ -141,80 +192,27 @@ welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframe
                   T scale, cx<T> *__restrict__ X, int M, int64_t Kp, int vec_ok) {
     using G = Geo<T, LOG2NC>;
     using C = cx<T>;
-    constexpr int NC = G::NC, FR = G::FR, NT = G::NT, NW = NT / 32;
+    constexpr int NC = G::NC, FR = G::FR, NT = G::NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *s = reinterpret_cast<C *>(smem_raw);
-    __shared__ T warp_part[NW];
-    __shared__ T frame_mean;
 
     const int tid = threadIdx.x;
-    const int m = blockIdx.x;                               // channel fastest: neighbours share a frame chunk
-    const int64_t k0 = int64_t(blockIdx.y) * FR;
+    // CTA order: frame group inside a 16-frame chunk fastest, then channel, then chunk -- the CTAs
+    // that complete one 16-frame run of the spectra layout run together (L2 merges their stores)
+    // and a whole wave stays inside one chunk window.
+    constexpr int GPC = 16 / (FR < 16 ? FR : 16);
+    const int64_t bid = blockIdx.x;
+    const int gi = int(bid % GPC);
+    const int64_t rest = bid / GPC;
+    const int m = int(rest % M);
+    const int64_t k0 = (rest / M) * 16 + int64_t(gi) * FR;
     const int64_t nb = NC + 1;
     const T *xrow = xc + int64_t(m) * Lp;
 
-    // ---- load + window (frames beyond nframes are all-zero) ----
-    for (int fr = 0; fr < FR; ++fr) {
-        const int64_t k = k0 + fr;
-        C *base = s + fr * G::PITCH;
-        if (k < nframes) {
-            const T *src = xrow + k * int64_t(step);
-            if (vec_ok) {
-                const C *src2 = reinterpret_cast<const C *>(src);
-                const C *w2 = reinterpret_cast<const C *>(window);
-                constexpr int PER = (NC + NT - 1) / NT;
-                constexpr int UN = PER < 8 ? PER : 8;
-                // issue UN independent loads before touching shared memory (memory-level parallelism)
-                for (int n0 = tid; n0 < NC; n0 += NT * UN) {
-                    C xv[UN], wv[UN];
-#pragma unroll
-                    for (int u = 0; u < UN; ++u) {
-                        const int n = n0 + u * NT;
-                        if (n < NC) { xv[u] = __ldg(src2 + n); wv[u] = __ldg(w2 + n); }
-                    }
-#pragma unroll
-                    for (int u = 0; u < UN; ++u) {
-                        const int n = n0 + u * NT;
-                        if (n < NC) base[padidx(n)] = mk<T>(xv[u].x * wv[u].x, xv[u].y * wv[u].y);
-                    }
-                }
-            } else {
-                for (int n = tid; n < NC; n += NT)
-                    base[padidx(n)] = mk<T>(src[2 * n] * window[2 * n], src[2 * n + 1] * window[2 * n + 1]);
-            }
-        } else {
-            for (int n = tid; n < NC; n += NT) base[padidx(n)] = mk<T>(T(0), T(0));
-        }
-    }
-    __syncthreads();
-
-    // ---- mean removal of the windowed (zero-padded) frame: _spectral_methods.py:136-137 ----
-    if (detrend) {
-        for (int fr = 0; fr < FR; ++fr) {
-            C *base = s + fr * G::PITCH;
-            T acc = T(0);
-            for (int n = tid; n < NC; n += NT) { C z = base[padidx(n)]; acc += z.x + z.y; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if ((tid & 31) == 0) warp_part[tid >> 5] = acc;
-            __syncthreads();
-            if (tid == 0) {
-                T tot = T(0);
-                for (int w = 0; w < NW; ++w) tot += warp_part[w];
-                frame_mean = tot / T(G::N);
-            }
-            __syncthreads();
-            const T mu = frame_mean;
-            for (int n = tid; n < NC; n += NT) {
-                C z = base[padidx(n)];
-                base[padidx(n)] = mk<T>(z.x - mu, z.y - mu);
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- wl/2-point complex FFT of every frame ----
-    stockham_all<T, LOG2NC, 1>(s, tw, tid);
+    // ---- wl/2-point complex FFT of every frame; the first pass reads global memory directly ----
+    constexpr int R1 = NC >= 8 ? 8 : NC;
+    first_pass_from_global<T, LOG2NC, R1>(s, xrow, step, k0, nframes, window, vec_ok, tid);
+    stockham_all<T, LOG2NC, R1>(s, tw, tid);
 
     // ---- untangle to the wl/2+1 real-FFT bins and store [bin][channel][frame] ----
     const T half = T(0.5) * scale;
@@ -227,6 +225,9 @@ welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframe
         C sum = cadd(a, b), dif = cmul(w, csub(a, b));
         // X = 0.5*(a+b) - 0.5*i*w*(a-b)
         C out = mk<T>((sum.x + dif.y) * half, (sum.y - dif.x) * half);
+        // Removing the frame mean (_spectral_methods.py:136-137) changes the DC bin only: the DFT of a
+        // constant vanishes at every other bin.  The reference's own DC value is rounding noise.
+        if (detrend && kf == 0) out = mk<T>(T(0), T(0));
         // spectra layout [frame chunk of 16][bin][channel][16 frames]: all CTAs of one frame chunk
         // write inside one (nb * M * 16)-element window, and the rank-K kernel reads whole tiles
         // of it as contiguous runs
@@ -312,8 +313,9 @@ int launch_rfft(const void *xc, int64_t Lp, int M, int step, int64_t nframes, co
     B2_REQUIRE(Kp % G::FR == 0, B2_EINVAL, "b2_welch_rfft: Kp=%lld must be a multiple of %d", (long long)Kp, G::FR);
     int vec_ok = (step % 2 == 0) && (Lp % 2 == 0) && (reinterpret_cast<uintptr_t>(xc) % (2 * sizeof(T)) == 0) &&
                  (reinterpret_cast<uintptr_t>(window) % (2 * sizeof(T)) == 0);
-    B2_REQUIRE(Kp % 16 == 0 && Kp / G::FR <= 65535, B2_EINVAL, "b2_welch_rfft: Kp=%lld must be a multiple of 16 (and at most %d)", (long long)Kp, 65535 * G::FR);
-    dim3 grid((unsigned)M, (unsigned)(Kp / G::FR));
+    const int64_t nblk = (Kp / G::FR) * int64_t(M);
+    B2_REQUIRE(Kp % 16 == 0 && nblk <= 0x7fffffff, B2_EINVAL, "b2_welch_rfft: Kp=%lld must be a multiple of 16 (grid too large otherwise)", (long long)Kp);
+    dim3 grid((unsigned)nblk);
     kern<<<grid, G::NT, G::SMEM, st>>>((const T *)xc, Lp, step, nframes, (const T *)window,
                                       (const cx<T> *)tw, detrend, T(scale), (cx<T> *)X, M, Kp, vec_ok);
     B2_LAUNCH_OK("b2_welch_rfft");
