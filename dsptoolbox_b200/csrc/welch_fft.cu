@@ -56,8 +56,32 @@ template <typename T> __device__ __forceinline__ void dft8(cx<T> *v) {
     v[2] = cadd(e2, w2); v[6] = csub(e2, w2);
     v[3] = cadd(e3, w3); v[7] = csub(e3, w3);
 }
+// 16-point DFT as 4 x 4: column DFT4s, twiddles W16^(n2*k1), row DFT4s; natural-order output.
+template <typename T> __device__ __forceinline__ void dft16(cx<T> *v) {
+    using C = cx<T>;
+    const T c1 = T(0.92387953251128675613), s1 = T(0.38268343236508977173);   // cos, sin(pi/8)
+    const T h = T(0.70710678118654752440);
+    C y[4][4];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        y[n2][0] = v[n2]; y[n2][1] = v[4 + n2]; y[n2][2] = v[8 + n2]; y[n2][3] = v[12 + n2];
+        dft4(y[n2][0], y[n2][1], y[n2][2], y[n2][3]);
+    }
+    // y[n2][k1] *= W16^(n2*k1), W16 = exp(-i pi/8)
+    auto mulw = [&](C a, T wr, T wi) { return mk<T>(a.x * wr - a.y * wi, a.x * wi + a.y * wr); };
+    y[1][1] = mulw(y[1][1], c1, -s1);  y[1][2] = mulw(y[1][2], h, -h);    y[1][3] = mulw(y[1][3], s1, -c1);
+    y[2][1] = mulw(y[2][1], h, -h);    y[2][2] = cmul_mi(y[2][2]);        y[2][3] = mulw(y[2][3], -h, -h);
+    y[3][1] = mulw(y[3][1], s1, -c1);  y[3][2] = mulw(y[3][2], -h, -h);   y[3][3] = mulw(y[3][3], -c1, s1);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        C a = y[0][k1], b = y[1][k1], c = y[2][k1], d = y[3][k1];
+        dft4(a, b, c, d);
+        v[k1] = a; v[k1 + 4] = b; v[k1 + 8] = c; v[k1 + 12] = d;
+    }
+}
 template <typename T, int R> __device__ __forceinline__ void dftR(cx<T> *v) {
-    if constexpr (R == 8) dft8<T>(v);
+    if constexpr (R == 16) dft16<T>(v);
+    else if constexpr (R == 8) dft8<T>(v);
     else if constexpr (R == 4) dft4(v[0], v[1], v[2], v[3]);
     else dft2(v[0], v[1]);
 }
@@ -91,12 +115,24 @@ __device__ __forceinline__ void stockham_pass(cx<T> *s, const cx<T> *__restrict_
                     v[it][1] = cmul(v[it][1], w1);
                     v[it][2] = cmul(v[it][2], w2);
                     v[it][3] = cmul(v[it][3], w3);
-                    if constexpr (R == 8) {
+                    if constexpr (R >= 8) {
                         const cx<T> w4 = cmul(w2, w2);
                         v[it][4] = cmul(v[it][4], w4);
                         v[it][5] = cmul(v[it][5], cmul(w4, w1));
                         v[it][6] = cmul(v[it][6], cmul(w4, w2));
                         v[it][7] = cmul(v[it][7], cmul(w4, w3));
+                        if constexpr (R == 16) {
+                            const cx<T> w8 = cmul(w4, w4);
+                            v[it][8] = cmul(v[it][8], w8);
+                            v[it][9] = cmul(v[it][9], cmul(w8, w1));
+                            v[it][10] = cmul(v[it][10], cmul(w8, w2));
+                            v[it][11] = cmul(v[it][11], cmul(w8, w3));
+                            const cx<T> w12 = cmul(w8, w4);
+                            v[it][12] = cmul(v[it][12], w12);
+                            v[it][13] = cmul(v[it][13], cmul(w12, w1));
+                            v[it][14] = cmul(v[it][14], cmul(w12, w2));
+                            v[it][15] = cmul(v[it][15], cmul(w12, w3));
+                        }
                     }
                 }
             }
@@ -170,14 +206,16 @@ __device__ __forceinline__ void first_pass_from_global(cx<T> *s, const T *__rest
     __syncthreads();
 }
 
-// Run all passes: radix 8 while >= 8 points remain, then one radix 4 / 2 pass.
+// Run the remaining passes: radix 16 while >= 16 points remain, then one radix 8 / 4 / 2 pass.
 template <typename T, int LOG2NC, int NS>
 __device__ __forceinline__ void stockham_all(cx<T> *s, const cx<T> *__restrict__ tw, int tid) {
     constexpr int NC = 1 << LOG2NC;
     constexpr int REM = NC / NS;
-    if constexpr (REM >= 8) {
+    if constexpr (REM >= 16) {
+        stockham_pass<T, LOG2NC, 16, NS>(s, tw, tid);
+        stockham_all<T, LOG2NC, NS * 16>(s, tw, tid);
+    } else if constexpr (REM == 8) {
         stockham_pass<T, LOG2NC, 8, NS>(s, tw, tid);
-        stockham_all<T, LOG2NC, NS * 8>(s, tw, tid);
     } else if constexpr (REM == 4) {
         stockham_pass<T, LOG2NC, 4, NS>(s, tw, tid);
     } else if constexpr (REM == 2) {
@@ -210,29 +248,33 @@ welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframe
     const T *xrow = xc + int64_t(m) * Lp;
 
     // ---- wl/2-point complex FFT of every frame; the first pass reads global memory directly ----
-    constexpr int R1 = NC >= 8 ? 8 : NC;
+    constexpr int R1 = NC >= 16 ? 16 : NC;
     first_pass_from_global<T, LOG2NC, R1>(s, xrow, step, k0, nframes, window, vec_ok, tid);
     stockham_all<T, LOG2NC, R1>(s, tw, tid);
 
-    // ---- untangle to the wl/2+1 real-FFT bins and store [bin][channel][frame] ----
+    // ---- untangle to the wl/2+1 real-FFT bins and store; bins k and wl/2-k share one pair of reads ----
+    // X[k] = 0.5 (a + conj b) - 0.5 i w_k (a - conj b),  a = Z[k], b = Z[NC-k], w_k = exp(-2 pi i k / wl)
+    // and, because w_{NC-k} = -conj(w_k), X[NC-k] = conj(0.5 (a + conj b) + 0.5 i w_k (a - conj b)).
+    // Spectra layout [frame chunk of 16][bin][channel][16 frames]: all CTAs of one frame chunk write
+    // inside one (nb * M * 16)-element window and the rank-K kernel reads whole tiles contiguously.
     const T half = T(0.5) * scale;
-    for (int idx = tid; idx < (NC + 1) * FR; idx += NT) {
-        const int fr = idx % FR, kf = idx / FR;
-        const C *base = s + fr * G::PITCH;
-        C a = base[padidx(kf & (NC - 1))];
-        C b = cconj(base[padidx((NC - kf) & (NC - 1))]);
-        C w = __ldg(tw + kf);
-        C sum = cadd(a, b), dif = cmul(w, csub(a, b));
-        // X = 0.5*(a+b) - 0.5*i*w*(a-b)
-        C out = mk<T>((sum.x + dif.y) * half, (sum.y - dif.x) * half);
+    auto store = [&](int kf, int fr, C out) {
         // Removing the frame mean (_spectral_methods.py:136-137) changes the DC bin only: the DFT of a
         // constant vanishes at every other bin.  The reference's own DC value is rounding noise.
         if (detrend && kf == 0) out = mk<T>(T(0), T(0));
-        // spectra layout [frame chunk of 16][bin][channel][16 frames]: all CTAs of one frame chunk
-        // write inside one (nb * M * 16)-element window, and the rank-K kernel reads whole tiles
-        // of it as contiguous runs
         const int64_t k = k0 + fr;
         X[(((k >> 4) * nb + kf) * M + m) * 16 + (k & 15)] = out;
+    };
+    for (int idx = tid; idx < (NC / 2 + 1) * FR; idx += NT) {
+        const int fr = idx % FR, kp = idx / FR;
+        const C *base = s + fr * G::PITCH;
+        const C a = base[padidx(kp)];
+        const C b = cconj(base[padidx((NC - kp) & (NC - 1))]);
+        const C w = __ldg(tw + kp);
+        const C sum = cadd(a, b), dif = cmul(w, csub(a, b));      // dif = w (a - conj b)
+        store(kp, fr, mk<T>((sum.x + dif.y) * half, (sum.y - dif.x) * half));
+        // partner bin NC - kp (kp = 0 gives the Nyquist bin; kp = NC/2 is its own partner)
+        if (2 * kp != NC) store(NC - kp, fr, mk<T>((sum.x - dif.y) * half, -(sum.y + dif.x) * half));
     }
 }
 
