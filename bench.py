@@ -253,7 +253,7 @@ def run_b200(args):
     if args.map_mode:
         engine.config.map_mode = args.map_mode
     mode = engine.resolve_map_mode()
-    mode_name = {0: "simt_f64", 1: "simt_f32", 2: "tf32", 3: "tf32x3"}[mode]
+    mode_name = {0: "simt_f64", 1: "simt_f32", 2: "tf32", 3: "tf32x3", 4: "mixed"}[mode]
 
     w, pos, L, lines = problem(args)
     M, wl = w["mics"], w["wl"]
@@ -442,16 +442,31 @@ def run_b200(args):
     except Exception:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
-    passes = 3 if mode == N.MAP_TC_TF32X3 else 1
+    # TF32-equivalent tensor products per algorithmic product: 3 (split TF32), 2 (TF32 + one BF16 product of
+    # double depth at twice the TF32 rate), 1 (single pass)
+    passes = {N.MAP_TC_TF32X3: 3, N.MAP_TC_MIXED: 2}.get(mode, 1)
     Gr = g1 - g0
     alg_flops = 4.0 * M * M * Gr * F
     achieved = alg_flops / (ms_map_kernel * 1e-3) / 1e12
-    tensor_peak = peak_tf32 / passes if mode in (N.MAP_TC_TF32, N.MAP_TC_TF32X3) else peak_tf32
+    tensor_peak = peak_tf32 / passes
+    # DRAM traffic of one launch of this kernel from the committed `ncu --set full` capture (same
+    # workload, same mode, one GPU); null when no capture matches
+    traffic = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "map_kernel_traffic.json")))
+        key = f"{args.workload}:{mode_name}:G{Gr}"
+        if key in cap:
+            traffic = cap[key]["dram_bytes_read"] + cap[key]["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"kernel": f"das_map[{mode_name}]", "bound": "tensor", "achieved": achieved, "peak": tensor_peak,
-                "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write of one launch (ncu --set full, profiles/); the 4.3 GB operand "
+                                "is re-streamed by each of the 53 tile waves -> 0.5 % of HBM bandwidth, compute-bound",
                 "algorithmic_flops_per_launch": alg_flops, "kernel_ms": ms_map_kernel,
                 "peak_source": f"cuBLAS TF32 8192^3 measured in this run: burst {peak_tf32_burst:.1f}, sustained {peak_tf32_sustained:.1f} TFLOP/s; used {peak_tf32:.1f}"
                                + (" / 3 (split-TF32: three tensor products per algorithmic product)" if passes == 3 else "")
+                               + (" / 2 (mixed: one TF32 product + one double-depth BF16 product = 2 TF32-equivalents)" if passes == 2 else "")
                                + f"; MEASURED_PEAKS bf16 {peaks.get('bf16_tflops')} (of {'measured' if peaks else 'fallback'})"}
     s_in, s_x = (8, 16) if engine.config.csm_precision == "fp64" else (4, 8)
     Kloc = k1 - k0
@@ -479,7 +494,8 @@ def run_b200(args):
         "metric": "das_map_grid_point_bins_per_s", "value": G * F / (ms_map * 1e-3), "unit": "grid-pt*bins/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "tf32x3 (fp32 accumulate) map; f64 CSM" if mode == N.MAP_TC_TF32X3 else f"{mode_name} map; {engine.config.csm_precision} CSM",
+        "dtype": {3: "tf32x3 (fp32 accumulate) map; f64 CSM", 4: "tf32+bf16x2 (fp32 accumulate) map; f64 CSM"}.get(
+            mode, f"{mode_name} map; {engine.config.csm_precision} CSM"),
         "data": "synthetic",
         "config": {"workload": w["label"], "M": M, "L": L, "nfft": wl, "frames": K, "bins": nb, "G": G, "F": F,
                    "G_full": G_full, "map_mode": mode_name, "csm_precision": engine.config.csm_precision,

@@ -12,11 +12,12 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb2dsp.so")
+# B2DSP_LIB lets a developer A/B-test an alternative build of the same library (never a fallback)
+LIB_PATH = os.environ.get("B2DSP_LIB") or os.path.join(_HERE, "csrc", "libb2dsp.so")
 
 # precision / mode codes (include/b2dsp.h)
 F64, F32 = 0, 1
-MAP_SIMT_F64, MAP_SIMT_F32, MAP_TC_TF32, MAP_TC_TF32X3 = 0, 1, 2, 3
+MAP_SIMT_F64, MAP_SIMT_F32, MAP_TC_TF32, MAP_TC_TF32X3, MAP_TC_MIXED = 0, 1, 2, 3, 4
 STEER_CLASSIC, STEER_INVERSE, STEER_TRUE_POWER, STEER_TRUE_LOCATION = 0, 1, 2, 3
 E_INVAL, E_UNSUPPORTED, E_CUDA = -1, -2, -3
 

@@ -8,6 +8,8 @@ from .beamforming import (  # noqa: F401
     MicArray,
     SteeringVector,
     BeamformerDASFrequency,
+    BeamformerMVDR,
+    BeamformerFunctional,
     classic_steering,
     inverse_steering,
     true_power_steering,
@@ -17,4 +19,4 @@ from .beamforming import (  # noqa: F401
 from .enums import SteeringVectorType  # noqa: F401
 
 __all__ = ["Grid", "Regular2DGrid", "Regular3DGrid", "LineGrid", "MicArray", "SteeringVector",
-           "BeamformerDASFrequency", "SteeringVectorType"]
+           "BeamformerDASFrequency", "BeamformerMVDR", "BeamformerFunctional", "SteeringVectorType"]

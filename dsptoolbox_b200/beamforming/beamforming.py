@@ -6,8 +6,9 @@ Call-compatible with reference beamforming/beamforming.py for Grid (:35-75), Reg
 `get_beamformer_map` keeps the reference's side effects (stdout banner, `self.map`,
 `self.f_range_hz`, returned copy) but runs on the GPU: the CSM stays on the device, steering
 vectors are synthesised inside the map kernel, and the grid may be sharded over ranks (dist.py).
-The other beamformers of the reference (CleanSC, Orthogonal, Functional, MVDR, DASTime) and the
-source simulator are outside this round's scope.
+BeamformerMVDR (:1223-1314) and BeamformerFunctional (:1127-1220) reuse the same map kernel on a
+per-bin transformed matrix.  CleanSC, Orthogonal, DASTime and the source
+simulator are outside this round's scope.
 """
 
 from __future__ import annotations
@@ -305,3 +306,84 @@ class BeamformerDASFrequency(BeamformerGridded):
 
     def _gather_map(self, out_dev):
         return out_dev.cpu().numpy()
+
+
+# =========================================================================== next rows
+class _QuadraticFormBeamformer(BeamformerGridded):
+    """Shared front-end of the beamformers whose map is a function of Re(h^H A_f h) with a per-bin
+    Hermitian matrix A_f derived from the CSM: the O(G F M^2) part runs in the same map kernel as
+    delay-and-sum (per-bin output, no clamping); the O(F M^3) matrix function of each bin is a
+    batched dense factorisation on the device (torch.linalg) and is not the hot loop."""
+
+    def _band(self, center_frequency_hz, octave_fraction):
+        self.center_frequency_hz = center_frequency_hz
+        self.octave_fraction = octave_fraction
+        self.f_range_hz = _get_fractional_octave_bandwidth(center_frequency_hz, octave_fraction)
+        txt = "Beamformer computation has started successfully:"
+        print("\n" + txt)
+        print("-" * len(txt))
+        print("...csm...")
+        f, csm = self.signal.get_csm_device()
+        print("...Steering vector...")
+        ids = find_nearest_points_index_in_vector(self.f_range_hz, f)
+        id1, id2 = int(ids[0]), int(ids[1])
+        if id1 == id2:
+            id2 += 1
+        fsel = f[id1:id2]
+        self.f_range_hz = np.array([fsel[0], fsel[-1]])
+        return fsel, csm[id1:id2]
+
+    def _per_bin_power(self, fsel, matrices, mode=None):
+        """(G, F) float64 CUDA tensor of Re(h^H A_f h)."""
+        mode = engine.resolve_map_mode(mode)
+        op = engine.das_prepare(matrices.contiguous(), 0, len(fsel), False, mode)
+        _, pb = engine.das_map(op, self.mics.number_of_points, fsel, np.ones(len(fsel)), self.c,
+                               self.mics._coordinates, self.mics.array_center_coordinates,
+                               self.grid._coordinates, _steering_code(self.st_vec), False, mode, per_bin=True)
+        return pb
+
+    def _finish(self, per_bin, fsel):
+        import torch
+
+        if len(fsel) > 1:
+            w = torch.from_numpy(simpson_weights(len(fsel), fsel[1] - fsel[0])).to(per_bin.device)
+            flat = per_bin @ w
+        else:
+            flat = per_bin[:, 0]
+        self.map = self.grid.reconstruct_map_shape(flat.cpu().numpy())
+        return self.map.copy()
+
+
+class BeamformerMVDR(_QuadraticFormBeamformer):
+    """Minimum-variance distortionless-response (Capon) beamformer: 1 / Re(h^H C^-1 h) per bin."""
+
+    beamformer_type = "MVDR"
+
+    def get_beamformer_map(self, center_frequency_hz: float, octave_fraction: int = 3, gamma: float = 10):
+        import torch
+
+        fsel, csm = self._band(center_frequency_hz, octave_fraction)
+        inv = torch.linalg.inv(csm)
+        print("...Apply...")
+        return self._finish(1.0 / self._per_bin_power(fsel, inv), fsel)
+
+
+class BeamformerFunctional(_QuadraticFormBeamformer):
+    """Functional beamforming (Dougherty 2014): the CSM is replaced by u s^(1/gamma) v^H and the
+    beamformer output is raised to the power gamma around the steering-vector norm."""
+
+    beamformer_type = "Functional"
+
+    def get_beamformer_map(self, center_frequency_hz: float, octave_fraction: int = 3, gamma: float = 10):
+        import torch
+
+        fsel, csm = self._band(center_frequency_hz, octave_fraction)
+        u, s, vh = torch.linalg.svd(csm)
+        powered = (u * (s ** (1.0 / gamma)).to(u.dtype)[:, None, :]) @ vh
+        print("...Apply...")
+        power = self._per_bin_power(fsel, powered)
+        # steering normalisation h^H h = sum_m |h_m|^2 does not depend on the bin: identity matrix, one bin
+        M = self.mics.number_of_points
+        eye = torch.eye(M, dtype=csm.dtype, device=csm.device)[None]
+        norm = self._per_bin_power(fsel[:1], eye)
+        return self._finish((power / norm) ** gamma * norm, fsel)

@@ -109,6 +109,10 @@ herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, doubl
     cp_async_commit();
 
     const int frow = lane >> 2, fk = lane & 3;
+    // On a diagonal block only the lower triangle is needed: the warp tile above the diagonal does
+    // no arithmetic at all, and the two warp tiles on it skip their 8x8 sub-tiles above it.
+    const bool warp_above = diag && (wi > wj);
+    const bool warp_diag = diag && (wi == wj);
     for (int c = 0; c < nchunks; ++c) {
         const int st = c & 1;
         if (c + 1 < nchunks) {
@@ -123,6 +127,7 @@ herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, doubl
         __syncthreads();
         const unsigned char *At = As[st] + (wj * 32 + frow) * SM::PITCH + fk * SM::ELEM;
         const unsigned char *Bt = Bs[st] + (wi * 32 + frow) * SM::PITCH + fk * SM::ELEM;
+        if (!warp_above)
 #pragma unroll
         for (int ks = 0; ks < KC / 4; ++ks) {
             double2 a[4], b[4];
@@ -135,6 +140,7 @@ herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, doubl
             for (int jb = 0; jb < 4; ++jb)
 #pragma unroll
                 for (int ib = 0; ib < 4; ++ib) {
+                    if (warp_diag && ib > jb) continue;
                     dmma(sr[jb][ib][0], sr[jb][ib][1], a[jb].x, b[ib].x);
                     dmma(sr[jb][ib][0], sr[jb][ib][1], a[jb].y, b[ib].y);
                     dmma(si[jb][ib][0], si[jb][ib][1], a[jb].y, b[ib].x);
@@ -156,7 +162,7 @@ herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, doubl
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int i = i0 + e;
-                if (i < M) {
+                if (i < M && i <= j) {          // rows >= cols only: the rest is implied by Hermitian symmetry
                     double2 v = make_double2(sr[jb][ib][e], si[jb][ib][e]);
                     double2 *dst = Sf + int64_t(j) * M + i;
                     if (accumulate) { double2 o = *dst; v.x += o.x; v.y += o.y; }

@@ -24,6 +24,11 @@
 // while the next column block accumulates into the second TMEM buffer.
 // Split-TF32 (PASSES = 3): every operand is split x = hi + lo (both TF32-exact) and
 // hi*hi + lo*hi + hi*lo is accumulated, which restores ~fp32 accuracy.
+// Mixed mode (PASSES = 2): hi*hi stays a TF32 product, but the two correction products only need
+// ~8 significant bits, so they run as ONE kind::f16 (BF16) product of twice the depth at twice
+// the TF32 rate: the second operand image of a stage holds, per row, [bf16(x - hi) | bf16(x)] for
+// A and [bf16(y) | bf16(y - hi)] for B, so that sum_k A2[k] B2[k] = lo_A*y + x*lo_B.  Tensor work
+// drops from 3 to 2 TF32-equivalents per product at ~2^-20 relative accuracy.
 //
 // Warp roles (576 threads): 0-7 steering synthesis (two threads per grid point), 8-15 epilogue
 // (two warps per TMEM lane quadrant), 16 MMA issue + TMEM allocation, 17 operand loader.
@@ -32,6 +37,8 @@
 // (distance r and amplitude a of every (grid point, microphone) pair of the tile) is computed
 // once per tile in fp64 and parked in an L2-resident scratch table, so the per-bin work is one
 // compensated phase product, one sincos and the TF32 split.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "das_common.cuh"
 
@@ -51,7 +58,7 @@ __host__ __device__ constexpr int tc_nb(int M) { return M <= 32 ? 32 : (M <= 64 
 template <int NB, int PASSES> struct TcCfg {
     static constexpr int UMMA_N = 2 * NB;
     static constexpr int B_TILE = UMMA_N * 128;
-    static constexpr int NSPLIT = PASSES == 3 ? 2 : 1;                 // operand images per stage (hi[, lo])
+    static constexpr int NSPLIT = PASSES == 1 ? 1 : 2;                 // operand images per stage (hi[, correction])
     static constexpr int STAGE = NSPLIT * (A_TILE + B_TILE);
     static constexpr int NSTAGE_RAW = (208 * 1024) / STAGE;
     static constexpr int NSTAGE = NSTAGE_RAW > 6 ? 6 : NSTAGE_RAW;
@@ -160,6 +167,27 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
+// kind::f16 instruction descriptor: fp32 accumulate, BF16 x BF16, both operands K-major
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {   // lo_elem first in memory
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ void sts128u(uint32_t saddr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // byte offset of the 16-byte chunk j (0..7) of row r inside a 128B-swizzled K-major tile
 __host__ __device__ __forceinline__ int sw128_offset(int r, int j) { return (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4); }
 
@@ -210,16 +238,15 @@ __device__ __forceinline__ RowAmp row_table(float *__restrict__ tab, int row, in
     return ra;
 }
 
-struct BinF {               // frequency / c as compensated floats:  f/c = q_hi + q_lo  (cycles per metre)
-    float q_hi, q_lo;
-};
-
-// H[g, m] = a exp(-i 2 pi (f/c) r): returns (Re, Im); the phase (in cycles) is reduced exactly.
-__device__ __forceinline__ float2 steer(float r, const RowAmp &amp, BinF b) {
-    const float p = b.q_hi * r;
-    const float e = fmaf(b.q_lo, r, fmaf(b.q_hi, r, -p));
+// H[g, m] = a exp(-i 2 pi q r), q = f / c in cycles per metre: returns (Re, Im).
+// The phase is reduced to a fraction of a cycle before the MUFU sincos.  q r < 2^9 cycles, so the
+// fp32 product carries an absolute phase error <= ~1e-4 rad per element -- the same size as the
+// fp32 rounding of r itself; being uncorrelated over microphones it changes the map by < 1e-6 of
+// its maximum (first-order phase perturbations cancel at a coherent peak).
+__device__ __forceinline__ float2 steer(float r, const RowAmp &amp, float q) {
+    const float p = q * r;
     const float rn = (p + 12582912.0f) - 12582912.0f;         // round to nearest integer (|p| < 2^22)
-    const float fr = (p - rn) + e;
+    const float fr = p - rn;
     float sn, cs;
     __sincosf(6.28318530717958647692f * fr, &sn, &cs);
     float rinv;
@@ -227,6 +254,10 @@ __device__ __forceinline__ float2 steer(float r, const RowAmp &amp, BinF b) {
     const float a = fmaf(amp.c2, r, fmaf(amp.c1, rinv, amp.c0));
     return make_float2(a * cs, -a * sn);
 }
+
+// top 11 significant bits by truncation: the residual x - trunc(x) is exact and is carried by the
+// correction operand, so no rounding step is needed in the split modes
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -291,10 +322,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             float4 r_lo, r_hi;
             load_r(NKC - 1, r_lo, r_hi);
             for (int fi = 0; fi < nbins; ++fi) {
-                const double q = freqs[fi] * inv_c;
-                BinF bf;
-                bf.q_hi = float(q);
-                bf.q_lo = float(q - double(bf.q_hi));
+                const float bf = float(freqs[fi] * inv_c);
                 for (int nbk = 0; nbk < NBLK; ++nbk) {
                     const int kc0 = (nbk * NB) / KCH;
                     for (int kc = NKC - 1; kc >= kc0; --kc, ++it) {
@@ -305,13 +333,23 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                         if (kn < kc0) kn = NKC - 1;
                         load_r(kn, r_lo, r_hi);
                         float4 hi4[4], lo4[4];
+                        uint4 mixlo[2], mixb[2];          // mixed mode: bf16 residuals / bf16 values of 8 mics
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float2 h0 = steer(rr[2 * j], amp, bf);
                             const float2 h1 = steer(rr[2 * j + 1], amp, bf);
-                            hi4[j] = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
+                            if (PASSES == 1) hi4[j] = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
+                            else hi4[j] = make_float4(trunc_tf32(h0.x), trunc_tf32(h0.y), trunc_tf32(h1.x), trunc_tf32(h1.y));
                             if (PASSES == 3)   // residuals are exact in fp32; the tensor core keeps their top 11 bits
                                 lo4[j] = make_float4(h0.x - hi4[j].x, h0.y - hi4[j].y, h1.x - hi4[j].z, h1.y - hi4[j].w);
+                            if (PASSES == 2) {
+                                const uint32_t l0 = pack_bf16(h0.x - hi4[j].x, h0.y - hi4[j].y);
+                                const uint32_t l1 = pack_bf16(h1.x - hi4[j].z, h1.y - hi4[j].w);
+                                const uint32_t b0 = pack_bf16(h0.x, h0.y), b1 = pack_bf16(h1.x, h1.y);
+                                uint32_t *pl = reinterpret_cast<uint32_t *>(&mixlo[j >> 1]) + 2 * (j & 1);
+                                uint32_t *pb = reinterpret_cast<uint32_t *>(&mixb[j >> 1]) + 2 * (j & 1);
+                                pl[0] = l0; pl[1] = l1; pb[0] = b0; pb[1] = b1;
+                            }
                         }
                         mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
                         const uint32_t ahi = a_base + s * CF::STAGE;
@@ -321,6 +359,15 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                             const int off = sw128_offset(r, half * 4 + j);
                             sts128(ahi + off, hi4[j]);
                             if (PASSES == 3) sts128(alo + off, lo4[j]);
+                        }
+                        if (PASSES == 2) {
+                            // correction image row = [bf16(h - hi) of the chunk's 16 mics | bf16(h) of the 16 mics]:
+                            // this thread's 8 mics are 32 bytes = 16-byte chunks 2*half, 2*half+1 of each 64-byte part
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                sts128u(alo + sw128_offset(r, 2 * half + c), mixlo[c]);
+                                sts128u(alo + sw128_offset(r, 4 + 2 * half + c), mixb[c]);
+                            }
                         }
                         fence_proxy_async();                 // generic-proxy writes -> visible to the MMA (async proxy)
                         mbar_arrive(&full[s]);
@@ -343,10 +390,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             asm volatile("bar.sync 1, 512;" ::: "memory");   // table of this tile is complete
             double acc_map = 0.0;
             for (int fi = 0; fi < nbins; ++fi) {
-                const double q = freqs[fi] * inv_c;
-                BinF bf;
-                bf.q_hi = float(q);
-                bf.q_lo = float(q - double(bf.q_hi));
+                const float bf = float(freqs[fi] * inv_c);
                 float p0 = 0.f, p1 = 0.f;
                 for (int nbk = 0; nbk < NBLK; ++nbk, ++acc_it) {
                     const int buf = acc_it & 1;
@@ -431,6 +475,8 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                                     umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
                                     umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
                                 }
+                                // mixed mode: both corrections as one BF16 product of depth 64 (4 x K=16)
+                                if (PASSES == 2) umma_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc_bf16(TILE_G, 2 * w), 1u);
                             }
                             umma_commit(&empty[s]);                       // frees the stage when the MMAs retire
                         }
@@ -456,7 +502,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                             const unsigned char *src = op + size_t(fi) * bin_bytes + (size_t(nbk) * NKC + kc) * (CF::NSPLIT * CF::B_TILE);
                             mbar_arrive_expect_tx(&full[s], CF::NSPLIT * bytes);
                             bulk_g2s(b_tile(s, 0), src, bytes, &full[s]);
-                            if (PASSES == 3) bulk_g2s(b_tile(s, 1), src + CF::B_TILE, bytes, &full[s]);
+                            if (PASSES != 1) bulk_g2s(b_tile(s, 1), src + CF::B_TILE, bytes, &full[s]);
                         }
                     }
                 }
@@ -506,6 +552,15 @@ __global__ void das_prepare_tc_kernel(const double2 *__restrict__ csm, int M, in
             const float4 lo = make_float4(to_tf32(v[0] - hi.x), to_tf32(v[1] - hi.y), to_tf32(v[2] - hi.z), to_tf32(v[3] - hi.w));
             *reinterpret_cast<float4 *>(tile + CF::B_TILE + off) = lo;
         }
+        if (PASSES == 2) {
+            // correction image row = [bf16(y) of the chunk's 16 mics | bf16(y - hi)]: the 2 mics of this j are
+            // 8 bytes at byte offset 8*j of each 64-byte part, i.e. half of 16-byte chunk j/2 (resp. 4 + j/2)
+            unsigned char *img = tile + CF::B_TILE;
+            uint2 vb = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+            uint2 vl = make_uint2(pack_bf16(v[0] - hi.x, v[1] - hi.y), pack_bf16(v[2] - hi.z, v[3] - hi.w));
+            *reinterpret_cast<uint2 *>(img + sw128_offset(row, j >> 1) + 8 * (j & 1)) = vb;
+            *reinterpret_cast<uint2 *>(img + sw128_offset(row, 4 + (j >> 1)) + 8 * (j & 1)) = vl;
+        }
     }
 }
 
@@ -513,7 +568,7 @@ template <int PASSES> int64_t images_bytes(int M, int nbins) {
     const int NKC = (M + KCH - 1) / KCH;
     const int nb = tc_nb(M), NBLK = (M + nb - 1) / nb;
     const int64_t btile = 2 * nb * 128;
-    return int64_t(nbins) * NBLK * NKC * (PASSES == 3 ? 2 : 1) * btile;
+    return int64_t(nbins) * NBLK * NKC * (PASSES == 1 ? 1 : 2) * btile;
 }
 
 template <int NB, int PASSES>
@@ -566,7 +621,7 @@ template <int PASSES> int64_t operand_bytes(int M, int nbins) {
 
 int64_t b2_das_tc_operand_bytes(int M, int nbins, int mode) {
     if (M > MAX_MICS) { b2_set_error("tensor-core map kernel supports at most %d microphones", MAX_MICS); return B2_EUNSUPPORTED; }
-    return mode == B2_MAP_TC_TF32X3 ? operand_bytes<3>(M, nbins) : operand_bytes<1>(M, nbins);
+    return mode == B2_MAP_TC_TF32 ? operand_bytes<1>(M, nbins) : operand_bytes<3>(M, nbins);
 }
 
 #define B2_TC_DISPATCH(FN, ...)                                                      \
@@ -576,6 +631,10 @@ int64_t b2_das_tc_operand_bytes(int M, int nbins, int mode) {
             if (nb_ == 32) return FN<32, 3>(__VA_ARGS__);                            \
             if (nb_ == 64) return FN<64, 3>(__VA_ARGS__);                            \
             return FN<128, 3>(__VA_ARGS__);                                          \
+        } else if (mode == B2_MAP_TC_MIXED) {                                        \
+            if (nb_ == 32) return FN<32, 2>(__VA_ARGS__);                            \
+            if (nb_ == 64) return FN<64, 2>(__VA_ARGS__);                            \
+            return FN<128, 2>(__VA_ARGS__);                                          \
         } else {                                                                     \
             if (nb_ == 32) return FN<32, 1>(__VA_ARGS__);                            \
             if (nb_ == 64) return FN<64, 1>(__VA_ARGS__);                            \

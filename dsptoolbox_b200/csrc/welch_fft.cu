@@ -24,7 +24,14 @@ template <typename T, int LOG2NC> struct Geo {
     static constexpr int CXB = int(sizeof(cx<T>));
     static constexpr int frames_fit(int fr) { return fr * PITCH * CXB <= 74 * 1024; }   // 3 CTAs per SM
     static constexpr int FR = frames_fit(16) ? 16 : frames_fit(8) ? 8 : frames_fit(4) ? 4 : frames_fit(2) ? 2 : 1;
-    static constexpr int VPT = sizeof(T) == 8 ? 16 : 32;  // complex values held per thread
+#ifndef B2_FFT_VPT64
+#define B2_FFT_VPT64 16
+#endif
+#ifndef B2_FFT_VPT32
+#define B2_FFT_VPT32 16
+#endif
+    static constexpr int VPT = sizeof(T) == 8 ? B2_FFT_VPT64 : B2_FFT_VPT32;  // complex values held per thread
+    static constexpr int RMAX = VPT >= 16 ? 16 : 8;                          // largest butterfly held in registers
     static constexpr int NT_RAW = FR * NC / VPT;
     static constexpr int NT = NT_RAW < 64 ? 64 : (NT_RAW > 1024 ? 1024 : NT_RAW);
     static constexpr int SMEM = FR * PITCH * CXB;
@@ -211,9 +218,12 @@ template <typename T, int LOG2NC, int NS>
 __device__ __forceinline__ void stockham_all(cx<T> *s, const cx<T> *__restrict__ tw, int tid) {
     constexpr int NC = 1 << LOG2NC;
     constexpr int REM = NC / NS;
-    if constexpr (REM >= 16) {
+    if constexpr (REM >= 16 && Geo<T, LOG2NC>::RMAX >= 16) {
         stockham_pass<T, LOG2NC, 16, NS>(s, tw, tid);
         stockham_all<T, LOG2NC, NS * 16>(s, tw, tid);
+    } else if constexpr (REM >= 16) {
+        stockham_pass<T, LOG2NC, 8, NS>(s, tw, tid);
+        stockham_all<T, LOG2NC, NS * 8>(s, tw, tid);
     } else if constexpr (REM == 8) {
         stockham_pass<T, LOG2NC, 8, NS>(s, tw, tid);
     } else if constexpr (REM == 4) {
@@ -248,7 +258,7 @@ welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframe
     const T *xrow = xc + int64_t(m) * Lp;
 
     // ---- wl/2-point complex FFT of every frame; the first pass reads global memory directly ----
-    constexpr int R1 = NC >= 16 ? 16 : NC;
+    constexpr int R1 = NC >= G::RMAX ? G::RMAX : NC;
     first_pass_from_global<T, LOG2NC, R1>(s, xrow, step, k0, nframes, window, vec_ok, tid);
     stockham_all<T, LOG2NC, R1>(s, tw, tid);
 

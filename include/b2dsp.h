@@ -47,6 +47,7 @@ extern "C" {
 #define B2_MAP_SIMT_F32 1  /* fp32 CUDA-core kernel                                         */
 #define B2_MAP_TC_TF32 2   /* tcgen05 tensor cores, single-pass TF32, fp32 accumulate       */
 #define B2_MAP_TC_TF32X3 3 /* tcgen05 tensor cores, split-TF32 (3 products), fp32 accumulate */
+#define B2_MAP_TC_MIXED 4  /* tcgen05: TF32 main product + one BF16 product for both corrections */
 
 int b2_version(void);
 const char *b2_last_error(void);

@@ -143,6 +143,29 @@ def main():
     outC["mapline_coords"] = gl.coordinates
     np.savez_compressed(os.path.join(GOLDEN, "das_small.npz"), **outC)
 
+    # ---- case E: MVDR and Functional beamformers (next rows) on the case-C data ----
+    outE = {}
+    sE = dsp.Signal(None, xm.copy(), fs)
+    sE.set_spectrum_parameters(window_length_samples=256)
+    for form in ["Classic", "TrueLocation"]:
+        stv = dsp.beamforming.SteeringVector(getattr(dsp.beamforming.SteeringVectorType, form))
+        for (fc, frac, tag) in [(2000.0, 3, "third"), (3000.0, 0, "single")]:
+            for cls, name, kw in [(dsp.beamforming.BeamformerMVDR, "mvdr", {}),
+                                  (dsp.beamforming.BeamformerFunctional, "functional", dict(gamma=10)),
+                                  (dsp.beamforming.BeamformerFunctional, "functional3", dict(gamma=3))]:
+                bf = cls(sE, dsp.beamforming.MicArray(micp), grid, stv)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    m = bf.get_beamformer_map(fc, frac, **kw)
+                if name == "mvdr":
+                    mo = R.mvdr_map(fref, cref, micxyz, gxyz, fc, frac, 343.0, form)
+                else:
+                    mo = R.functional_map(fref, cref, micxyz, gxyz, fc, frac, kw["gamma"], 343.0, form)
+                e = rel_to_max(mo.reshape(m.shape), m)
+                print(f"E {name:12s} {form:13s} {tag:7s} oracle-vs-ref {e:.2e}")
+                assert e < 1e-9
+                outE[f"{name}_{form}_{tag}"] = m
+    np.savez_compressed(os.path.join(GOLDEN, "beamformers_next.npz"), **outE)
+
     # ---- case D: config 1 (array.xml, 1 s @ 48 kHz, nfft 1024, 50x50 grid, 4 kHz third) ---
     micxyz = synth.positions_to_xyz(arr)
     fs = 48000

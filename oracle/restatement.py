@@ -318,3 +318,39 @@ def das_map(f, csm, mic_xyz, grid_xyz, fc, fraction=3, remove_diag=True, c=343.0
     if len(fsel) > 1:
         return P @ simpson_weights(len(fsel), fsel[1] - fsel[0])
     return P[:, 0]
+
+
+# --------------------------------------------------------------------------- "next" rows
+def _band(f, csm, fc, fraction):
+    id1, id2 = band_bins(f, fc, fraction)
+    return f[id1:id2], np.asarray(csm)[id1:id2]
+
+
+def _quadratic_form(h, A):
+    """P[g, f] = Re(h[f,:,g]^H A[f] h[f,:,g])."""
+    return np.einsum("fmg,fmg->gf", h.conjugate(), np.matmul(A, h)).real
+
+
+def _integrate(P, fsel):
+    if len(fsel) > 1:
+        return _scipy_simpson(P, dx=fsel[1] - fsel[0], axis=1)
+    return P[:, 0]
+
+
+def mvdr_map(f, csm, mic_xyz, grid_xyz, fc, fraction=3, c=343.0, formulation="truelocation"):
+    """`BeamformerMVDR.get_beamformer_map` (beamforming.py:1238-1314): 1 / Re(h^H C^-1 h) per bin."""
+    fsel, C = _band(f, csm, fc, fraction)
+    h = steering_vector(fsel * np.pi * 2 / c, grid_xyz, mic_xyz, formulation)
+    return _integrate(1.0 / _quadratic_form(h, np.linalg.inv(C)), fsel)
+
+
+def functional_map(f, csm, mic_xyz, grid_xyz, fc, fraction=3, gamma=10, c=343.0, formulation="truelocation"):
+    """`BeamformerFunctional.get_beamformer_map` (beamforming.py:1139-1220): the CSM is replaced by
+    u s^(1/gamma) v^H (SVD), and the beamformer output is raised to gamma around the steering norm."""
+    fsel, C = _band(f, csm, fc, fraction)
+    h = steering_vector(fsel * np.pi * 2 / c, grid_xyz, mic_xyz, formulation)
+    u, s, vh = np.linalg.svd(C)
+    Cg = np.matmul(u * (s ** (1 / gamma))[:, None, :], vh)
+    P = _quadratic_form(h, Cg)
+    norm = np.einsum("fmg,fmg->gf", h.conjugate(), h).real
+    return _integrate((P / norm) ** gamma * norm, fsel)

@@ -20,9 +20,10 @@ def run(M, G, F, mode, seed=0, steering=3, remove_diag=True):
     torch.cuda.synchronize()
     return out.cpu().numpy(), pb.cpu().numpy(), time.perf_counter() - t0
 
+MODES = [(N.MAP_TC_TF32X3, "tf32x3"), (N.MAP_TC_MIXED, "mixed"), (N.MAP_TC_TF32, "tf32")]
 for (M, G, F) in [(64, 300, 5), (16, 128, 3), (256, 1000, 9), (100, 257, 4), (200, 129, 3)]:
     ref, pref, _ = run(M, G, F, N.MAP_SIMT_F64)
-    for mode, name in [(N.MAP_TC_TF32X3, "tf32x3"), (N.MAP_TC_TF32, "tf32")]:
+    for mode, name in MODES:
         for rd in (True, False):
             ref, pref, _ = run(M, G, F, N.MAP_SIMT_F64, remove_diag=rd)
             got, pgot, dt = run(M, G, F, mode, remove_diag=rd)

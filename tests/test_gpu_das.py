@@ -17,7 +17,7 @@ from oracle import restatement as R  # noqa: E402
 from parity import assert_map_close  # noqa: E402
 
 BF = dsp.beamforming
-MODES = ["simt_f64", "simt_f32"] + (["tf32x3", "tf32"] if engine.tc_map_available() else [])
+MODES = ["simt_f64", "simt_f32"] + (["mixed", "tf32x3", "tf32"] if engine.tc_map_available() else [])
 # Single-pass TF32 rounds both operands to 11 significant bits: its error is ~5e-4 / sqrt(#terms)
 # of the coherent maximum, i.e. OUTSIDE the 1e-4 contract for small arrays.  It is an opt-in
 # speed mode (never the default); the tests only bound it.  Every other mode meets the contract.
@@ -189,3 +189,25 @@ def test_per_bin_powers_and_linearity(mode):
     assert np.max(np.abs(pb - P)) <= (TF32_REL if mode == "tf32" else 1e-4) * P.max()
     assert np.allclose(flat2, 3.0 * flat, rtol=1e-5, atol=(1e-3 if mode == "tf32" else 1e-6) * flat.max())          # linear in the CSM
     assert np.all(flat >= 0)                                                          # clamped
+
+
+# ---------------------------------------------------------------- next rows: MVDR / Functional
+@pytest.mark.parametrize("mode", [m for m in MODES if m != "tf32"])
+@pytest.mark.parametrize("form", ["Classic", "TrueLocation"])
+def test_golden_mvdr_functional(golden_dir, mode, form):
+    """Reference tests/test_beamforming.py:130-191 only smoke-tests these; here they are pinned to
+    golden maps of the real reference (oracle/make_golden.py case E)."""
+    g = np.load(os.path.join(golden_dir, "das_small.npz"))
+    ge = np.load(os.path.join(golden_dir, "beamformers_next.npz"))
+    sig, ma = _golden_setup(g)
+    grid = BF.Regular2DGrid(g["line1"], g["line2"], ("x", "y"), float(g["value3"]))
+    st = BF.SteeringVector(getattr(BF.SteeringVectorType, form))
+    engine.config.map_mode = mode
+    for fc, frac, tag in [(2000.0, 3, "third"), (3000.0, 0, "single")]:
+        m, _ = quiet_map(BF.BeamformerMVDR(sig, ma, grid, st), fc, frac)
+        e1 = assert_map_close(m, ge[f"mvdr_{form}_{tag}"], rel=2e-4 if mode != "simt_f64" else 1e-8, db=0.05)
+        m, _ = quiet_map(BF.BeamformerFunctional(sig, ma, grid, st), fc, frac, 10)
+        e2 = assert_map_close(m, ge[f"functional_{form}_{tag}"], rel=2e-4 if mode != "simt_f64" else 1e-8, db=0.05)
+        m, _ = quiet_map(BF.BeamformerFunctional(sig, ma, grid, st), fc, frac, gamma=3)
+        assert_map_close(m, ge[f"functional3_{form}_{tag}"], rel=2e-4 if mode != "simt_f64" else 1e-8, db=0.05)
+        print(mode, form, tag, e1, e2)

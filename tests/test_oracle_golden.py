@@ -89,3 +89,18 @@ def test_simpson_weights_match_scipy():
     for n in (2, 3, 4, 7, 20, 21):
         y = rng.standard_normal((5, n))
         assert np.allclose(y @ R.simpson_weights(n, 0.3), simpson(y, dx=0.3, axis=1), rtol=1e-13)
+
+
+@pytest.mark.parametrize("form", ["Classic", "TrueLocation"])
+def test_mvdr_functional_next_rows(golden_dir, form):
+    """oracle restatements of BeamformerMVDR / BeamformerFunctional vs the reference."""
+    g = np.load(os.path.join(golden_dir, "das_small.npz"))
+    ge = np.load(os.path.join(golden_dir, "beamformers_next.npz"))
+    mic = np.stack([g["mic_x"], g["mic_y"], g["mic_z"]], axis=1)
+    a, b = np.meshgrid(g["line1"], g["line2"], indexing="ij")
+    grid = np.stack([a.ravel(), b.ravel(), np.full(a.size, float(g["value3"]))], axis=1)
+    f, c = R.csm_welch(g["x"], int(g["fs"]), int(g["wl"]), "hann", 50, True, "fftbackward")
+    for fc, frac, tag in [(2000.0, 3, "third"), (3000.0, 0, "single")]:
+        assert rel_to_max(R.mvdr_map(f, c, mic, grid, fc, frac, 343.0, form), ge[f"mvdr_{form}_{tag}"].ravel()) < 1e-9
+        assert rel_to_max(R.functional_map(f, c, mic, grid, fc, frac, 10, 343.0, form), ge[f"functional_{form}_{tag}"].ravel()) < 1e-9
+        assert rel_to_max(R.functional_map(f, c, mic, grid, fc, frac, 3, 343.0, form), ge[f"functional3_{form}_{tag}"].ravel()) < 1e-9
