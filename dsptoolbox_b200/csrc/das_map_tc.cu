@@ -497,7 +497,11 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                         for (int kc = NKC - 1; kc >= kc0; --kc, ++it) {
                             const int s = it % NSTAGE;
                             const int w = min(NB, KCH * (kc - kc0 + 1));
+#ifdef B2_EXPERIMENT_BDIV
+                            const uint32_t bytes = uint32_t(2 * w) * 128 / B2_EXPERIMENT_BDIV;   // timing experiment only (wrong results)
+#else
                             const uint32_t bytes = uint32_t(2 * w) * 128;          // first 2w rows of each image
+#endif
                             mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
                             const unsigned char *src = op + size_t(fi) * bin_bytes + (size_t(nbk) * NKC + kc) * (CF::NSPLIT * CF::B_TILE);
                             mbar_arrive_expect_tx(&full[s], CF::NSPLIT * bytes);
