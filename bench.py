@@ -485,7 +485,7 @@ def run_b200(args):
                                       "peak": hbm, "unit": "GB/s", "frac": b0 / k_times["k0_prepare"] / 1e6 / hbm}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # reported at N = 1 only
         r = CpuReference(w, pos, L, lines, channels=6).step(pairs=21, points=96)
         cpu = {"value": r["map_rate"], "unit": "grid-pt*bins/s", "cores": os.cpu_count(), "kind": "port",
                "sample": r["sample"], "csm_value": r["csm_rate"], "csm_unit": "ch-samples/s", "sample_seconds": r["t_sample_s"]}
