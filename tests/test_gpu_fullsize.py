@@ -1,0 +1,116 @@
+"""Parity at BASELINE.json's full sizes (configs[3] and [4]): 256 microphones x 60 s @ 48 kHz,
+nfft 4096, and the 2048-bin band of the 1e6-point map.  The oracle cannot run these sizes in full,
+so the GPU result is checked (a) against the oracle on seeded sub-samples (channel pairs / grid
+points), and (b) through size-independent properties (Hermitian symmetry, linearity, shard
+additivity, energy conservation)."""
+
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import dsptoolbox_b200 as dsp  # noqa: E402
+from dsptoolbox_b200 import engine, synth  # noqa: E402
+from dsptoolbox_b200.standard._spectral_methods import csm_welch_device  # noqa: E402
+from oracle import restatement as R  # noqa: E402
+
+FS, WL, M, L = 48_000, 4096, 256, 60 * 48_000
+
+
+@pytest.fixture(scope="module")
+def recording():
+    mic = synth.positions_to_xyz(synth.disc_array(M, 1.0, seed=7))
+    x = synth.point_source_recording_torch(mic, L, FS, noise_sigma=0.1, seed=1, device="cuda")
+    return mic, x
+
+
+@pytest.fixture(scope="module")
+def csm(recording):
+    _, x = recording
+    engine.config.csm_precision = "fp64"
+    f, c = csm_welch_device(x, FS, WL, dsp.Window.Hann, 50, True, "mean", dsp.SpectrumScaling.FFTBackward)
+    return f, c
+
+
+def test_csm_full_size_subsample_against_oracle(recording, csm):
+    _, x = recording
+    f, c = csm
+    assert c.shape == (WL // 2 + 1, M, M) and c.dtype == torch.complex128
+    rng = np.random.default_rng(0)
+    chans = sorted(int(v) for v in rng.choice(M, size=5, replace=False))
+    xs = x[:, chans].cpu().numpy()
+    for a in range(len(chans)):
+        for b in range(a, len(chans)):
+            i, j = chans[a], chans[b]
+            ref = R.welch_pair(xs[:, a], None if a == b else xs[:, b], FS, "hann", WL, 50, True, "fftbackward")
+            got = c[:, j, i].cpu().numpy()
+            rel = np.abs(got[1:] - ref[1:]) / np.abs(ref[1:])
+            assert rel.max() <= 1e-5, (i, j, rel.max())          # north-star tolerance, element-wise
+            assert rel.max() <= 1e-9                              # what strict mode actually delivers
+
+
+def test_csm_full_size_properties(recording, csm):
+    _, x = recording
+    f, c = csm
+    # Hermitian by construction; real non-negative diagonal
+    blk = c[100:110]
+    assert torch.equal(blk, blk.transpose(1, 2).conj())
+    d = torch.diagonal(c, dim1=1, dim2=2)
+    assert torch.all(d.imag == 0) and torch.all(d.real >= 0)
+    # linearity of the un-normalised sums in the frame set: shards add up to the whole
+    w = R.welch_window("hann", WL)
+    step = WL // 2
+    sub = x[: 40 * step + WL, :64]
+    Ls = sub.shape[0]
+    K, _ = engine.welch_frames(Ls, WL, step)
+    full, _ = engine.csm_partial_sums(sub, Ls, WL, step, w, True, 1.0)
+    parts = sum(engine.csm_partial_sums(sub, Ls, WL, step, w, True, 1.0, frame_range=r)[0]
+                for r in ((0, 13), (13, 30), (30, K)))
+    low = torch.tril(torch.ones(64, 64, dtype=torch.bool, device="cuda"))
+    assert (parts[:, low] - full[:, low]).abs().max() <= 1e-12 * full[:, low].abs().max()
+    # scaling the recording by a scales the default (amplitude, sqrt-ed) CSM by |a|
+    f2, c2 = csm_welch_device(3.0 * sub, FS, WL, dsp.Window.Hann, 50, True, "mean", dsp.SpectrumScaling.FFTBackward)
+    f1, c1 = csm_welch_device(sub, FS, WL, dsp.Window.Hann, 50, True, "mean", dsp.SpectrumScaling.FFTBackward)
+    assert ((c2[1:] - 3.0 * c1[1:]).abs() <= 1e-10 * c1[1:].abs()).all()
+    # energy: with a boxcar window, no overlap and power scaling the diagonal sums to the signal power
+    fb, cb = csm_welch_device(sub[: 16 * WL], FS, WL, dsp.Window.Boxcar, 0, False, "mean", dsp.SpectrumScaling.FFTBackward)
+    pw = torch.diagonal(cb, dim1=1, dim2=2).real ** 2                        # undo the amplitude sqrt
+    spec_energy = (pw[0] + pw[-1] + 2 * pw[1:-1].sum(0)) / WL               # Parseval, one-sided
+    time_energy = (sub[: 16 * WL] ** 2).sum(0) / 16
+    assert torch.allclose(spec_energy, time_energy, rtol=1e-10)
+
+
+@pytest.mark.parametrize("mode", ["mixed", "tf32x3"])
+def test_map_full_band_subsample_against_oracle(recording, csm, mode):
+    """2048 bins x 256 mics (configs[4]) on 16 384 grid points of the 100^3 grid; 24 seeded points
+    are recomputed by the oracle from the same CSM."""
+    mic, _ = recording
+    f, c = csm
+    if not engine.tc_map_available():
+        pytest.skip("tensor-core map kernel not built")
+    rng = np.random.default_rng(1)
+    lines = (np.linspace(-1, 1, 100), np.linspace(-1, 1, 100), np.linspace(0.5, 1.5, 100))
+    idx = rng.choice(10 ** 6, size=16_384, replace=False)
+    ix, iy, iz = np.unravel_index(idx, (100, 100, 100))
+    gxyz = np.stack([lines[0][ix], lines[1][iy], lines[2][iz]], axis=1)
+    fc, frac = 219.089, 0.0738
+    id1, id2 = R.band_bins(f, fc, frac)
+    assert (id1, id2) == (0, 2048)
+    fsel = f[id1:id2]
+    weights = dsp.beamforming.simpson_weights(id2 - id1, fsel[1] - fsel[0])
+    m = engine._MAP_MODES[mode]
+    op = engine.das_prepare(c, id1, id2 - id1, True, m)
+    _, center = R.array_center(mic)
+    out, _ = engine.das_map(op, M, fsel, weights, 343.0, mic, center, gxyz, 3, True, m)
+    out = out.cpu().numpy()
+    pick = rng.choice(len(idx), size=24, replace=False)
+    ref = R.das_map(f, c.cpu().numpy(), mic, gxyz[pick], fc, frac, True, 343.0, "truelocation", chunk_points=8)
+    assert np.max(np.abs(out[pick] - ref)) <= 1e-4 * out.max()
+    sel = ref >= out.max() * 1e-2
+    if sel.any():
+        assert np.max(np.abs(10 * np.log10(out[pick][sel] / ref[sel]))) <= 0.01
+    assert np.all(out >= 0)
