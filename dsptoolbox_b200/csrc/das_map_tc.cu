@@ -267,13 +267,19 @@ __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
 }
 
 // ---------------------------------------------------------------- the kernel
+// work unit -> (tile of 128 grid points, contiguous range of bins); units are dealt round-robin
+#define B2_UNIT_DECODE                                                        \
+    const int tile = unit / nsplit, upart = unit - tile * nsplit;            \
+    const int f_begin = int(int64_t(nbins) * upart / nsplit);                \
+    const int f_end = int(int64_t(nbins) * (upart + 1) / nsplit);
+
 template <int NB, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scratch, int M, int nbins,
                   const double *__restrict__ freqs, const double *__restrict__ weights, double inv_c,
                   const double *__restrict__ mic, double cx0, double cy0, double cz0,
                   const double *__restrict__ grid, int64_t G, int steering, int clamp_negative,
-                  double *__restrict__ map_out, double *__restrict__ per_bin, int ntiles) {
+                  double *__restrict__ map_out, double *__restrict__ per_bin, int ntiles, int nsplit) {
     using CF = TcCfg<NB, PASSES>;
     constexpr int UMMA_N = CF::UMMA_N, NSTAGE = CF::NSTAGE;
     extern __shared__ unsigned char smem_raw[];
@@ -309,7 +315,8 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         const int r = tid & 127, half = tid >> 7;            // row of the tile, which 8 of a chunk's 16 mics
         const uint32_t a_base = smem_u32(smem);
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
+            B2_UNIT_DECODE
             // the epilogue warps are done with the previous tile's table before it is overwritten
             asm volatile("bar.sync 1, 512;" ::: "memory");
             const RowAmp amp = row_table(tab, r, half, true, int64_t(tile) * TILE_G + r, G, grid, mic, M, Mk, cx0, cy0,
@@ -324,7 +331,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             };
             float4 r_lo, r_hi;
             load_r(NKC - 1, r_lo, r_hi);
-            for (int fi = 0; fi < nbins; ++fi) {
+            for (int fi = f_begin; fi < f_end; ++fi) {
                 const float bf = float(freqs[fi] * inv_c);
                 for (int nbk = 0; nbk < NBLK; ++nbk) {
                     const int kc0 = (nbk * NB) / KCH;
@@ -386,13 +393,14 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         const uint32_t lane_base = uint32_t(quad * 32) << 16;
         constexpr int CG_PER_HALF = (NB / 32 + 1) / 2;       // 32-column groups per epilogue half
         uint32_t acc_it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
+            B2_UNIT_DECODE
             const int64_t g = int64_t(tile) * TILE_G + r;
             asm volatile("bar.sync 1, 512;" ::: "memory");
             const RowAmp amp = row_table(tab, r, 0, false, g, G, grid, mic, M, Mk, cx0, cy0, cz0, steering);
             asm volatile("bar.sync 1, 512;" ::: "memory");   // table of this tile is complete
             double acc_map = 0.0;
-            for (int fi = 0; fi < nbins; ++fi) {
+            for (int fi = f_begin; fi < f_end; ++fi) {
                 const float bf = float(freqs[fi] * inv_c);
                 float p0 = 0.f, p1 = 0.f;
                 for (int nbk = 0; nbk < NBLK; ++nbk, ++acc_it) {
@@ -445,14 +453,17 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                     if (per_bin != nullptr && g < G) per_bin[g * nbins + fi] = p;
                 }
             }
-            if (half == 0 && g < G) map_out[g] = acc_map;
+            // the bins of a tile may be split over several work units: the map is zeroed by the
+            // launcher and every unit adds its weighted partial sum
+            if (half == 0 && g < G) atomicAdd(map_out + g, acc_map);
         }
     } else if (warp == 16) {
         // =========================== MMA issue (one thread) ===========================
         if (lane == 0) {
             uint32_t it = 0, acc_it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int fi = 0; fi < nbins; ++fi) {
+            for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
+            B2_UNIT_DECODE
+                for (int fi = f_begin; fi < f_end; ++fi) {
                     for (int nbk = 0; nbk < NBLK; ++nbk, ++acc_it) {
                         const int buf = acc_it & 1;
                         mbar_wait(&tempty[buf], ((acc_it >> 1) & 1) ^ 1);
@@ -493,8 +504,9 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         if (lane == 0) {
             uint32_t it = 0;
             const size_t bin_bytes = size_t(NBLK) * NKC * CF::NSPLIT * CF::B_TILE;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int fi = 0; fi < nbins; ++fi) {
+            for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
+            B2_UNIT_DECODE
+                for (int fi = f_begin; fi < f_end; ++fi) {
                     for (int nbk = 0; nbk < NBLK; ++nbk) {
                         const int kc0 = (nbk * NB) / KCH;
                         for (int kc = NKC - 1; kc >= kc0; --kc, ++it) {
@@ -607,13 +619,26 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
     }
     const int64_t ntiles = (G + TILE_G - 1) / TILE_G;
     B2_REQUIRE(ntiles <= 0x7fffffff, B2_EINVAL, "b2_das_map: too many grid points");
-    int nblocks = int(ntiles < num_sms ? ntiles : num_sms);            // persistent: one CTA per SM
-    if (nblocks > MAX_CTAS) nblocks = MAX_CTAS;
+    // Persistent grid, one CTA per SM.  When the tiles do not fill the last round of CTAs evenly
+    // (e.g. 977 tiles on 148 SMs: 60 % of the SMs idle in round 7), the bins of every tile are split
+    // into up to 4 work units so that the tail shrinks; partial maps are combined with atomicAdd.
+    int cap = num_sms < MAX_CTAS ? num_sms : MAX_CTAS;
+    int nsplit = 1;
+    double best = 0.0;
+    for (int sp = 1; sp <= 4 && nbins / sp >= 32; ++sp) {
+        const int64_t units = ntiles * sp;
+        const int64_t rounds = (units + cap - 1) / cap;
+        const double eff = double(units) / double(rounds * cap);
+        if (eff > best + 0.01) { best = eff; nsplit = sp; }
+    }
+    const int64_t units = ntiles * nsplit;
+    const int nblocks = int(units < cap ? units : cap);
+    B2_CUDA_OK(cudaMemsetAsync(map_out, 0, size_t(G) * sizeof(double), st));
     float *scratch = reinterpret_cast<float *>((unsigned char *)op + images_bytes<PASSES>(M, nbins));
     kern<<<nblocks, TC_THREADS, CF::SMEM, st>>>((const unsigned char *)op, scratch, M, nbins, (const double *)freqs,
                                                 (const double *)weights, 1.0 / c, (const double *)mic, center[0],
                                                 center[1], center[2], (const double *)grid, G, steering,
-                                                clamp_negative, (double *)map_out, (double *)per_bin, int(ntiles));
+                                                clamp_negative, (double *)map_out, (double *)per_bin, int(ntiles), nsplit);
     B2_LAUNCH_OK("b2_das_map(tc)");
     return B2_OK;
 }
