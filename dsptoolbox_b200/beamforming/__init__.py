@@ -10,6 +10,7 @@ from .beamforming import (  # noqa: F401
     BeamformerDASFrequency,
     BeamformerMVDR,
     BeamformerFunctional,
+    BeamformerOrthogonal,
     classic_steering,
     inverse_steering,
     true_power_steering,
@@ -19,4 +20,4 @@ from .beamforming import (  # noqa: F401
 from .enums import SteeringVectorType  # noqa: F401
 
 __all__ = ["Grid", "Regular2DGrid", "Regular3DGrid", "LineGrid", "MicArray", "SteeringVector",
-           "BeamformerDASFrequency", "BeamformerMVDR", "BeamformerFunctional", "SteeringVectorType"]
+           "BeamformerDASFrequency", "BeamformerMVDR", "BeamformerFunctional", "BeamformerOrthogonal", "SteeringVectorType"]

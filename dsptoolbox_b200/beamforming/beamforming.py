@@ -6,9 +6,9 @@ Call-compatible with reference beamforming/beamforming.py for Grid (:35-75), Reg
 `get_beamformer_map` keeps the reference's side effects (stdout banner, `self.map`,
 `self.f_range_hz`, returned copy) but runs on the GPU: the CSM stays on the device, steering
 vectors are synthesised inside the map kernel, and the grid may be sharded over ranks (dist.py).
-BeamformerMVDR (:1223-1314) and BeamformerFunctional (:1127-1220) reuse the same map kernel on a
-per-bin transformed matrix.  CleanSC, Orthogonal, DASTime and the source
-simulator are outside this round's scope.
+BeamformerMVDR (:1223-1314), BeamformerFunctional (:1127-1220) and BeamformerOrthogonal (:1010-1124)
+reuse the same map kernel on per-bin transformed matrices.  CleanSC,
+DASTime and the source simulator are outside this round's scope.
 """
 
 from __future__ import annotations
@@ -387,3 +387,42 @@ class BeamformerFunctional(_QuadraticFormBeamformer):
         eye = torch.eye(M, dtype=csm.dtype, device=csm.device)[None]
         norm = self._per_bin_power(fsel[:1], eye)
         return self._finish((power / norm) ** gamma * norm, fsel)
+
+
+class BeamformerOrthogonal(_QuadraticFormBeamformer):
+    """Orthogonal beamforming (Sarradj 2010): per bin, each of the largest eigenpairs of the CSM is
+    mapped with |h^H v|^2 = h^H (v v^H) h and its eigenvalue is assigned to the grid point where
+    that map peaks.  The peak location is an arg-max over the grid, so the quadratic forms run on
+    the fp64 CUDA-core kernel (`simt_f64`): a tensor-core rounding difference could move it."""
+
+    beamformer_type = "Orthogonal"
+
+    def get_beamformer_map(self, center_frequency_hz: float, octave_fraction: int = 3,
+                           number_eigenvalues: int | None = None):
+        import torch
+
+        if number_eigenvalues is None:
+            number_eigenvalues = self.signal.number_of_channels // 2
+        else:
+            assert number_eigenvalues <= self.signal.number_of_channels, (
+                "Number of eigenvalues cannot be more than number of microphones")
+            assert number_eigenvalues > 0, "At least one eigenvalue of the CSM must be regarded"
+        fsel, csm = self._band(center_frequency_hz, octave_fraction)
+        F, G = len(fsel), self.grid.number_of_points
+        w, v = torch.linalg.eigh(csm)                          # ascending eigenvalues
+        print("...Apply...")
+        out = torch.zeros((G, F), dtype=torch.float64, device=csm.device)
+        cols = torch.arange(F, device=csm.device)
+        # a few eigenpairs at a time keeps the batch of rank-1 matrices small: (chunk * F, M, M)
+        chunk = max(1, min(number_eigenvalues, (1 << 28) // max(1, F * csm.shape[1] ** 2 * 16)))
+        for e0 in range(0, number_eigenvalues, chunk):
+            es = range(e0, min(number_eigenvalues, e0 + chunk))
+            vecs = torch.stack([v[:, :, -e - 1] for e in es])                         # (E, F, M)
+            rank1 = vecs[..., :, None] * vecs.conj()[..., None, :]                    # (E, F, M, M)
+            power = self._per_bin_power(np.tile(fsel, len(es)), rank1.reshape(-1, *rank1.shape[2:]),
+                                        mode="simt_f64")                              # (G, E*F)
+            power = power.reshape(G, len(es), F)
+            for i, e in enumerate(es):                                                 # eigenpair order matters
+                peak = torch.argmax(power[:, i, :], dim=0)                             # (F,)
+                out[peak, cols] = power[peak, i, cols] * w[:, -e - 1]
+        return self._finish(out, fsel)

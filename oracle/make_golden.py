@@ -164,6 +164,15 @@ def main():
                 print(f"E {name:12s} {form:13s} {tag:7s} oracle-vs-ref {e:.2e}")
                 assert e < 1e-9
                 outE[f"{name}_{form}_{tag}"] = m
+            for ne, nm in [(None, "orthogonal"), (3, "orthogonal3")]:
+                bf = dsp.beamforming.BeamformerOrthogonal(sE, dsp.beamforming.MicArray(micp), grid, stv)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    m = bf.get_beamformer_map(fc, frac, ne)
+                mo = R.orthogonal_map(fref, cref, micxyz, gxyz, fc, frac, ne, 343.0, form)
+                e = rel_to_max(mo.reshape(m.shape), m)
+                print(f"E {nm:12s} {form:13s} {tag:7s} oracle-vs-ref {e:.2e}")
+                assert e < 1e-9
+                outE[f"{nm}_{form}_{tag}"] = m
     np.savez_compressed(os.path.join(GOLDEN, "beamformers_next.npz"), **outE)
 
     # ---- case D: config 1 (array.xml, 1 s @ 48 kHz, nfft 1024, 50x50 grid, 4 kHz third) ---

@@ -354,3 +354,23 @@ def functional_map(f, csm, mic_xyz, grid_xyz, fc, fraction=3, gamma=10, c=343.0,
     P = _quadratic_form(h, Cg)
     norm = np.einsum("fmg,fmg->gf", h.conjugate(), h).real
     return _integrate((P / norm) ** gamma * norm, fsel)
+
+
+def orthogonal_map(f, csm, mic_xyz, grid_xyz, fc, fraction=3, number_eigenvalues=None, c=343.0,
+                   formulation="truelocation"):
+    """`BeamformerOrthogonal.get_beamformer_map` (beamforming.py:1025-1124): per bin and per retained
+    eigenpair (largest first) the grid point maximising |h^H v|^2 receives that value times the
+    eigenvalue (assignment: a later eigenpair landing on the same point overwrites it)."""
+    M = mic_xyz.shape[0]
+    E = M // 2 if number_eigenvalues is None else number_eigenvalues
+    fsel, C = _band(f, csm, fc, fraction)
+    h = steering_vector(fsel * np.pi * 2 / c, grid_xyz, mic_xyz, formulation)
+    out = np.zeros((grid_xyz.shape[0], len(fsel)))
+    for fi in range(len(fsel)):
+        w, v = np.linalg.eigh(C[fi])
+        for e in range(E):
+            prod = h[fi].conj().T @ v[:, -e - 1]                     # (G,)
+            em = (prod * prod.conj()).real
+            gi = int(np.argmax(em))
+            out[gi, fi] = em[gi] * w[-e - 1]
+    return _integrate(out, fsel)

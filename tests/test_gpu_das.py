@@ -211,3 +211,22 @@ def test_golden_mvdr_functional(golden_dir, mode, form):
         m, _ = quiet_map(BF.BeamformerFunctional(sig, ma, grid, st), fc, frac, gamma=3)
         assert_map_close(m, ge[f"functional3_{form}_{tag}"], rel=2e-4 if mode != "simt_f64" else 1e-8, db=0.05)
         print(mode, form, tag, e1, e2)
+
+
+def test_golden_orthogonal(golden_dir):
+    """BeamformerOrthogonal (reference beamforming.py:1010-1124) against golden maps of the real reference."""
+    g = np.load(os.path.join(golden_dir, "das_small.npz"))
+    ge = np.load(os.path.join(golden_dir, "beamformers_next.npz"))
+    sig, ma = _golden_setup(g)
+    grid = BF.Regular2DGrid(g["line1"], g["line2"], ("x", "y"), float(g["value3"]))
+    for form in ("Classic", "TrueLocation"):
+        st = BF.SteeringVector(getattr(BF.SteeringVectorType, form))
+        for fc, frac, tag in [(2000.0, 3, "third"), (3000.0, 0, "single")]:
+            m, _ = quiet_map(BF.BeamformerOrthogonal(sig, ma, grid, st), fc, frac)
+            ref = ge[f"orthogonal_{form}_{tag}"]
+            assert np.array_equal(m != 0, ref != 0)                      # same peak locations
+            assert np.max(np.abs(m - ref)) <= 1e-8 * np.max(np.abs(ref))
+            m3, _ = quiet_map(BF.BeamformerOrthogonal(sig, ma, grid, st), fc, frac, 3)
+            assert np.max(np.abs(m3 - ge[f"orthogonal3_{form}_{tag}"])) <= 1e-8 * np.max(np.abs(ref))
+    with pytest.raises(AssertionError):
+        quiet_map(BF.BeamformerOrthogonal(sig, ma, grid, st), 2000.0, 3, 11)
