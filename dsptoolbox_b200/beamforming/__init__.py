@@ -11,6 +11,7 @@ from .beamforming import (  # noqa: F401
     BeamformerMVDR,
     BeamformerFunctional,
     BeamformerOrthogonal,
+    BeamformerCleanSC,
     classic_steering,
     inverse_steering,
     true_power_steering,
@@ -20,4 +21,4 @@ from .beamforming import (  # noqa: F401
 from .enums import SteeringVectorType  # noqa: F401
 
 __all__ = ["Grid", "Regular2DGrid", "Regular3DGrid", "LineGrid", "MicArray", "SteeringVector",
-           "BeamformerDASFrequency", "BeamformerMVDR", "BeamformerFunctional", "BeamformerOrthogonal", "SteeringVectorType"]
+           "BeamformerDASFrequency", "BeamformerMVDR", "BeamformerFunctional", "BeamformerOrthogonal", "BeamformerCleanSC", "SteeringVectorType"]

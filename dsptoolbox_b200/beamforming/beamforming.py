@@ -7,8 +7,8 @@ Call-compatible with reference beamforming/beamforming.py for Grid (:35-75), Reg
 `self.f_range_hz`, returned copy) but runs on the GPU: the CSM stays on the device, steering
 vectors are synthesised inside the map kernel, and the grid may be sharded over ranks (dist.py).
 BeamformerMVDR (:1223-1314), BeamformerFunctional (:1127-1220) and BeamformerOrthogonal (:1010-1124)
-reuse the same map kernel on per-bin transformed matrices.  CleanSC,
-DASTime and the source simulator are outside this round's scope.
+and BeamformerCleanSC (:883-1007) reuse the same map kernel on per-bin transformed matrices
+(SURVEY.md section 8f.1).  DASTime and the source simulator are outside this round's scope.
 """
 
 from __future__ import annotations
@@ -426,3 +426,73 @@ class BeamformerOrthogonal(_QuadraticFormBeamformer):
                 peak = torch.argmax(power[:, i, :], dim=0)                             # (F,)
                 out[peak, cols] = power[peak, i, cols] * w[:, -e - 1]
         return self._finish(out, fsel)
+
+
+class BeamformerCleanSC(_QuadraticFormBeamformer):
+    """CLEAN-SC deconvolution (Sijtsma 2007) of the delay-and-sum map.
+
+    The reference deconvolves one bin after the other (`_clean_sc_deconvolve`,
+    beamforming/_beamforming.py:194-297); here all bins of the band iterate in lock-step: every
+    iteration is one arg-max per bin, a handful of M-vector updates (torch, on the device) and ONE
+    launch of the map kernel that subtracts the coherent source component h^H G_f h of every bin
+    from its dirty map.  The peak search makes the iteration sensitive to rounding, so the
+    quadratic forms use the fp64 CUDA-core kernel."""
+
+    beamformer_type = "CleanSC"
+
+    def get_beamformer_map(self, center_frequency_hz: float, octave_fraction: int = 3,
+                           maximum_iterations: int | None = None, safety_factor: float = 0.5,
+                           remove_csm_diagonal: bool = False):
+        import torch
+
+        if maximum_iterations is None:
+            maximum_iterations = self.signal.number_of_channels * 2
+        else:
+            assert maximum_iterations > 0, "Number of iterations must be positive"
+        assert safety_factor > 0 and safety_factor <= 1, (
+            f"{safety_factor} is not valid. The safety factor (loop gain) should be in ]0, 1]")
+        fsel, csm = self._band(center_frequency_hz, octave_fraction)
+        F, M = len(fsel), self.mics.number_of_points
+        dev = csm.device
+        csm = csm.clone()
+        diag = torch.arange(M, device=dev)
+        if remove_csm_diagonal:
+            csm[:, diag, diag] = 0
+        print("...Create and deconvolve map...")
+        dirty = self._per_bin_power(fsel, csm, mode="simt_f64").clone()          # (G, F)
+        second = torch.zeros_like(dirty)
+        D0, D1 = 2 * csm, csm.clone()
+        active = torch.ones(F, dtype=torch.bool, device=dev)
+        cols = torch.arange(F, device=dev)
+        k = fsel * np.pi * 2 / self.c
+        gxyz = self.grid._coordinates
+        for _ in range(maximum_iterations):
+            peak = torch.argmax(dirty, dim=0)                                     # (F,)
+            pmax = dirty[peak, cols]
+            second[peak[active], cols[active]] += pmax[active] * safety_factor
+            # stopping criterion of the reference: the degraded CSM stopped shrinking (matrix 1-norm)
+            n1 = D1.abs().sum(dim=1).amax(dim=1)
+            n0 = D0.abs().sum(dim=1).amax(dim=1)
+            active = active & ~(n1 >= n0)
+            if not bool(active.any()):
+                break
+            # steering vectors of every bin to its own peak point
+            pk = peak.cpu().numpy()
+            uniq, inv = np.unique(pk, return_inverse=True)
+            h_u = engine.steering_vector(k, self.mics._coordinates, self.mics.array_center_coordinates,
+                                         gxyz[uniq], _steering_code(self.st_vec))      # (F, M, U)
+            w_max = h_u[cols, :, torch.as_tensor(inv, device=dev)]                     # (F, M)
+            w2 = (w_max.conj() * w_max)
+            D_ = torch.einsum("fmn,fn->fm", D1, w_max) / pmax[:, None]
+            h_ = w_max.clone()
+            for _ in range(20):
+                H = h_.conj() * h_
+                h_ = (D_ + H * w_max) / torch.sqrt(1 + (H * w2).sum(dim=1, keepdim=True))
+            Gm = h_[:, :, None] * h_.conj()[:, None, :] * pmax[:, None, None]
+            if remove_csm_diagonal:
+                Gm[:, diag, diag] = 0
+            Gm = torch.where(active[:, None, None], Gm, torch.zeros_like(Gm))       # finished bins stay put
+            dirty -= self._per_bin_power(fsel, Gm, mode="simt_f64") * safety_factor
+            D0 = torch.where(active[:, None, None], D1, D0)
+            D1 = D1 - safety_factor * Gm
+        return self._finish(second, fsel)

@@ -173,6 +173,16 @@ def main():
                 print(f"E {nm:12s} {form:13s} {tag:7s} oracle-vs-ref {e:.2e}")
                 assert e < 1e-9
                 outE[f"{nm}_{form}_{tag}"] = m
+            for kw, nm in [(dict(), "cleansc"), (dict(maximum_iterations=5, safety_factor=0.8, remove_csm_diagonal=True), "cleansc_rd")]:
+                bf = dsp.beamforming.BeamformerCleanSC(sE, dsp.beamforming.MicArray(micp), grid, stv)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    m = bf.get_beamformer_map(fc, frac, **kw)
+                mo = R.clean_sc_map(fref, cref, micxyz, gxyz, fc, frac, kw.get("maximum_iterations"), kw.get("safety_factor", 0.5),
+                                    kw.get("remove_csm_diagonal", False), 343.0, form)
+                e = rel_to_max(mo.reshape(m.shape), m)
+                print(f"E {nm:12s} {form:13s} {tag:7s} oracle-vs-ref {e:.2e}")
+                assert e < 1e-9
+                outE[f"{nm}_{form}_{tag}"] = m
     np.savez_compressed(os.path.join(GOLDEN, "beamformers_next.npz"), **outE)
 
     # ---- case D: config 1 (array.xml, 1 s @ 48 kHz, nfft 1024, 50x50 grid, 4 kHz third) ---

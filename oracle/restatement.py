@@ -374,3 +374,47 @@ def orthogonal_map(f, csm, mic_xyz, grid_xyz, fc, fraction=3, number_eigenvalues
             gi = int(np.argmax(em))
             out[gi, fi] = em[gi] * w[-e - 1]
     return _integrate(out, fsel)
+
+
+def _clean_sc_deconvolve(dirty, csm, h, maximum_iterations, remove_diag, safety_factor):
+    """beamforming/_beamforming.py:194-297 for one bin.  h: (M, G)."""
+    D0, D1 = 2 * csm, csm.copy()
+    m = np.array(dirty, dtype=np.float64, copy=True)
+    second = np.zeros_like(m)
+    for _ in range(maximum_iterations):
+        gi = int(np.argmax(m))
+        pmax = m[gi]
+        second[gi] += pmax * safety_factor
+        if np.linalg.norm(D1, ord=1) >= np.linalg.norm(D0, ord=1):
+            break
+        w_max = h[:, gi]
+        h_ = w_max.copy()
+        w2 = w_max.conjugate() * w_max
+        D_ = D1 @ w_max / pmax
+        for _ in range(20):
+            H = h_.conjugate() * h_
+            h_ = (D_ + H * w_max) / np.sqrt(1 + H @ w2)
+        Gm = np.outer(h_, h_.conjugate()) * pmax
+        if remove_diag:
+            np.fill_diagonal(Gm, 0)
+        m -= np.einsum("mg,mg->g", h.conjugate(), Gm @ h).real * safety_factor
+        D0, D1 = D1, D1 - safety_factor * Gm
+    return second
+
+
+def clean_sc_map(f, csm, mic_xyz, grid_xyz, fc, fraction=3, maximum_iterations=None, safety_factor=0.5,
+                 remove_diag=False, c=343.0, formulation="truelocation"):
+    """`BeamformerCleanSC.get_beamformer_map` (beamforming.py:897-1007)."""
+    M = mic_xyz.shape[0]
+    maxit = 2 * M if maximum_iterations is None else maximum_iterations
+    fsel, C = _band(f, csm, fc, fraction)
+    C = np.array(C, dtype=np.complex128, copy=True)
+    if remove_diag:
+        idx = np.arange(M)
+        C[:, idx, idx] = 0
+    h = steering_vector(fsel * np.pi * 2 / c, grid_xyz, mic_xyz, formulation)
+    dirty = _quadratic_form(h, C)
+    out = np.zeros_like(dirty)
+    for fi in range(len(fsel)):
+        out[:, fi] = _clean_sc_deconvolve(dirty[:, fi], C[fi], h[fi], maxit, remove_diag, safety_factor).real
+    return _integrate(out, fsel)

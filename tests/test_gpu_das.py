@@ -230,3 +230,22 @@ def test_golden_orthogonal(golden_dir):
             assert np.max(np.abs(m3 - ge[f"orthogonal3_{form}_{tag}"])) <= 1e-8 * np.max(np.abs(ref))
     with pytest.raises(AssertionError):
         quiet_map(BF.BeamformerOrthogonal(sig, ma, grid, st), 2000.0, 3, 11)
+
+
+def test_golden_cleansc(golden_dir):
+    """BeamformerCleanSC (reference beamforming.py:883-1007 + _beamforming.py:194-297) against golden maps."""
+    g = np.load(os.path.join(golden_dir, "das_small.npz"))
+    ge = np.load(os.path.join(golden_dir, "beamformers_next.npz"))
+    sig, ma = _golden_setup(g)
+    grid = BF.Regular2DGrid(g["line1"], g["line2"], ("x", "y"), float(g["value3"]))
+    for form in ("Classic", "TrueLocation"):
+        st = BF.SteeringVector(getattr(BF.SteeringVectorType, form))
+        for fc, frac, tag in [(2000.0, 3, "third"), (3000.0, 0, "single")]:
+            m, _ = quiet_map(BF.BeamformerCleanSC(sig, ma, grid, st), fc, frac)
+            ref = ge[f"cleansc_{form}_{tag}"]
+            assert np.max(np.abs(m - ref)) <= 1e-7 * np.max(np.abs(ref)), (form, tag)
+            m2, _ = quiet_map(BF.BeamformerCleanSC(sig, ma, grid, st), fc, frac, 5, 0.8, True)
+            ref2 = ge[f"cleansc_rd_{form}_{tag}"]
+            assert np.max(np.abs(m2 - ref2)) <= 1e-7 * np.max(np.abs(ref2)), (form, tag)
+    with pytest.raises(AssertionError):
+        quiet_map(BF.BeamformerCleanSC(sig, ma, grid, st), 2000.0, 3, 5, 1.5)

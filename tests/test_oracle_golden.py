@@ -117,3 +117,16 @@ def test_orthogonal_next_row(golden_dir, form):
     for fc, frac, tag in [(2000.0, 3, "third"), (3000.0, 0, "single")]:
         assert rel_to_max(R.orthogonal_map(f, c, mic, grid, fc, frac, None, 343.0, form), ge[f"orthogonal_{form}_{tag}"].ravel()) < 1e-9
         assert rel_to_max(R.orthogonal_map(f, c, mic, grid, fc, frac, 3, 343.0, form), ge[f"orthogonal3_{form}_{tag}"].ravel()) < 1e-9
+
+
+@pytest.mark.parametrize("form", ["Classic", "TrueLocation"])
+def test_cleansc_next_row(golden_dir, form):
+    g = np.load(os.path.join(golden_dir, "das_small.npz"))
+    ge = np.load(os.path.join(golden_dir, "beamformers_next.npz"))
+    mic = np.stack([g["mic_x"], g["mic_y"], g["mic_z"]], axis=1)
+    a, b = np.meshgrid(g["line1"], g["line2"], indexing="ij")
+    grid = np.stack([a.ravel(), b.ravel(), np.full(a.size, float(g["value3"]))], axis=1)
+    f, c = R.csm_welch(g["x"], int(g["fs"]), int(g["wl"]), "hann", 50, True, "fftbackward")
+    for fc, frac, tag in [(2000.0, 3, "third"), (3000.0, 0, "single")]:
+        assert rel_to_max(R.clean_sc_map(f, c, mic, grid, fc, frac, None, 0.5, False, 343.0, form), ge[f"cleansc_{form}_{tag}"].ravel()) < 1e-9
+        assert rel_to_max(R.clean_sc_map(f, c, mic, grid, fc, frac, 5, 0.8, True, 343.0, form), ge[f"cleansc_rd_{form}_{tag}"].ravel()) < 1e-9
