@@ -169,8 +169,18 @@ class Signal(MultichannelData):
         return f, csm.cpu().numpy()
 
     # ---- explicitly out of scope -------------------------------------------------------------------
-    def get_spectrum(self, *a, **k):
-        raise NotImplementedError("Signal.get_spectrum is outside the accelerated path (SURVEY.md section 8f)")
+    def get_spectrum(self, force_computation: bool = False):
+        """(f, spectrum) with the Welch auto-spectrum of every channel, float64 (nb, channels) --
+        the WelchPeriodogram branch of reference signal.py:861-946.  The
+        single-FFT branch (arbitrary-length FFT, smoothing) is outside the accelerated path."""
+        if self.spectrum_method != SpectrumMethod.WelchPeriodogram:
+            raise NotImplementedError("SpectrumMethod.FFT spectra are outside the accelerated path")
+        p = self._spectrum_parameters
+        spec = _sm.welch_autospectra_device(self.time_data, self.sampling_rate_hz, p["window_length_samples"],
+                                            p["window_type"], p["overlap_percent"], p["detrend"], p["average"],
+                                            p["scaling"])
+        freqs = np.fft.rfftfreq(p["window_length_samples"], 1 / self.sampling_rate_hz)
+        return freqs, spec.cpu().numpy()
 
     def get_spectrogram(self, *a, **k):
         raise NotImplementedError("Signal.get_spectrogram is outside the accelerated path (SURVEY.md section 8f)")

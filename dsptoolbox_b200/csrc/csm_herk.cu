@@ -225,6 +225,48 @@ csm_finalize_kernel(const double2 *__restrict__ S, int M, int nb, double inv_fra
     }
 }
 
+// Auto-spectra only (the CSM diagonal): P[f][m] (+)= sum_k |X_f[m,k]|^2.  Replaces `_welch(x, None)`
+// (standard/_spectral_methods.py:146-152) for Signal.get_spectrum's Welch branch, where the full
+// rank-K update would be M times too much work.  One warp per pair of channels of one bin: the
+// 2 x 16 frames of a chunk are one contiguous run, read as one coalesced warp access.
+template <typename TIN>
+__global__ void __launch_bounds__(256)
+autopower_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, double *__restrict__ P, int accumulate) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pairs = (M + 1) / 2;
+    const int64_t item = int64_t(blockIdx.x) * 8 + warp;            // (bin, channel pair)
+    if (item >= int64_t(nb) * pairs) return;
+    const int f = int(item / pairs), m = 2 * int(item % pairs) + (lane >> 4);
+    const int nchunks = int(Kp / KC);
+    double acc = 0.0;
+    if (m < M) {
+        const cx<TIN> *src = X + (int64_t(f) * M + m) * KC + (lane & 15);
+        const int64_t chunk_stride = int64_t(nb) * M * KC;
+        for (int c = 0; c < nchunks; ++c) {
+            const cx<TIN> v = src[int64_t(c) * chunk_stride];
+            acc += double(v.x) * double(v.x) + double(v.y) * double(v.y);
+        }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((lane & 15) == 0 && m < M) {
+        double *dst = P + int64_t(f) * M + m;
+        *dst = accumulate ? *dst + acc : acc;
+    }
+}
+
+// mean, factor, DC/Nyquist halving, sqrt for amplitude scalings (_spectral_methods.py:152,164-171)
+__global__ void auto_finalize_kernel(const double *__restrict__ P, int M, int nb, double inv_frames, double factor,
+                                     int halve_edges, int amplitude_sqrt, double *__restrict__ out) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= int64_t(nb) * M) return;
+    const int f = int(i / M);
+    double v = P[i] * inv_frames;
+    v *= factor;
+    if (halve_edges && (f == 0 || f == nb - 1)) v *= 0.5;
+    out[i] = amplitude_sqrt ? sqrt(v) : v;
+}
+
 template <typename TIN>
 int launch_herk(const void *X, int M, int64_t Kp, int nb, void *S, int accumulate, cudaStream_t st) {
     using SM = HerkSmem<TIN>;
@@ -264,5 +306,31 @@ extern "C" int b2_csm_finalize(const void *S_dev, int M, int nb, double inv_fram
     csm_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const double2 *)S_dev, M, nb, inv_frames, factor,
                                                                 halve_edges, amplitude_sqrt, (double2 *)csm_out_dev);
     B2_LAUNCH_OK("b2_csm_finalize");
+    return B2_OK;
+}
+
+extern "C" int b2_welch_autopower(const void *X_dev, int M, int64_t Kp, int nb, void *P_dev, int accumulate,
+                                  int precision, void *stream) {
+    B2_REQUIRE(X_dev && P_dev, B2_EINVAL, "b2_welch_autopower: null pointer");
+    B2_REQUIRE(M > 0 && nb > 0, B2_EINVAL, "b2_welch_autopower: bad M=%d / nb=%d", M, nb);
+    B2_REQUIRE(Kp > 0 && Kp % KC == 0, B2_EINVAL, "b2_welch_autopower: Kp=%lld must be a positive multiple of %d", (long long)Kp, KC);
+    const int64_t items = int64_t(nb) * ((M + 1) / 2);
+    const unsigned blocks = (unsigned)((items + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == B2_F64) autopower_kernel<double><<<blocks, 256, 0, st>>>((const double2 *)X_dev, M, Kp, nb, (double *)P_dev, accumulate);
+    else if (precision == B2_F32) autopower_kernel<float><<<blocks, 256, 0, st>>>((const float2 *)X_dev, M, Kp, nb, (double *)P_dev, accumulate);
+    else { b2_set_error("b2_welch_autopower: bad precision %d", precision); return B2_EINVAL; }
+    B2_LAUNCH_OK("b2_welch_autopower");
+    return B2_OK;
+}
+
+extern "C" int b2_auto_finalize(const void *P_dev, int M, int nb, double inv_frames, double factor, int halve_edges,
+                                int amplitude_sqrt, void *out_dev, void *stream) {
+    B2_REQUIRE(P_dev && out_dev, B2_EINVAL, "b2_auto_finalize: null pointer");
+    B2_REQUIRE(M > 0 && nb > 0, B2_EINVAL, "b2_auto_finalize: bad M=%d / nb=%d", M, nb);
+    const int64_t n = int64_t(nb) * M;
+    auto_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const double *)P_dev, M, nb, inv_frames, factor, halve_edges, amplitude_sqrt, (double *)out_dev);
+    B2_LAUNCH_OK("b2_auto_finalize");
     return B2_OK;
 }

@@ -152,13 +152,14 @@ class _Timer:
 # --------------------------------------------------------------------------- stage 1
 def csm_partial_sums(x, length: int, wl: int, step: int, window: np.ndarray, detrend: bool,
                      fft_scale: float, frame_range: tuple[int, int] | None = None,
-                     precision: str | None = None, device=None, row_offset: int = 0):
+                     precision: str | None = None, device=None, row_offset: int = 0, diag_only: bool = False):
     """Un-normalised per-bin sums S_f = sum_k X_k X_k^H over the frames in `frame_range`.
 
     Returns (S, n_frames_total): S is a complex128 CUDA tensor (nb, M, M) whose lower triangle
     (row >= col) is valid.  Partial sums of disjoint frame ranges add up to the full sum, which
     is what makes the stage frame-shardable.  `x` may hold only the rows
     [row_offset, row_offset + x.shape[0]) of the recording of `length` samples (a rank's shard).
+    With `diag_only` only the auto-spectra are accumulated: S is then float64 (nb, M).
     """
     torch = _torch()
     lib = N.lib()
@@ -181,7 +182,8 @@ def csm_partial_sums(x, length: int, wl: int, step: int, window: np.ndarray, det
 
     win = torch.from_numpy(np.ascontiguousarray(window, dtype=np.float64)).to(device).to(rdt)
     tw = _twiddles(wl, prec, device)
-    S = torch.empty((nb, M, M), dtype=torch.complex128, device=device)
+    S = (torch.empty((nb, M), dtype=torch.float64, device=device) if diag_only
+         else torch.empty((nb, M, M), dtype=torch.complex128, device=device))
     first = True
     timer.mark("start")
     kc = k0
@@ -208,7 +210,10 @@ def csm_partial_sums(x, length: int, wl: int, step: int, window: np.ndarray, det
                                   float(fft_scale), N.ptr(X), Kp, prec, st), "b2_welch_rfft")
         _count()
         timer.mark("k1_rfft")
-        N.check(lib.b2_csm_herk(N.ptr(X), M, Kp, nb, N.ptr(S), 0 if first else 1, prec, st), "b2_csm_herk")
+        if diag_only:
+            N.check(lib.b2_welch_autopower(N.ptr(X), M, Kp, nb, N.ptr(S), 0 if first else 1, prec, st), "b2_welch_autopower")
+        else:
+            N.check(lib.b2_csm_herk(N.ptr(X), M, Kp, nb, N.ptr(S), 0 if first else 1, prec, st), "b2_csm_herk")
         _count()
         timer.mark("k2_herk")
         first = False
@@ -226,6 +231,17 @@ def csm_finalize(S, n_frames: int, factor: float, halve_edges: bool, amplitude_s
     out = torch.empty_like(S)
     N.check(N.lib().b2_csm_finalize(N.ptr(S), M, nb, 1.0 / float(n_frames), float(factor), int(bool(halve_edges)),
                                     int(bool(amplitude_sqrt)), N.ptr(out), N.stream_handle()), "b2_csm_finalize")
+    _count()
+    return out
+
+
+def auto_finalize(P, n_frames: int, factor: float, halve_edges: bool, amplitude_sqrt: bool):
+    """Average / scale / sqrt the summed auto-spectra -> float64 (nb, M) CUDA tensor."""
+    torch = _torch()
+    nb, M = P.shape
+    out = torch.empty_like(P)
+    N.check(N.lib().b2_auto_finalize(N.ptr(P), M, nb, 1.0 / float(n_frames), float(factor), int(bool(halve_edges)),
+                                     int(bool(amplitude_sqrt)), N.ptr(out), N.stream_handle()), "b2_auto_finalize")
     _count()
     return out
 

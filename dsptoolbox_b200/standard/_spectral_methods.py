@@ -83,6 +83,18 @@ def csm_welch_device(time_data, sampling_rate_hz, window_length_samples, window_
     return f, csm
 
 
+def welch_autospectra_device(time_data, sampling_rate_hz, window_length_samples, window_type, overlap_percent,
+                             detrend, average, scaling):
+    """Welch auto-spectra of every channel, left on the device: float64 CUDA tensor (nb, M).
+    Same frames / window / FFT kernels as the CSM, but only sum_k |X|^2 is accumulated."""
+    _validate(window_length_samples, overlap_percent, average)
+    window, step = _window_and_step(window_type, window_length_samples, overlap_percent)
+    fft_scale, factor, halve, amp = _scaling_terms(scaling, window_length_samples, sampling_rate_hz, window)
+    P, n_frames = engine.csm_partial_sums(time_data, int(time_data.shape[0]), window_length_samples, step, window,
+                                          detrend, fft_scale, diag_only=True)
+    return engine.auto_finalize(P, n_frames, factor, halve, amp)
+
+
 def _csm_welch(time_data, sampling_rate_hz: int, window_length_samples: int, window_type,
                overlap_percent, detrend: bool, average: str, scaling: SpectrumScaling):
     """Cross-spectral matrix (frequency, channels, channels) with Welch's method.
@@ -111,12 +123,13 @@ def _welch(x, y, fs_hz: int, window_type, window_length_samples: int, overlap_pe
     flat = x.ndim == 1
     xs = x[:, None] if flat else x
     ch = xs.shape[1]
-    stacked = xs if auto else np.concatenate([xs, y[:, None] if flat else y], axis=1)
-    _, csm = csm_welch_device(stacked, fs_hz, window_length_samples, window_type, overlap_percent,
-                              detrend, average, scaling)
-    idx = np.arange(ch)
     if auto:
-        out = csm[:, idx, idx].real.cpu().numpy()
+        out = welch_autospectra_device(xs, fs_hz, window_length_samples, window_type, overlap_percent,
+                                       detrend, average, scaling).cpu().numpy()
     else:
+        stacked = np.concatenate([xs, y[:, None] if flat else y], axis=1)
+        _, csm = csm_welch_device(stacked, fs_hz, window_length_samples, window_type, overlap_percent,
+                                  detrend, average, scaling)
+        idx = np.arange(ch)
         out = csm[:, idx + ch, idx].cpu().numpy()
     return out[:, 0] if flat else out

@@ -103,6 +103,15 @@ int b2_csm_herk(const void *X_dev, int M, int64_t Kp, int nb, void *S_dev, int a
 int b2_csm_finalize(const void *S_dev, int M, int nb, double inv_frames, double factor,
                     int halve_edges, int amplitude_sqrt, void *csm_out_dev, void *stream);
 
+/* Auto-spectra only (the diagonal of the CSM): P[f][m] (+)= sum_k |X_f[m,k]|^2 as float64 [nb][M], and
+ * its finalisation (mean, factor, DC/Nyquist halving, sqrt for amplitude scalings).  Replaces
+ * `_welch(x, None)` (_spectral_methods.py:146-152, 164-171) behind Signal.get_spectrum's Welch branch
+ * (classes/signal.py:886-898). */
+int b2_welch_autopower(const void *X_dev, int M, int64_t Kp, int nb, void *P_dev, int accumulate,
+                       int precision, void *stream);
+int b2_auto_finalize(const void *P_dev, int M, int nb, double inv_frames, double factor, int halve_edges,
+                     int amplitude_sqrt, void *out_dev, void *stream);
+
 /* K3a: operand preparation for the map: diagonal removal + M/(M-1) gain
  * (beamforming/beamforming.py:841-845), bin selection (:853-855) and the split of the
  * Hermitian matrix into L = strict lower triangle + diag/2 so that h^H C h = 2 Re(h^H L h).

@@ -80,6 +80,13 @@ def main():
         print(f"A {sc:26s} oracle-vs-ref rel-to-max: vectorised {e1:.2e} pairwise {e2:.2e}")
         assert e1 < 1e-13 and e2 < 1e-13
         out["csm_" + sc] = c
+        # Signal.get_spectrum, Welch branch (classes/signal.py:886-898): auto-spectra of every channel
+        sg = dsp.Signal(None, x.copy(), fs)
+        sg.set_spectrum_parameters(window_length_samples=128, scaling=getattr(dsp.SpectrumScaling, sc))
+        fsp, sp = sg.get_spectrum()
+        so = np.stack([R.welch_pair(x[:, i], None, fs, "hann", 128, 50, True, sc) for i in range(x.shape[1])], axis=1)
+        assert rel_to_max(so, sp) < 1e-13
+        out["spectrum_" + sc] = sp
     out["f"] = f
     np.savez_compressed(os.path.join(GOLDEN, "csm_small_scalings.npz"), **out)
 

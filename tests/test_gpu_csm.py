@@ -175,3 +175,21 @@ def test_cache_semantics():
     assert s.get_csm()[1].shape[0] == 257
     s.time_data = rng.standard_normal((4000, 3))
     assert s._csm_dirty
+
+
+@pytest.mark.parametrize("scaling", SCALINGS)
+def test_get_spectrum_welch_golden(golden_dir, scaling):
+    """Signal.get_spectrum, WelchPeriodogram branch (reference classes/signal.py:886-898)."""
+    g = np.load(os.path.join(golden_dir, "csm_small_scalings.npz"))
+    s = dsp.Signal(None, g["x"].copy(), int(g["fs"]))
+    s.set_spectrum_parameters(window_length_samples=int(g["wl"]), scaling=getattr(dsp.SpectrumScaling, scaling))
+    f, sp = s.get_spectrum()
+    ref = g["spectrum_" + scaling]
+    assert sp.shape == ref.shape and sp.dtype == np.float64 and np.array_equal(f, g["f"])
+    assert np.max(np.abs(sp[1:] - ref[1:]) / np.abs(ref[1:])) <= 1e-9
+    # the auto-spectra are the diagonal of the CSM
+    c = s.get_csm()[1]
+    assert np.allclose(sp[1:], np.einsum("fii->fi", c).real[1:], rtol=1e-10)
+    s.spectrum_method = dsp.SpectrumMethod.FFT
+    with pytest.raises(NotImplementedError):
+        s.get_spectrum()

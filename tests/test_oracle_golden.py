@@ -130,3 +130,11 @@ def test_cleansc_next_row(golden_dir, form):
     for fc, frac, tag in [(2000.0, 3, "third"), (3000.0, 0, "single")]:
         assert rel_to_max(R.clean_sc_map(f, c, mic, grid, fc, frac, None, 0.5, False, 343.0, form), ge[f"cleansc_{form}_{tag}"].ravel()) < 1e-9
         assert rel_to_max(R.clean_sc_map(f, c, mic, grid, fc, frac, 5, 0.8, True, 343.0, form), ge[f"cleansc_rd_{form}_{tag}"].ravel()) < 1e-9
+
+
+@pytest.mark.parametrize("scaling", SCALINGS)
+def test_get_spectrum_welch(golden_dir, scaling):
+    g = np.load(os.path.join(golden_dir, "csm_small_scalings.npz"))
+    x = g["x"]
+    so = np.stack([R.welch_pair(x[:, i], None, int(g["fs"]), "hann", int(g["wl"]), 50, True, scaling) for i in range(x.shape[1])], axis=1)
+    assert rel_to_max(so, g["spectrum_" + scaling]) < 1e-13
