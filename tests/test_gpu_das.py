@@ -249,3 +249,33 @@ def test_golden_cleansc(golden_dir):
             assert np.max(np.abs(m2 - ref2)) <= 1e-7 * np.max(np.abs(ref2)), (form, tag)
     with pytest.raises(AssertionError):
         quiet_map(BF.BeamformerCleanSC(sig, ma, grid, st), 2000.0, 3, 5, 1.5)
+
+
+@pytest.mark.parametrize("mode", [m for m in MODES if m in ("mixed", "tf32x3")])
+@pytest.mark.parametrize("M", [300, 520])
+def test_many_microphones_against_oracle(mode, M):
+    """More than two 128-column blocks (3 and 5) and a microphone count off the 16-mic chunk: beyond the
+    shared-memory range of the CUDA-core kernels, so the tensor-core kernel is checked against the oracle."""
+    rng = np.random.default_rng(M)
+    G, F = 200, 6
+    nb = F + 2
+    a = rng.standard_normal((nb, M, 5)) + 1j * rng.standard_normal((nb, M, 5))
+    csm = a @ np.conj(np.swapaxes(a, 1, 2))
+    mic = np.stack([rng.uniform(-0.8, 0.8, M), rng.uniform(-0.8, 0.8, M), rng.uniform(-0.05, 0.05, M)], 1)
+    grid = np.stack([rng.uniform(-1, 1, G), rng.uniform(-1, 1, G), rng.uniform(0.6, 1.4, G)], 1)
+    f = 1000.0 + 50.0 * np.arange(nb)
+    m = engine._MAP_MODES[mode]
+    _, center = R.array_center(mic)
+    for rd in (True, False):
+        op = engine.das_prepare(torch.from_numpy(csm).cuda(), 1, F, rd, m)
+        w = BF.simpson_weights(F, 50.0)
+        out, pb = engine.das_map(op, M, f[1:1 + F], w, 343.0, mic, center, grid, 3, rd, m, per_bin=True)
+        C = R._prepare_csm(csm, M, rd)[1:1 + F]
+        h = R.steering_vector(f[1:1 + F] * 2 * np.pi / 343.0, grid, mic)
+        P = np.einsum("fmg,fmn,fng->gf", h.conj(), C, h).real
+        if rd:
+            P[P < 0] = 0
+        assert np.max(np.abs(pb.cpu().numpy() - P)) <= 1e-4 * P.max()
+        assert np.max(np.abs(out.cpu().numpy() - P @ w)) <= 1e-4 * (P @ w).max()
+    with pytest.raises(NotImplementedError):
+        engine.das_prepare(torch.zeros((1, 1100, 1100), dtype=torch.complex128, device="cuda"), 0, 1, True, m)
