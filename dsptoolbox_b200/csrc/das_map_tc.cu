@@ -39,6 +39,8 @@
 // compensated phase product, one sincos and the TF32 split.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "das_common.cuh"
 
@@ -200,18 +202,22 @@ __host__ __device__ __forceinline__ int sw128_offset(int r, int j) { return (r >
 // constants, |h| = c0 + c1 / r + c2 * r  (the four formulations of beamforming.py:1515-1703).
 __device__ __forceinline__ int tab_index(int m, int row) { return (((m >> 3) * TILE_G) + row) * 8 + (m & 7); }
 
-struct RowAmp { float c0, c1, c2; };
+// The four formulations of beamforming.py:1515-1703 all have |h_m| = c_g * u(r_m) with ONE per-grid-point
+// constant c_g and u = 1 (classic), r (inverse) or 1/r (true power / true location).  Because the map is
+// quadratic in h, the kernels work with h' = u(r) exp(-i phi) and scale the finished power by c_g^2.
+enum { AMP_ONE = 0, AMP_R = 1, AMP_RINV = 2 };
+__host__ __device__ inline int amp_kind(int steering) {
+    return steering == B2_STEER_CLASSIC ? AMP_ONE : (steering == B2_STEER_INVERSE ? AMP_R : AMP_RINV);
+}
 
-// Fill r for the microphones with ((m >> 3) & 1) == half of one grid point; returns the row's
-// amplitude constants.  Padded microphones get r = 1 (their operand columns are zero anyway).
-__device__ __forceinline__ RowAmp row_table(float *__restrict__ tab, int row, int half, bool write, int64_t g,
+// Fill r for the microphones with ((m >> 3) & 1) == half of one grid point (if `write`); returns c_g^2
+// (0 for rows past the end of the grid).  Padded microphones get r = 1 (their operand columns are zero).
+__device__ __forceinline__ double row_table(float *__restrict__ tab, int row, int half, bool write, int64_t g,
                                             int64_t G, const double *__restrict__ grid,
                                             const double *__restrict__ mic, int M, int Mk, double cx0, double cy0,
                                             double cz0, int steering) {
-    RowAmp ra;
-    ra.c0 = ra.c1 = ra.c2 = 0.f;
     const bool valid = g < G;
-    double x = 0, y = 0, z = 0;
+    double x = 0, y = 0, z = 0, c = 0.0;
     if (valid) {
         x = grid[3 * g]; y = grid[3 * g + 1]; z = grid[3 * g + 2];
         double s = 0.0;
@@ -221,10 +227,10 @@ __device__ __forceinline__ RowAmp row_table(float *__restrict__ tab, int row, in
         }
         const double r0 = das_distance(x, y, z, cx0, cy0, cz0);
         switch (steering) {
-        case B2_STEER_CLASSIC: ra.c0 = float(1.0 / double(M)); break;
-        case B2_STEER_INVERSE: ra.c2 = float(1.0 / (double(M) * r0)); break;
-        case B2_STEER_TRUE_POWER: ra.c1 = float(1.0 / (r0 * s)); break;
-        default: ra.c1 = float(1.0 / sqrt(double(M) * s)); break;
+        case B2_STEER_CLASSIC: c = 1.0 / double(M); break;
+        case B2_STEER_INVERSE: c = 1.0 / (double(M) * r0); break;
+        case B2_STEER_TRUE_POWER: c = 1.0 / (r0 * s); break;
+        default: c = 1.0 / sqrt(double(M) * s); break;
         }
     }
     if (write) {
@@ -238,24 +244,25 @@ __device__ __forceinline__ RowAmp row_table(float *__restrict__ tab, int row, in
             }
         }
     }
-    return ra;
+    return c * c;
 }
 
-// H[g, m] = a exp(-i 2 pi q r), q = f / c in cycles per metre: returns (Re, Im).
+// h'[g, m] = u(r) exp(-i 2 pi q r), q = f / c in cycles per metre: returns (Re, Im).
 // The phase is reduced to a fraction of a cycle before the MUFU sincos.  q r < 2^9 cycles, so the
 // fp32 product carries an absolute phase error <= ~1e-4 rad per element -- the same size as the
 // fp32 rounding of r itself; being uncorrelated over microphones it changes the map by < 1e-6 of
 // its maximum (first-order phase perturbations cancel at a coherent peak).
-__device__ __forceinline__ float2 steer(float r, const RowAmp &amp, float q) {
+template <int AMP>
+__device__ __forceinline__ float2 steer(float r, float q) {
     const float p = q * r;
     const float rn = (p + 12582912.0f) - 12582912.0f;         // round to nearest integer (|p| < 2^22)
     const float fr = p - rn;
     float sn, cs;
     __sincosf(6.28318530717958647692f * fr, &sn, &cs);
-    float rinv;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r));
-    const float a = fmaf(amp.c2, r, fmaf(amp.c1, rinv, amp.c0));
-    return make_float2(a * cs, -a * sn);
+    if (AMP == AMP_ONE) return make_float2(cs, -sn);
+    float u = r;
+    if (AMP == AMP_RINV) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(r));
+    return make_float2(u * cs, -u * sn);
 }
 
 // top 11 significant bits by truncation: the residual x - trunc(x) is exact and is carried by the
@@ -293,6 +300,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
     const int NKC = (M + KCH - 1) / KCH;          // K chunks
     const int Mk = NKC * KCH;
     const int NBLK = (M + NB - 1) / NB;           // column blocks
+    const int akind = amp_kind(steering);
     float *tab = scratch + size_t(blockIdx.x) * TILE_G * Mk;
 
     // stage s: [A_hi][A_lo?][B_hi][B_lo?]
@@ -319,8 +327,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             B2_UNIT_DECODE
             // the epilogue warps are done with the previous tile's table before it is overwritten
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            const RowAmp amp = row_table(tab, r, half, true, int64_t(tile) * TILE_G + r, G, grid, mic, M, Mk, cx0, cy0,
-                                         cz0, steering);
+            row_table(tab, r, half, true, int64_t(tile) * TILE_G + r, G, grid, mic, M, Mk, cx0, cy0, cz0, steering);
             __threadfence_block();
             asm volatile("bar.sync 1, 512;" ::: "memory");
             // distances of this thread's 8 microphones of a chunk: 32 contiguous bytes, coalesced over rows
@@ -344,23 +351,29 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                         load_r(kn, r_lo, r_hi);
                         float4 hi4[4], lo4[4];
                         uint4 mixlo[2], mixb[2];          // mixed mode: bf16 residuals / bf16 values of 8 mics
+                        auto synth = [&](auto amp_tag) {
+                            constexpr int AMP = decltype(amp_tag)::value;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 h0 = steer(rr[2 * j], amp, bf);
-                            const float2 h1 = steer(rr[2 * j + 1], amp, bf);
-                            if (PASSES == 1) hi4[j] = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
-                            else hi4[j] = make_float4(trunc_tf32(h0.x), trunc_tf32(h0.y), trunc_tf32(h1.x), trunc_tf32(h1.y));
-                            if (PASSES == 3)   // residuals are exact in fp32; the tensor core keeps their top 11 bits
-                                lo4[j] = make_float4(h0.x - hi4[j].x, h0.y - hi4[j].y, h1.x - hi4[j].z, h1.y - hi4[j].w);
-                            if (PASSES == 2) {
-                                const uint32_t l0 = pack_bf16(h0.x - hi4[j].x, h0.y - hi4[j].y);
-                                const uint32_t l1 = pack_bf16(h1.x - hi4[j].z, h1.y - hi4[j].w);
-                                const uint32_t b0 = pack_bf16(h0.x, h0.y), b1 = pack_bf16(h1.x, h1.y);
-                                uint32_t *pl = reinterpret_cast<uint32_t *>(&mixlo[j >> 1]) + 2 * (j & 1);
-                                uint32_t *pb = reinterpret_cast<uint32_t *>(&mixb[j >> 1]) + 2 * (j & 1);
-                                pl[0] = l0; pl[1] = l1; pb[0] = b0; pb[1] = b1;
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 h0 = steer<AMP>(rr[2 * j], bf);
+                                const float2 h1 = steer<AMP>(rr[2 * j + 1], bf);
+                                if (PASSES == 1) hi4[j] = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
+                                else hi4[j] = make_float4(trunc_tf32(h0.x), trunc_tf32(h0.y), trunc_tf32(h1.x), trunc_tf32(h1.y));
+                                if (PASSES == 3)   // residuals are exact in fp32; the tensor core keeps their top 11 bits
+                                    lo4[j] = make_float4(h0.x - hi4[j].x, h0.y - hi4[j].y, h1.x - hi4[j].z, h1.y - hi4[j].w);
+                                if (PASSES == 2) {
+                                    const uint32_t l0 = pack_bf16(h0.x - hi4[j].x, h0.y - hi4[j].y);
+                                    const uint32_t l1 = pack_bf16(h1.x - hi4[j].z, h1.y - hi4[j].w);
+                                    const uint32_t b0 = pack_bf16(h0.x, h0.y), b1 = pack_bf16(h1.x, h1.y);
+                                    uint32_t *pl = reinterpret_cast<uint32_t *>(&mixlo[j >> 1]) + 2 * (j & 1);
+                                    uint32_t *pb = reinterpret_cast<uint32_t *>(&mixb[j >> 1]) + 2 * (j & 1);
+                                    pl[0] = l0; pl[1] = l1; pb[0] = b0; pb[1] = b1;
+                                }
                             }
-                        }
+                        };
+                        if (akind == AMP_RINV) synth(std::integral_constant<int, AMP_RINV>{});
+                        else if (akind == AMP_R) synth(std::integral_constant<int, AMP_R>{});
+                        else synth(std::integral_constant<int, AMP_ONE>{});
                         mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
                         const uint32_t ahi = a_base + s * CF::STAGE;
                         const uint32_t alo = ahi + (CF::NSPLIT - 1) * A_TILE;
@@ -397,7 +410,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             B2_UNIT_DECODE
             const int64_t g = int64_t(tile) * TILE_G + r;
             asm volatile("bar.sync 1, 512;" ::: "memory");
-            const RowAmp amp = row_table(tab, r, 0, false, g, G, grid, mic, M, Mk, cx0, cy0, cz0, steering);
+            const double c2 = row_table(tab, r, 0, false, g, G, grid, mic, M, Mk, cx0, cy0, cz0, steering);
             asm volatile("bar.sync 1, 512;" ::: "memory");   // table of this tile is complete
             double acc_map = 0.0;
             for (int fi = f_begin; fi < f_end; ++fi) {
@@ -424,20 +437,26 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                             rq[2 * k8 + 1] = __ldcg(src + 1);
                         }
                         tmem_ld_wait();
+                        auto reduce = [&](auto amp_tag) {
+                            constexpr int AMP = decltype(amp_tag)::value;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            // padded microphones have all-zero operand rows, so T is 0 there: no bounds test
-                            const float2 h0 = steer(rq[j].x, amp, bf), h1 = steer(rq[j].y, amp, bf);
-                            const float2 h2 = steer(rq[j].z, amp, bf), h3 = steer(rq[j].w, amp, bf);
-                            p0 = fmaf(t[8 * j], h0.x, p0);
-                            p0 = fmaf(-t[8 * j + 1], h0.y, p0);
-                            p1 = fmaf(t[8 * j + 2], h1.x, p1);
-                            p1 = fmaf(-t[8 * j + 3], h1.y, p1);
-                            p0 = fmaf(t[8 * j + 4], h2.x, p0);
-                            p0 = fmaf(-t[8 * j + 5], h2.y, p0);
-                            p1 = fmaf(t[8 * j + 6], h3.x, p1);
-                            p1 = fmaf(-t[8 * j + 7], h3.y, p1);
-                        }
+                            for (int j = 0; j < 4; ++j) {
+                                // padded microphones have all-zero operand rows, so T is 0 there: no bounds test
+                                const float2 h0 = steer<AMP>(rq[j].x, bf), h1 = steer<AMP>(rq[j].y, bf);
+                                const float2 h2 = steer<AMP>(rq[j].z, bf), h3 = steer<AMP>(rq[j].w, bf);
+                                p0 = fmaf(t[8 * j], h0.x, p0);
+                                p0 = fmaf(-t[8 * j + 1], h0.y, p0);
+                                p1 = fmaf(t[8 * j + 2], h1.x, p1);
+                                p1 = fmaf(-t[8 * j + 3], h1.y, p1);
+                                p0 = fmaf(t[8 * j + 4], h2.x, p0);
+                                p0 = fmaf(-t[8 * j + 5], h2.y, p0);
+                                p1 = fmaf(t[8 * j + 6], h3.x, p1);
+                                p1 = fmaf(-t[8 * j + 7], h3.y, p1);
+                            }
+                        };
+                        if (akind == AMP_RINV) reduce(std::integral_constant<int, AMP_RINV>{});
+                        else if (akind == AMP_R) reduce(std::integral_constant<int, AMP_R>{});
+                        else reduce(std::integral_constant<int, AMP_ONE>{});
                     }
                     tc_fence_before();
                     mbar_arrive(&tempty[buf]);
@@ -447,7 +466,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 if (half == 1) pp[r] = p0 + p1;
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (half == 0) {
-                    double p = double(p0 + p1) + double(pp[r]);
+                    double p = (double(p0 + p1) + double(pp[r])) * c2;        // |h|^2 scale of this grid point
                     if (clamp_negative && p < 0.0) p = 0.0;                         // beamforming.py:871-872
                     acc_map += weights[fi] * p;                                       // :875-876
                     if (per_bin != nullptr && g < G) per_bin[g * nbins + fi] = p;
