@@ -207,13 +207,15 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------- B200 arm
-def tf32_peak(torch, sustained_seconds=2.5):
-    """cuBLAS TF32 GEMM throughput (8192^3): best of 5 (burst) and a back-to-back loop of
-    `sustained_seconds` (sustained, under the power cap) -- the tensor roofline denominators that
-    MEASURED_PEAKS.json (bf16 only) does not carry.  Returns (burst, sustained) in TFLOP/s."""
+def gemm_peak(torch, dtype="tf32", sustained_seconds=2.5):
+    """cuBLAS GEMM throughput (8192^3) in TF32 or FP16: best of 5 (burst) and a back-to-back loop of
+    `sustained_seconds` (sustained, under the power cap) -- the tensor roofline denominators measured
+    on the same GPU in the same run (MEASURED_PEAKS.json carries bf16 only).
+    Returns (burst, sustained) in TFLOP/s."""
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
-    a = torch.randn(8192, 8192, device="cuda"); b = torch.randn(8192, 8192, device="cuda")
+    tdt = torch.float16 if dtype == "f16" else torch.float32
+    a = torch.randn(8192, 8192, device="cuda").to(tdt); b = torch.randn(8192, 8192, device="cuda").to(tdt)
     for _ in range(2):
         a @ b
     best = 1e9
@@ -253,7 +255,7 @@ def run_b200(args):
     if args.map_mode:
         engine.config.map_mode = args.map_mode
     mode = engine.resolve_map_mode()
-    mode_name = {0: "simt_f64", 1: "simt_f32", 2: "tf32", 3: "tf32x3", 4: "mixed"}[mode]
+    mode_name = {0: "simt_f64", 1: "simt_f32", 2: "tf32", 3: "tf32x3", 4: "mixed", 5: "f16x3"}[mode]
 
     w, pos, L, lines = problem(args)
     M, wl = w["mics"], w["wl"]
@@ -432,7 +434,10 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    peak_tf32_burst, peak_tf32_sustained = tf32_peak(torch)
+    # FP16x3 mode runs three kind::f16 products per algorithmic product -> FP16 GEMM peak / 3; the TF32-based
+    # modes are counted in TF32-equivalents against the TF32 GEMM peak
+    peak_kind = "f16" if mode == N.MAP_TC_F16X3 else "tf32"
+    peak_tf32_burst, peak_tf32_sustained = gemm_peak(torch, peak_kind)
     # the map kernel runs for seconds under the 1 kW cap: the sustained figure is its denominator;
     # a kernel shorter than ~0.5 s is compared with the burst figure
     peak_tf32 = peak_tf32_sustained if ms_map_kernel > 500.0 else peak_tf32_burst
@@ -444,7 +449,7 @@ def run_b200(args):
     hbm = peaks.get("hbm_gbs", 6650.0)
     # TF32-equivalent tensor products per algorithmic product: 3 (split TF32), 2 (TF32 + one BF16 product of
     # double depth at twice the TF32 rate), 1 (single pass)
-    passes = {N.MAP_TC_TF32X3: 3, N.MAP_TC_MIXED: 2}.get(mode, 1)
+    passes = {N.MAP_TC_TF32X3: 3, N.MAP_TC_MIXED: 2, N.MAP_TC_F16X3: 3}.get(mode, 1)
     Gr = g1 - g0
     alg_flops = 4.0 * M * M * Gr * F
     achieved = alg_flops / (ms_map_kernel * 1e-3) / 1e12
@@ -464,8 +469,9 @@ def run_b200(args):
                 "traffic_note": "dram__bytes_read+write of one launch (ncu --set full, profiles/); the 4.3 GB operand "
                                 "is re-streamed by each of the 53 tile waves -> 0.5 % of HBM bandwidth, compute-bound",
                 "algorithmic_flops_per_launch": alg_flops, "kernel_ms": ms_map_kernel,
-                "peak_source": f"cuBLAS TF32 8192^3 measured in this run: burst {peak_tf32_burst:.1f}, sustained {peak_tf32_sustained:.1f} TFLOP/s; used {peak_tf32:.1f}"
-                               + (" / 3 (split-TF32: three tensor products per algorithmic product)" if passes == 3 else "")
+                "peak_source": f"cuBLAS {peak_kind.upper()} 8192^3 measured in this run: burst {peak_tf32_burst:.1f}, sustained {peak_tf32_sustained:.1f} TFLOP/s; used {peak_tf32:.1f}"
+                               + (" / 3 (FP16x3: three FP16 tensor products per algorithmic product)" if mode == N.MAP_TC_F16X3 else "")
+                               + (" / 3 (split-TF32: three tensor products per algorithmic product)" if mode == N.MAP_TC_TF32X3 else "")
                                + (" / 2 (mixed: one TF32 product + one double-depth BF16 product = 2 TF32-equivalents)" if passes == 2 else "")
                                + f"; MEASURED_PEAKS bf16 {peaks.get('bf16_tflops')} (of {'measured' if peaks else 'fallback'})"}
     s_in, s_x = (8, 16) if engine.config.csm_precision == "fp64" else (4, 8)
@@ -494,7 +500,8 @@ def run_b200(args):
         "metric": "das_map_grid_point_bins_per_s", "value": G * F / (ms_map * 1e-3), "unit": "grid-pt*bins/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": {3: "tf32x3 (fp32 accumulate) map; f64 CSM", 4: "tf32+bf16x2 (fp32 accumulate) map; f64 CSM"}.get(
+        "dtype": {3: "tf32x3 (fp32 accumulate) map; f64 CSM", 4: "tf32+bf16x2 (fp32 accumulate) map; f64 CSM",
+                  5: "f16x3 (two FP16 halves per operand, 3 products, fp32 accumulate) map; f64 CSM"}.get(
             mode, f"{mode_name} map; {engine.config.csm_precision} CSM"),
         "data": "synthetic",
         "config": {"workload": w["label"], "M": M, "L": L, "nfft": wl, "frames": K, "bins": nb, "G": G, "F": F,

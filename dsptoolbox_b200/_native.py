@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("B2DSP_LIB") or os.path.join(_HERE, "csrc", "libb2dsp.
 
 # precision / mode codes (include/b2dsp.h)
 F64, F32 = 0, 1
-MAP_SIMT_F64, MAP_SIMT_F32, MAP_TC_TF32, MAP_TC_TF32X3, MAP_TC_MIXED = 0, 1, 2, 3, 4
+MAP_SIMT_F64, MAP_SIMT_F32, MAP_TC_TF32, MAP_TC_TF32X3, MAP_TC_MIXED, MAP_TC_F16X3 = 0, 1, 2, 3, 4, 5
 STEER_CLASSIC, STEER_INVERSE, STEER_TRUE_POWER, STEER_TRUE_LOCATION = 0, 1, 2, 3
 E_INVAL, E_UNSUPPORTED, E_CUDA = -1, -2, -3
 

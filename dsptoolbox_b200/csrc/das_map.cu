@@ -206,7 +206,7 @@ extern "C" int64_t b2_das_operand_bytes(int M, int nbins, int mode) {
     const int64_t Mp = das_padded_mics(M);
     if (mode == B2_MAP_SIMT_F64) return int64_t(nbins) * Mp * Mp * 16;
     if (mode == B2_MAP_SIMT_F32) return int64_t(nbins) * Mp * Mp * 8;
-    if (mode == B2_MAP_TC_TF32 || mode == B2_MAP_TC_TF32X3 || mode == B2_MAP_TC_MIXED) return b2_das_tc_operand_bytes(M, nbins, mode);
+    if (mode >= B2_MAP_TC_TF32 && mode <= B2_MAP_TC_F16X3) return b2_das_tc_operand_bytes(M, nbins, mode);
     b2_set_error("b2_das_operand_bytes: bad mode %d", mode);
     return B2_EINVAL;
 }
@@ -219,7 +219,7 @@ extern "C" int b2_das_prepare(const void *csm_dev, int M, int nb, int bin0, int 
                "b2_das_prepare: bins [%d, %d) outside [0, %d)", bin0, bin0 + nbins, nb);
     B2_REQUIRE(nbins <= 65535, B2_EINVAL, "b2_das_prepare: too many bins");
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == B2_MAP_TC_TF32 || mode == B2_MAP_TC_TF32X3 || mode == B2_MAP_TC_MIXED)
+    if (mode >= B2_MAP_TC_TF32 && mode <= B2_MAP_TC_F16X3)
         return b2_das_tc_prepare(csm_dev, M, nb, bin0, nbins, remove_diag, op_dev, mode, st);
     const int Mp = das_padded_mics(M);
     const double gain = remove_diag ? double(M) / double(M - 1) : 1.0;   // beamforming.py:843
@@ -253,6 +253,7 @@ extern "C" int b2_das_map(const void *op_dev, int M, int nbins, const void *freq
     case B2_MAP_TC_TF32:
     case B2_MAP_TC_TF32X3:
     case B2_MAP_TC_MIXED:
+    case B2_MAP_TC_F16X3:
         return b2_das_tc_map(op_dev, M, nbins, freqs_dev, weights_dev, c, mic_xyz_dev, center_xyz, grid_xyz_dev, G, steering, clamp_negative, map_out_dev, per_bin_out_dev, mode, st);
     default: break;
     }

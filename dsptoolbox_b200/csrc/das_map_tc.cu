@@ -17,8 +17,9 @@
 // in TMEM as fp32.  L is lower triangular: K chunks (16 microphones) entirely above the diagonal
 // are skipped, and a chunk that straddles it only touches its first w = 16, 32, ... columns, so
 // the MMA is issued with N = 2w and only the first 2w operand rows are fetched.  Chunks are
-// walked from the last one down so that the first MMA of an accumulator (the one that
-// overwrites instead of accumulating) is the widest.
+// walked widest, narrowest, second widest, ... so that the first MMA of an accumulator (the one
+// that overwrites instead of accumulating) is the widest and tensor-heavy and synthesis-heavy
+// chunks alternate.
 // The epilogue warps read D back with tcgen05.ld, re-synthesise H[g, n] and reduce
 //     P[g, f] = sum_n Re(T[g, n] H[g, n]),   clamp,   map[g] += w_f P[g, f]
 // while the next column block accumulates into the second TMEM buffer.
@@ -29,15 +30,24 @@
 // the TF32 rate: the second operand image of a stage holds, per row, [bf16(x - hi) | bf16(x)] for
 // A and [bf16(y) | bf16(y - hi)] for B, so that sum_k A2[k] B2[k] = lo_A*y + x*lo_B.  Tensor work
 // drops from 3 to 2 TF32-equivalents per product at ~2^-20 relative accuracy.
+// FP16x3 mode (PASSES = 4): both operands are split into two FP16 halves x = f1 + f2 (22 significant
+// bits) and f1*g1 + f1*g2 + f2*g1 is accumulated as three kind::f16 products: 1.5 TF32-equivalents
+// of tensor work and -- what matters more, because the kernel is bound by shared-memory bandwidth
+// (every operand byte is written once and read once per product) -- operand rows of 128 B per 16
+// microphones instead of 256 B.  FP16's narrow exponent is handled by exact power-of-two scalings:
+// one per bin for L (max |L| -> [2^11, 2^12)) and one per grid point for the amplitude u(r), both
+// divided out of the finished power in fp64.
 //
-// Warp roles (576 threads): 0-7 steering synthesis (two threads per grid point), 8-15 epilogue
-// (two warps per TMEM lane quadrant), 16 MMA issue + TMEM allocation, 17 operand loader.
-// Pipelines: smem ring full/empty mbarriers (loader + synthesis -> MMA -> tcgen05.commit), TMEM
-// full/empty mbarriers (MMA -> epilogue).  The bin-independent part of the steering vector
+// Warp roles: 4*TPR steering-synthesis warps (TPR threads per grid point), 8 epilogue warps (two per
+// TMEM lane quadrant), 1 MMA issue + TMEM allocation warp, 1 operand loader warp.
+// Pipelines: two shared-memory rings with full/empty mbarriers -- A (synthesis -> MMA, 3+ stages) and
+// B (loader -> MMA, 2-3 stages), both released by tcgen05.commit -- and TMEM full/empty mbarriers
+// (MMA -> epilogue).  The bin-independent part of the steering vector
 // (distance r and amplitude a of every (grid point, microphone) pair of the tile) is computed
 // once per tile in fp64 and parked in an L2-resident scratch table, so the per-bin work is one
 // compensated phase product, one sincos and the TF32 split.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <type_traits>
 
@@ -49,9 +59,18 @@ namespace {
 constexpr int TILE_G = 128;
 constexpr int KCH = 16;                       // microphones per K chunk = 32 reals = one 128 B row
 constexpr int A_TILE = TILE_G * 128;          // bytes of one A operand image
-constexpr int TC_THREADS = 576;
-constexpr int NGEN = 256;                     // synthesis threads
+#ifndef B2_TPR
+#define B2_TPR 2
+#endif
+constexpr int TPR = B2_TPR;                   // synthesis threads per grid point (1, 2 or 4)
+constexpr int MPT = KCH / TPR;                // microphones of a chunk per synthesis thread
+constexpr int G4 = MPT / 4;                   // ... as groups of 4 (16 bytes of the distance table)
+constexpr int NGEN = TILE_G * TPR;            // synthesis threads
 constexpr int NEPI = 256;                     // epilogue threads
+constexpr int W_EPI0 = NGEN / 32;             // first epilogue warp
+constexpr int W_MMA = W_EPI0 + NEPI / 32;     // MMA issue warp; the loader warp follows
+constexpr int TC_THREADS = NGEN + NEPI + 64;
+
 constexpr int MAX_CTAS = 160;                 // scratch tables are sized for this many persistent CTAs
 constexpr int MAX_MICS = 1024;
 
@@ -60,13 +79,39 @@ __host__ __device__ constexpr int tc_nb(int M) { return M <= 32 ? 32 : (M <= 64 
 template <int NB, int PASSES> struct TcCfg {
     static constexpr int UMMA_N = 2 * NB;
     static constexpr int B_TILE = UMMA_N * 128;
-    static constexpr int NSPLIT = PASSES == 1 ? 1 : 2;                 // operand images per stage (hi[, correction])
-    static constexpr int STAGE = NSPLIT * (A_TILE + B_TILE);
-    static constexpr int NSTAGE_RAW = (208 * 1024) / STAGE;
-    static constexpr int NSTAGE = NSTAGE_RAW > 6 ? 6 : NSTAGE_RAW;
+    static constexpr int NSPLIT = (PASSES == 1 || PASSES == 4) ? 1 : 2; // operand images per stage (hi[, correction])
+    // Two independent shared-memory rings: A (synthesised steering tiles, small stages) and B (streamed
+    // operand images, large stages).  The A ring is made as deep as the 227 KB allow, because the
+    // synthesis warps and the tensor pipe have different per-chunk costs (the MMA width varies with the
+    // chunk) and a deep ring is what lets them overlap instead of waiting for each other.
+    static constexpr int A_STAGE = NSPLIT * A_TILE;
+    static constexpr int B_STAGE = NSPLIT * B_TILE;
+#ifdef B2_NSB
+    static constexpr int NSB = B2_NSB;
+#else
+    static constexpr int NSB = B_STAGE >= 64 * 1024 ? 2 : 3;
+#endif
+    static constexpr int NSA_RAW = (224 * 1024 - NSB * B_STAGE) / A_STAGE;
+#ifdef B2_NSA
+    static constexpr int NSA = B2_NSA;
+#else
+    static constexpr int NSA = NSA_RAW > 6 ? 6 : NSA_RAW;
+#endif
     static constexpr int TMEM_COLS = 2 * UMMA_N;                       // two accumulator buffers
-    static constexpr int SMEM = 1024 /*align slack*/ + NSTAGE * STAGE + 2 * TILE_G * 4 + 256;
+    static constexpr int SMEM = 1024 /*align slack*/ + NSA * A_STAGE + NSB * B_STAGE + 2 * TILE_G * 4 + 256;
 };
+
+#ifdef B2_MAP_PROFILE
+// Debug instrumentation: cycles each role spends blocked on its barriers (CTA 0 only).
+// [0] synthesis wait empty  [1] synthesis total  [2] mma wait full  [3] mma wait tmem-empty  [4] mma total
+// [5] epilogue wait tmem-full  [6] epilogue total  [7] mma wait B ring full
+__device__ unsigned long long g_map_prof[8];
+#define PROF_T0() const long long _t0 = clock64()
+#define PROF_ADD(slot, cond) do { if (cond) atomicAdd(&g_map_prof[slot], (unsigned long long)(clock64() - _t0)); } while (0)
+#else
+#define PROF_T0()
+#define PROF_ADD(slot, cond)
+#endif
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -98,6 +143,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "r"(addr), "r"(parity), "r"(0x989680u)
             : "memory");
     } while (!done);
+}
+// non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -168,6 +227,22 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(64) << 32) | (uint64_t(1) << 46) |
            (uint64_t(2) << 61);
 }
+// The same descriptor as (constant high word, low word): low = start>>4 | LBO<<16, so that stepping through
+// stages and K slices is 32-bit arithmetic.
+constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return (uint64_t(DESC_HI) << 32) | lo; }
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 // kind::tf32 instruction descriptor: fp32 accumulate, TF32 x TF32, both operands K-major
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
@@ -175,6 +250,10 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
 // kind::f16 instruction descriptor: fp32 accumulate, BF16 x BF16, both operands K-major
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+// same, FP16 x FP16
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -190,6 +269,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {   
     __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);
     return *reinterpret_cast<uint32_t *>(&v);
 }
+__device__ __forceinline__ uint32_t pack_f16(__half2 v) { return *reinterpret_cast<uint32_t *>(&v); }
 __device__ __forceinline__ void sts128u(uint32_t saddr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -197,10 +277,10 @@ __device__ __forceinline__ void sts128u(uint32_t saddr, uint4 v) {
 __host__ __device__ __forceinline__ int sw128_offset(int r, int j) { return (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4); }
 
 // ---------------------------------------------------------------- per-tile geometry table
-// tab[((m >> 3) * 128 + row) * 8 + (m & 7)] = r = |grid_row - mic_m| (fp32 of an fp64 result): the
+// tab[((m >> 2) * 128 + row) * 4 + (m & 3)] = r = |grid_row - mic_m| (fp32 of an fp64 result): the
 // bin-independent part of the steering phase.  The amplitude follows from r and three per-row
 // constants, |h| = c0 + c1 / r + c2 * r  (the four formulations of beamforming.py:1515-1703).
-__device__ __forceinline__ int tab_index(int m, int row) { return (((m >> 3) * TILE_G) + row) * 8 + (m & 7); }
+__device__ __forceinline__ int tab_index(int m, int row) { return (((m >> 2) * TILE_G) + row) * 4 + (m & 3); }
 
 // The four formulations of beamforming.py:1515-1703 all have |h_m| = c_g * u(r_m) with ONE per-grid-point
 // constant c_g and u = 1 (classic), r (inverse) or 1/r (true power / true location).  Because the map is
@@ -210,14 +290,16 @@ __host__ __device__ inline int amp_kind(int steering) {
     return steering == B2_STEER_CLASSIC ? AMP_ONE : (steering == B2_STEER_INVERSE ? AMP_R : AMP_RINV);
 }
 
-// Fill r for the microphones with ((m >> 3) & 1) == half of one grid point (if `write`); returns c_g^2
+// Fill r for the microphones with ((m >> 2) % TPR) == part of one grid point (if `write`); returns c_g^2
 // (0 for rows past the end of the grid).  Padded microphones get r = 1 (their operand columns are zero).
-__device__ __forceinline__ double row_table(float *__restrict__ tab, int row, int half, bool write, int64_t g,
+// *amp_scale = the power of two s_g that brings u(r) of this grid point near 1 (FP16 operands).
+__device__ __forceinline__ double row_table(float *__restrict__ tab, int row, int part, bool write, int64_t g,
                                             int64_t G, const double *__restrict__ grid,
                                             const double *__restrict__ mic, int M, int Mk, double cx0, double cy0,
-                                            double cz0, int steering) {
+                                            double cz0, int steering, float *amp_scale) {
     const bool valid = g < G;
     double x = 0, y = 0, z = 0, c = 0.0;
+    *amp_scale = 1.0f;
     if (valid) {
         x = grid[3 * g]; y = grid[3 * g + 1]; z = grid[3 * g + 2];
         double s = 0.0;
@@ -226,6 +308,11 @@ __device__ __forceinline__ double row_table(float *__restrict__ tab, int row, in
             s += 1.0 / (dx * dx + dy * dy + dz * dz);
         }
         const double r0 = das_distance(x, y, z, cx0, cy0, cz0);
+        if (steering != B2_STEER_CLASSIC && r0 > 0.0 && r0 < 1e30) {
+            int e = ilogb(r0);                                     // r0 = 2^e * [1, 2)
+            e = e < -60 ? -60 : (e > 60 ? 60 : e);
+            *amp_scale = float(scalbn(1.0, steering == B2_STEER_INVERSE ? -e : e));
+        }
         switch (steering) {
         case B2_STEER_CLASSIC: c = 1.0 / double(M); break;
         case B2_STEER_INVERSE: c = 1.0 / (double(M) * r0); break;
@@ -234,10 +321,10 @@ __device__ __forceinline__ double row_table(float *__restrict__ tab, int row, in
         }
     }
     if (write) {
-        for (int m8 = half * 8; m8 < Mk; m8 += 16) {
+        for (int m4 = part * 4; m4 < Mk; m4 += 4 * TPR) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = m8 + i;
+            for (int i = 0; i < 4; ++i) {
+                const int m = m4 + i;
                 float v = 1.0f;
                 if (valid && m < M) v = float(das_distance(x, y, z, mic[3 * m], mic[3 * m + 1], mic[3 * m + 2]));
                 tab[tab_index(m, row)] = v;
@@ -253,7 +340,7 @@ __device__ __forceinline__ double row_table(float *__restrict__ tab, int row, in
 // fp32 rounding of r itself; being uncorrelated over microphones it changes the map by < 1e-6 of
 // its maximum (first-order phase perturbations cancel at a coherent peak).
 template <int AMP>
-__device__ __forceinline__ float2 steer(float r, float q) {
+__device__ __forceinline__ float2 steer(float r, float q, float us = 1.0f) {
     const float p = q * r;
     const float rn = (p + 12582912.0f) - 12582912.0f;         // round to nearest integer (|p| < 2^22)
     const float fr = p - rn;
@@ -262,6 +349,7 @@ __device__ __forceinline__ float2 steer(float r, float q) {
     if (AMP == AMP_ONE) return make_float2(cs, -sn);
     float u = r;
     if (AMP == AMP_RINV) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(r));
+    u *= us;                                                   // us = 1 except for the FP16 operands
     return make_float2(u * cs, -u * sn);
 }
 
@@ -274,6 +362,20 @@ __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
 }
 
 // ---------------------------------------------------------------- the kernel
+// Order in which the K chunks [kc0, NKC) of one accumulator are walked: widest, narrowest, second
+// widest, second narrowest, ...  (chunk width = number of columns it can reach, growing with kc).
+// The first chunk (the one whose MMA overwrites the accumulator) is the widest, and wide (tensor-
+// heavy) and narrow (synthesis-heavy) chunks alternate, so the A ring only has to absorb the
+// imbalance of one pair of chunks.
+__device__ __forceinline__ int chunk_at(int i, int kc0, int NKC) {
+#ifdef B2_CHUNK_DESCENDING
+    (void)kc0;
+    return NKC - 1 - i;                                     // A/B-test build: plain descending walk
+#else
+    return (i & 1) ? kc0 + (i >> 1) : NKC - 1 - (i >> 1);
+#endif
+}
+
 // work unit -> (tile of 128 grid points, contiguous range of bins); units are dealt round-robin
 #define B2_UNIT_DECODE                                                        \
     const int tile = unit / nsplit, upart = unit - tile * nsplit;            \
@@ -282,19 +384,21 @@ __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
 
 template <int NB, int PASSES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scratch, int M, int nbins,
+das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scratch,
+                  const float *__restrict__ bin_scale, int M, int nbins,
                   const double *__restrict__ freqs, const double *__restrict__ weights, double inv_c,
                   const double *__restrict__ mic, double cx0, double cy0, double cz0,
                   const double *__restrict__ grid, int64_t G, int steering, int clamp_negative,
                   double *__restrict__ map_out, double *__restrict__ per_bin, int ntiles, int nsplit) {
     using CF = TcCfg<NB, PASSES>;
-    constexpr int UMMA_N = CF::UMMA_N, NSTAGE = CF::NSTAGE;
+    constexpr int UMMA_N = CF::UMMA_N, NSA = CF::NSA, NSB = CF::NSB;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float *part = reinterpret_cast<float *>(smem + NSTAGE * CF::STAGE);                // [2][128] epilogue partials
+    float *part = reinterpret_cast<float *>(smem + NSA * CF::A_STAGE + NSB * CF::B_STAGE);   // [2][128] epilogue partials
     uint64_t *bars = reinterpret_cast<uint64_t *>(part + 2 * TILE_G);
-    uint64_t *full = bars, *empty = bars + NSTAGE, *tfull = bars + 2 * NSTAGE, *tempty = bars + 2 * NSTAGE + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * NSTAGE + 4);
+    uint64_t *fullA = bars, *emptyA = fullA + NSA, *fullB = emptyA + NSA, *emptyB = fullB + NSB;
+    uint64_t *tfull = emptyB + NSB, *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NKC = (M + KCH - 1) / KCH;          // K chunks
@@ -303,104 +407,152 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
     const int akind = amp_kind(steering);
     float *tab = scratch + size_t(blockIdx.x) * TILE_G * Mk;
 
-    // stage s: [A_hi][A_lo?][B_hi][B_lo?]
-    auto a_tile = [&](int s, int split) { return smem + s * CF::STAGE + split * A_TILE; };
-    auto b_tile = [&](int s, int split) { return smem + s * CF::STAGE + CF::NSPLIT * A_TILE + split * CF::B_TILE; };
+    // A ring stage: [A_hi][A_corr?]; B ring stage: [B_hi][B_corr?]
+    auto a_tile = [&](int s, int split) { return smem + s * CF::A_STAGE + split * A_TILE; };
+    auto b_tile = [&](int s, int split) { return smem + NSA * CF::A_STAGE + s * CF::B_STAGE + split * CF::B_TILE; };
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], NGEN + 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEPI); }
+        for (int s = 0; s < NSA; ++s) { mbar_init(&fullA[s], NGEN / 32); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < NSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEPI / 32); }
         fence_barrier_init();
     }
-    if (warp == 16) tmem_alloc(tmem_slot, CF::TMEM_COLS);
+    if (warp == W_MMA) tmem_alloc(tmem_slot, CF::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+#ifdef B2_MAP_PROFILE
+    const long long t_kernel0 = clock64();
+#endif
 
-    if (warp < 8) {
+    if (warp < W_EPI0) {
         // =========================== steering synthesis -> A operand tiles ===========================
-        const int r = tid & 127, half = tid >> 7;            // row of the tile, which 8 of a chunk's 16 mics
+        // TPR threads per grid point; each handles MPT = 16 / TPR microphones of every chunk as G4 groups of 4
+        const int r = tid & 127, part = tid >> 7;
         const uint32_t a_base = smem_u32(smem);
-        uint32_t it = 0;
+        // this thread's distances of chunk kc: G4 runs of 16 bytes, tab_index(kc * 16 + (part * G4 + gi) * 4, r)
+        const float *tabp = tab + (part * G4 * TILE_G + r) * 4;
+        uint32_t sa = 0, pha = 0;                            // A ring stage and its phase bit
         for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
             B2_UNIT_DECODE
             // the epilogue warps are done with the previous tile's table before it is overwritten
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            row_table(tab, r, half, true, int64_t(tile) * TILE_G + r, G, grid, mic, M, Mk, cx0, cy0, cz0, steering);
+            asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");
+            float us;                                     // power-of-two amplitude scale of this grid point
+            row_table(tab, r, part, true, int64_t(tile) * TILE_G + r, G, grid, mic, M, Mk, cx0, cy0, cz0, steering, &us);
+            if (PASSES != 4) us = 1.0f;
             __threadfence_block();
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            // distances of this thread's 8 microphones of a chunk: 32 contiguous bytes, coalesced over rows
-            auto load_r = [&](int kc, float4 &lo, float4 &hi) {
-                const float4 *src = reinterpret_cast<const float4 *>(tab + tab_index(kc * KCH + half * 8, r));
-                lo = __ldcg(src);
-                hi = __ldcg(src + 1);
+            asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");
+            // Distances are prefetched TWO chunks ahead and the load is issued right after the arrive: the
+            // proxy fence in front of the arrive is a MEMBAR that waits for every outstanding load of the
+            // thread, so a load issued one chunk ahead would expose its whole L2 latency there.
+            // Two register buffers alternate (the chunk loop is flat and unrolled by two); rotating one
+            // buffer into the other would make the compiler wait for the newest load at the top of the body.
+            float4 r_a[G4], r_b[G4];
+            int pf_nbk = 0, pf_ci = 0;                       // cursor of the next chunk to prefetch
+            auto prefetch = [&](float4 *dst) {
+                const int kc0p = (pf_nbk * NB) / KCH;
+                const int kc = chunk_at(pf_ci, kc0p, NKC);
+#pragma unroll
+                for (int gi = 0; gi < G4; ++gi)
+                    dst[gi] = __ldcg(reinterpret_cast<const float4 *>(tabp + (kc * 4 + gi) * (TILE_G * 4)));
+                if (++pf_ci == NKC - kc0p) { pf_ci = 0; if (++pf_nbk == NBLK) pf_nbk = 0; }
             };
-            float4 r_lo, r_hi;
-            load_r(NKC - 1, r_lo, r_hi);
-            for (int fi = f_begin; fi < f_end; ++fi) {
-                const float bf = float(freqs[fi] * inv_c);
-                for (int nbk = 0; nbk < NBLK; ++nbk) {
-                    const int kc0 = (nbk * NB) / KCH;
-                    for (int kc = NKC - 1; kc >= kc0; --kc, ++it) {
-                        const int s = it % NSTAGE;
-                        const float rr[8] = {r_lo.x, r_lo.y, r_lo.z, r_lo.w, r_hi.x, r_hi.y, r_hi.z, r_hi.w};
-                        // prefetch the next chunk's distances (the walk only depends on kc)
-                        int kn = kc - 1;
-                        if (kn < kc0) kn = NKC - 1;
-                        load_r(kn, r_lo, r_hi);
-                        float4 hi4[4], lo4[4];
-                        uint4 mixlo[2], mixb[2];          // mixed mode: bf16 residuals / bf16 values of 8 mics
+            prefetch(r_a);
+            prefetch(r_b);
+            int chunks_per_bin = 0;
+            for (int nbk = 0; nbk < NBLK; ++nbk) chunks_per_bin += NKC - (nbk * NB) / KCH;
+            const int total = (f_end - f_begin) * chunks_per_bin;
+            int fi = f_begin, cib = 0;                       // bin of the current chunk, its index inside the bin
+            float bf = float(freqs[fi] * inv_c);
+            {
+                {
+                    auto chunk_body = [&](float4 (&r_cur)[G4]) {
+                        // probe the ring slot now so that the barrier round trip overlaps the arithmetic
+                        const bool slot_free = mbar_test(&emptyA[sa], pha ^ 1);
+                        float rr[MPT];
+#pragma unroll
+                        for (int gi = 0; gi < G4; ++gi) {
+                            rr[4 * gi] = r_cur[gi].x; rr[4 * gi + 1] = r_cur[gi].y;
+                            rr[4 * gi + 2] = r_cur[gi].z; rr[4 * gi + 3] = r_cur[gi].w;
+                        }
+                        float4 hi4[MPT / 2], lo4[MPT / 2];   // TF32 images: 2 microphones per 16 bytes
+                        uint4 img1[G4], img2[G4];            // 16-bit images: 4 microphones per 16 bytes
                         auto synth = [&](auto amp_tag) {
                             constexpr int AMP = decltype(amp_tag)::value;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 h0 = steer<AMP>(rr[2 * j], bf);
-                                const float2 h1 = steer<AMP>(rr[2 * j + 1], bf);
+                            for (int j = 0; j < MPT / 2; ++j) {
+                                const float2 h0 = steer<AMP>(rr[2 * j], bf, us);
+                                const float2 h1 = steer<AMP>(rr[2 * j + 1], bf, us);
+                                uint32_t *p1 = reinterpret_cast<uint32_t *>(&img1[j >> 1]) + 2 * (j & 1);
+                                uint32_t *p2 = reinterpret_cast<uint32_t *>(&img2[j >> 1]) + 2 * (j & 1);
+                                if (PASSES == 4) {           // img1 = first FP16 halves, img2 = second halves
+                                    const __half2 a1 = __floats2half2_rn(h0.x, h0.y), b1 = __floats2half2_rn(h1.x, h1.y);
+                                    const float2 af = __half22float2(a1), bfl = __half22float2(b1);
+                                    p1[0] = pack_f16(a1);
+                                    p1[1] = pack_f16(b1);
+                                    p2[0] = pack_f16(__floats2half2_rn(h0.x - af.x, h0.y - af.y));
+                                    p2[1] = pack_f16(__floats2half2_rn(h1.x - bfl.x, h1.y - bfl.y));
+                                    continue;
+                                }
                                 if (PASSES == 1) hi4[j] = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
                                 else hi4[j] = make_float4(trunc_tf32(h0.x), trunc_tf32(h0.y), trunc_tf32(h1.x), trunc_tf32(h1.y));
                                 if (PASSES == 3)   // residuals are exact in fp32; the tensor core keeps their top 11 bits
                                     lo4[j] = make_float4(h0.x - hi4[j].x, h0.y - hi4[j].y, h1.x - hi4[j].z, h1.y - hi4[j].w);
-                                if (PASSES == 2) {
-                                    const uint32_t l0 = pack_bf16(h0.x - hi4[j].x, h0.y - hi4[j].y);
-                                    const uint32_t l1 = pack_bf16(h1.x - hi4[j].z, h1.y - hi4[j].w);
-                                    const uint32_t b0 = pack_bf16(h0.x, h0.y), b1 = pack_bf16(h1.x, h1.y);
-                                    uint32_t *pl = reinterpret_cast<uint32_t *>(&mixlo[j >> 1]) + 2 * (j & 1);
-                                    uint32_t *pb = reinterpret_cast<uint32_t *>(&mixb[j >> 1]) + 2 * (j & 1);
-                                    pl[0] = l0; pl[1] = l1; pb[0] = b0; pb[1] = b1;
+                                if (PASSES == 2) {           // img1 = bf16 residuals, img2 = bf16 values
+                                    p1[0] = pack_bf16(h0.x - hi4[j].x, h0.y - hi4[j].y);
+                                    p1[1] = pack_bf16(h1.x - hi4[j].z, h1.y - hi4[j].w);
+                                    p2[0] = pack_bf16(h0.x, h0.y);
+                                    p2[1] = pack_bf16(h1.x, h1.y);
                                 }
                             }
                         };
                         if (akind == AMP_RINV) synth(std::integral_constant<int, AMP_RINV>{});
                         else if (akind == AMP_R) synth(std::integral_constant<int, AMP_R>{});
                         else synth(std::integral_constant<int, AMP_ONE>{});
-                        mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
-                        const uint32_t ahi = a_base + s * CF::STAGE;
+                        if (!slot_free) { PROF_T0(); mbar_wait(&emptyA[sa], pha ^ 1); PROF_ADD(0, blockIdx.x == 0 && tid == 0); }
+                        const uint32_t ahi = a_base + sa * CF::A_STAGE;
                         const uint32_t alo = ahi + (CF::NSPLIT - 1) * A_TILE;
+                        if (PASSES != 4) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int off = sw128_offset(r, half * 4 + j);
-                            sts128(ahi + off, hi4[j]);
-                            if (PASSES == 3) sts128(alo + off, lo4[j]);
-                        }
-                        if (PASSES == 2) {
-                            // correction image row = [bf16(h - hi) of the chunk's 16 mics | bf16(h) of the 16 mics]:
-                            // this thread's 8 mics are 32 bytes = 16-byte chunks 2*half, 2*half+1 of each 64-byte part
-#pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                sts128u(alo + sw128_offset(r, 2 * half + c), mixlo[c]);
-                                sts128u(alo + sw128_offset(r, 4 + 2 * half + c), mixb[c]);
+                            for (int j = 0; j < MPT / 2; ++j) {
+                                const int off = sw128_offset(r, part * (MPT / 2) + j);
+                                sts128(ahi + off, hi4[j]);
+                                if (PASSES == 3) sts128(alo + off, lo4[j]);
                             }
                         }
-                        fence_proxy_async();                 // generic-proxy writes -> visible to the MMA (async proxy)
-                        mbar_arrive(&full[s]);
-                    }
+                        if (PASSES == 2 || PASSES == 4) {
+                            // 16-bit image row = [img1 of the chunk's 16 mics | img2 of the 16 mics]: a group of 4 mics
+                            // is 16 bytes = 16-byte chunk (part * G4 + gi) of each 64-byte half.  In FP16x3 mode it is
+                            // the only image of the stage (alo == ahi).
+#pragma unroll
+                            for (int gi = 0; gi < G4; ++gi) {
+                                sts128u(alo + sw128_offset(r, part * G4 + gi), img1[gi]);
+                                sts128u(alo + sw128_offset(r, 4 + part * G4 + gi), img2[gi]);
+                            }
+                        }
+                        // generic-proxy writes -> visible to the MMA (async proxy); one arrival per warp
+                        // (32 same-address arrivals serialise in the shared-memory atomic unit)
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&fullA[sa]);
+                        if (++sa == NSA) { sa = 0; pha ^= 1; }
+                        prefetch(r_cur);                     // the chunk after next uses this buffer again
+                        if (++cib == chunks_per_bin) {
+                            cib = 0;
+                            if (++fi < f_end) bf = float(freqs[fi] * inv_c);
+                        }
+                    };
+                    int i = 0;
+#pragma unroll 1
+                    for (; i + 1 < total; i += 2) { chunk_body(r_a); chunk_body(r_b); }
+                    if (i < total) chunk_body(r_a);
                 }
             }
         }
-    } else if (warp < 16) {
+    } else if (warp < W_MMA) {
         // =========================== epilogue: TMEM -> P[g,f] -> map ===========================
-        const int ew = warp - 8;
+        const int ew = warp - W_EPI0;
         const int quad = ew & 3, half = ew >> 2;             // TMEM lane quadrant, which half of the columns
         const int r = quad * 32 + lane;
         const uint32_t lane_base = uint32_t(quad * 32) << 16;
@@ -409,32 +561,40 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
             B2_UNIT_DECODE
             const int64_t g = int64_t(tile) * TILE_G + r;
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            const double c2 = row_table(tab, r, 0, false, g, G, grid, mic, M, Mk, cx0, cy0, cz0, steering);
-            asm volatile("bar.sync 1, 512;" ::: "memory");   // table of this tile is complete
+            asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");
+            float us;
+            double c2 = row_table(tab, r, 0, false, g, G, grid, mic, M, Mk, cx0, cy0, cz0, steering, &us);
+            if (PASSES == 4) c2 /= double(us);            // T carries the amplitude scale once (the epilogue's h does not)
+            asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");   // table of this tile is complete
             double acc_map = 0.0;
             for (int fi = f_begin; fi < f_end; ++fi) {
                 const float bf = float(freqs[fi] * inv_c);
                 float p0 = 0.f, p1 = 0.f;
                 for (int nbk = 0; nbk < NBLK; ++nbk, ++acc_it) {
                     const int buf = acc_it & 1;
-                    mbar_wait(&tfull[buf], (acc_it >> 1) & 1);
+                    // this warp's groups of 8 columns (microphones) of the block: col0, col0 + 8, ...
+                    const int col0 = half * CG_PER_HALF * 32;
+                    const int cols_here = min(min(NB, Mk - nbk * NB) - col0, CG_PER_HALF * 32);
+                    const int ngrp = cols_here > 0 ? cols_here >> 3 : 0;
+                    // distances of the 8 microphones of a group for this row (two 16-byte runs of the table),
+                    // fetched one group ahead -- the first group before the accumulator is even complete
+                    const float *tabq = tab + tab_index(nbk * NB + col0, r);
+                    float4 ra = make_float4(1.f, 1.f, 1.f, 1.f), rb = ra;
+                    if (ngrp > 0) {
+                        ra = __ldcg(reinterpret_cast<const float4 *>(tabq));
+                        rb = __ldcg(reinterpret_cast<const float4 *>(tabq + TILE_G * 4));
+                    }
+                    { PROF_T0(); mbar_wait(&tfull[buf], (acc_it >> 1) & 1); PROF_ADD(5, blockIdx.x == 0 && ew == 0 && lane == 0); }
                     tc_fence_after();
-                    const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N;
+                    const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N + 2 * col0;
 #pragma unroll 1
-                    for (int c = 0; c < 2 * CG_PER_HALF; ++c) {          // 16 columns (microphones) at a time
-                        const int col = half * CG_PER_HALF * 32 + c * 16;
-                        const int n0 = nbk * NB + col;
-                        if (col >= NB || n0 >= Mk) break;
-                        float t[32];                                     // (Re T, Im T) of 16 columns n
-                        tmem_ld32(tcol + 2 * col, t);
-                        // distances of the 16 microphones n0 .. n0+15 of this row (two 32-byte runs)
-                        float4 rq[4];
-#pragma unroll
-                        for (int k8 = 0; k8 < 2; ++k8) {
-                            const float4 *src = reinterpret_cast<const float4 *>(tab + tab_index(n0 + 8 * k8, r));
-                            rq[2 * k8] = __ldcg(src);
-                            rq[2 * k8 + 1] = __ldcg(src + 1);
+                    for (int c = 0; c < ngrp; ++c) {
+                        float t[16];                                     // (Re T, Im T) of 8 columns n
+                        tmem_ld16(tcol + 16 * c, t);
+                        const float rq[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                        if (c + 1 < ngrp) {
+                            ra = __ldcg(reinterpret_cast<const float4 *>(tabq + (2 * c + 2) * (TILE_G * 4)));
+                            rb = __ldcg(reinterpret_cast<const float4 *>(tabq + (2 * c + 3) * (TILE_G * 4)));
                         }
                         tmem_ld_wait();
                         auto reduce = [&](auto amp_tag) {
@@ -442,16 +602,11 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 // padded microphones have all-zero operand rows, so T is 0 there: no bounds test
-                                const float2 h0 = steer<AMP>(rq[j].x, bf), h1 = steer<AMP>(rq[j].y, bf);
-                                const float2 h2 = steer<AMP>(rq[j].z, bf), h3 = steer<AMP>(rq[j].w, bf);
-                                p0 = fmaf(t[8 * j], h0.x, p0);
-                                p0 = fmaf(-t[8 * j + 1], h0.y, p0);
-                                p1 = fmaf(t[8 * j + 2], h1.x, p1);
-                                p1 = fmaf(-t[8 * j + 3], h1.y, p1);
-                                p0 = fmaf(t[8 * j + 4], h2.x, p0);
-                                p0 = fmaf(-t[8 * j + 5], h2.y, p0);
-                                p1 = fmaf(t[8 * j + 6], h3.x, p1);
-                                p1 = fmaf(-t[8 * j + 7], h3.y, p1);
+                                const float2 h0 = steer<AMP>(rq[2 * j], bf), h1 = steer<AMP>(rq[2 * j + 1], bf);
+                                p0 = fmaf(t[4 * j], h0.x, p0);
+                                p0 = fmaf(-t[4 * j + 1], h0.y, p0);
+                                p1 = fmaf(t[4 * j + 2], h1.x, p1);
+                                p1 = fmaf(-t[4 * j + 3], h1.y, p1);
                             }
                         };
                         if (akind == AMP_RINV) reduce(std::integral_constant<int, AMP_RINV>{});
@@ -459,7 +614,8 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                         else reduce(std::integral_constant<int, AMP_ONE>{});
                     }
                     tc_fence_before();
-                    mbar_arrive(&tempty[buf]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[buf]);
                 }
                 // combine the two column halves of this row
                 float *pp = part + (fi & 1) * TILE_G;
@@ -467,6 +623,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 asm volatile("bar.sync 2, 256;" ::: "memory");
                 if (half == 0) {
                     double p = (double(p0 + p1) + double(pp[r])) * c2;        // |h|^2 scale of this grid point
+                    if (PASSES == 4) p /= double(bin_scale[fi]);                    // power-of-two scale of L_f
                     if (clamp_negative && p < 0.0) p = 0.0;                         // beamforming.py:871-872
                     acc_map += weights[fi] * p;                                       // :875-876
                     if (per_bin != nullptr && g < G) per_bin[g * nbins + fi] = p;
@@ -476,44 +633,71 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             // launcher and every unit adds its weighted partial sum
             if (half == 0 && g < G) atomicAdd(map_out + g, acc_map);
         }
-    } else if (warp == 16) {
-        // =========================== MMA issue (one thread) ===========================
-        if (lane == 0) {
-            uint32_t it = 0, acc_it = 0;
-            for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
+    } else if (warp == W_MMA) {
+        // =========================== MMA issue ===========================
+        // The whole warp walks the loop, so every address, descriptor and flag is warp-uniform and lives in
+        // uniform registers; one elected lane issues the tcgen05 instructions.  (Running the loop inside an
+        // `if (lane == 0)` made every tcgen05.mma cost ~13 instructions of register shuffling, and the issue
+        // thread -- not the tensor pipe -- set the pace of the kernel: time grew linearly with the number of
+        // MMA instructions, 110 cycles each.)
+        const uint32_t a0 = desc_lo(smem_u32(smem)), b0 = desc_lo(smem_u32(smem) + NSA * CF::A_STAGE);
+        uint32_t sa = 0, pha = 0, sb = 0, phb = 0, acc_it = 0;
+        for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
             B2_UNIT_DECODE
-                for (int fi = f_begin; fi < f_end; ++fi) {
-                    for (int nbk = 0; nbk < NBLK; ++nbk, ++acc_it) {
-                        const int buf = acc_it & 1;
-                        mbar_wait(&tempty[buf], ((acc_it >> 1) & 1) ^ 1);
+            (void)tile;
+            for (int fi = f_begin; fi < f_end; ++fi) {
+                for (int nbk = 0; nbk < NBLK; ++nbk, ++acc_it) {
+                    const uint32_t buf = acc_it & 1;
+                    { PROF_T0(); mbar_wait(&tempty[buf], ((acc_it >> 1) & 1) ^ 1); PROF_ADD(3, blockIdx.x == 0 && lane == 0); }
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * UMMA_N;
+                    const int kc0 = (nbk * NB) / KCH;
+                    const int nch = NKC - kc0;
+                    for (int ci = 0; ci < nch; ++ci) {
+                        const int kc = chunk_at(ci, kc0, NKC);
+                        // columns of this block that chunk kc can reach (lower triangle): w, N = 2w
+                        const int w = min(NB, KCH * (kc - kc0 + 1));
+                        { PROF_T0(); mbar_wait(&fullB[sb], phb); PROF_ADD(7, blockIdx.x == 0 && lane == 0); }
+                        { PROF_T0(); mbar_wait(&fullA[sa], pha); PROF_ADD(2, blockIdx.x == 0 && lane == 0); }
                         tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + buf * UMMA_N;
-                        const int kc0 = (nbk * NB) / KCH;
-                        for (int kc = NKC - 1; kc >= kc0; --kc, ++it) {
-                            const int s = it % NSTAGE;
-                            // columns of this block that chunk kc can reach (lower triangle): w, N = 2w
-                            const int w = min(NB, KCH * (kc - kc0 + 1));
-                            const uint32_t idesc = idesc_tf32(TILE_G, 2 * w);
-                            mbar_wait(&full[s], (it / NSTAGE) & 1);
-                            tc_fence_after();
-                            const uint64_t a_hi = smem_desc_sw128(smem_u32(a_tile(s, 0)));
-                            const uint64_t b_hi = smem_desc_sw128(smem_u32(b_tile(s, 0)));
-                            const uint64_t a_lo = smem_desc_sw128(smem_u32(a_tile(s, CF::NSPLIT - 1)));
-                            const uint64_t b_lo = smem_desc_sw128(smem_u32(b_tile(s, CF::NSPLIT - 1)));
+                        // low words of the operand descriptors: first image, second (correction) image
+                        const uint32_t a1 = a0 + sa * (CF::A_STAGE >> 4), b1 = b0 + sb * (CF::B_STAGE >> 4);
+                        const uint32_t a2 = a1 + (CF::NSPLIT - 1) * (A_TILE >> 4), b2 = b1 + (CF::NSPLIT - 1) * (CF::B_TILE >> 4);
+                        const uint32_t first = ci > 0 ? 1u : 0u;           // 0: the first MMA overwrites the accumulator
+                        if (elect_one_sync()) {
+                            if (PASSES == 4) {
+                                // row = [f1 | f2] (A) resp. [g1 | g2] (B), 64 B each = 2 K-steps of 16 halfs:
+                                // f1*g1 + f1*g2 + f2*g1
+                                const uint32_t idh = idesc_f16(TILE_G, 2 * w);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {              // UMMA K = 8 tf32 = 32 bytes
-                                const uint64_t adv = uint64_t(ks * 2);    // (32 B) >> 4
-                                umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (kc < NKC - 1 || ks > 0) ? 1u : 0u);
-                                if (PASSES == 3) {
-                                    umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-                                    umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                                for (uint32_t ks = 0; ks < 2; ++ks) {
+                                    const uint32_t adv = ks * 2;               // (32 B) >> 4
+                                    umma_bf16(d_tmem, desc64(a1 + adv), desc64(b1 + adv), idh, ks > 0 ? 1u : first);
+                                    umma_bf16(d_tmem, desc64(a1 + adv), desc64(b1 + 4 + adv), idh, 1u);
+                                    umma_bf16(d_tmem, desc64(a1 + 4 + adv), desc64(b1 + adv), idh, 1u);
                                 }
-                                // mixed mode: both corrections as one BF16 product of depth 64 (4 x K=16)
-                                if (PASSES == 2) umma_bf16(d_tmem, a_lo + adv, b_lo + adv, idesc_bf16(TILE_G, 2 * w), 1u);
+                            } else {
+                                const uint32_t idesc = idesc_tf32(TILE_G, 2 * w);
+#pragma unroll
+                                for (uint32_t ks = 0; ks < 4; ++ks) {          // UMMA K = 8 tf32 = 32 bytes
+                                    const uint32_t adv = ks * 2;
+                                    umma_tf32(d_tmem, desc64(a1 + adv), desc64(b1 + adv), idesc, ks > 0 ? 1u : first);
+                                    if (PASSES == 3) {
+                                        umma_tf32(d_tmem, desc64(a2 + adv), desc64(b1 + adv), idesc, 1u);
+                                        umma_tf32(d_tmem, desc64(a1 + adv), desc64(b2 + adv), idesc, 1u);
+                                    }
+                                    // mixed mode: both corrections as one BF16 product of depth 64 (4 x K=16)
+                                    if (PASSES == 2)
+                                        umma_bf16(d_tmem, desc64(a2 + adv), desc64(b2 + adv), idesc_bf16(TILE_G, 2 * w), 1u);
+                                }
                             }
-                            umma_commit(&empty[s]);                       // frees the stage when the MMAs retire
+                            umma_commit(&emptyA[sa]);                     // free both stages when the MMAs retire
+                            umma_commit(&emptyB[sb]);
+                            if (ci == nch - 1) umma_commit(&tfull[buf]);  // accumulator complete -> epilogue
                         }
-                        umma_commit(&tfull[buf]);                         // accumulator complete -> epilogue
+                        __syncwarp();
+                        if (++sa == NSA) { sa = 0; pha ^= 1; }
+                        if (++sb == NSB) { sb = 0; phb ^= 1; }
                     }
                 }
             }
@@ -528,19 +712,20 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 for (int fi = f_begin; fi < f_end; ++fi) {
                     for (int nbk = 0; nbk < NBLK; ++nbk) {
                         const int kc0 = (nbk * NB) / KCH;
-                        for (int kc = NKC - 1; kc >= kc0; --kc, ++it) {
-                            const int s = it % NSTAGE;
+                        for (int ci = 0; ci < NKC - kc0; ++ci, ++it) {
+                            const int kc = chunk_at(ci, kc0, NKC);
+                            const int s = it % NSB;
                             const int w = min(NB, KCH * (kc - kc0 + 1));
 #ifdef B2_EXPERIMENT_BDIV
                             const uint32_t bytes = uint32_t(2 * w) * 128 / B2_EXPERIMENT_BDIV;   // timing experiment only (wrong results)
 #else
                             const uint32_t bytes = uint32_t(2 * w) * 128;          // first 2w rows of each image
 #endif
-                            mbar_wait(&empty[s], ((it / NSTAGE) & 1) ^ 1);
+                            mbar_wait(&emptyB[s], ((it / NSB) & 1) ^ 1);
                             const unsigned char *src = op + size_t(fi) * bin_bytes + (size_t(nbk) * NKC + kc) * (CF::NSPLIT * CF::B_TILE);
-                            mbar_arrive_expect_tx(&full[s], CF::NSPLIT * bytes);
-                            bulk_g2s(b_tile(s, 0), src, bytes, &full[s]);
-                            if (PASSES != 1) bulk_g2s(b_tile(s, 1), src + CF::B_TILE, bytes, &full[s]);
+                            mbar_arrive_expect_tx(&fullB[s], CF::NSPLIT * bytes);
+                            bulk_g2s(b_tile(s, 0), src, bytes, &fullB[s]);
+                            if (CF::NSPLIT == 2) bulk_g2s(b_tile(s, 1), src + CF::B_TILE, bytes, &fullB[s]);
                         }
                     }
                 }
@@ -548,17 +733,53 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         }
     }
 
+#ifdef B2_MAP_PROFILE
+    if (blockIdx.x == 0) {
+        const unsigned long long dt = (unsigned long long)(clock64() - t_kernel0);
+        if (tid == 0) atomicAdd(&g_map_prof[1], dt);
+        if (warp == W_MMA && lane == 0) atomicAdd(&g_map_prof[4], dt);
+        if (warp == W_EPI0 && lane == 0) atomicAdd(&g_map_prof[6], dt);
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 16) tmem_dealloc(tmem_base, CF::TMEM_COLS);
+    if (warp == W_MMA) tmem_dealloc(tmem_base, CF::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------- K3a for the tensor-core path
+// FP16x3 mode: exact power-of-two scale per bin that maps max |L_f| into [2^11, 2^12) (one CTA per bin).
+__global__ void das_bin_scale_kernel(const double2 *__restrict__ csm, int M, int bin0, double gain, int remove_diag,
+                                     float *__restrict__ scale) {
+    const double2 *c = csm + int64_t(bin0 + blockIdx.x) * M * M;
+    double mx = 0.0;
+    for (int i = threadIdx.x; i < M * M; i += blockDim.x) {
+        const int m = i / M, n = i - m * M;
+        if (n > m) continue;
+        const double f = n == m ? (remove_diag ? 0.0 : gain) : 2.0 * gain;
+        const double v = f * fmax(fabs(c[i].x), fabs(c[i].y));
+        if (v < 1e300) mx = fmax(mx, v);                     // ignores inf / nan
+    }
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < int(blockDim.x >> 5); ++w) mx = fmax(mx, red[w]);
+        int k = 0;
+        if (mx > 0.0) {
+            k = 11 - ilogb(mx);                              // mx * 2^k in [2^11, 2^12)
+            k = k < -100 ? -100 : (k > 100 ? 100 : k);
+        }
+        scale[blockIdx.x] = float(scalbn(1.0, k));
+    }
+}
+
 // One thread per 16-byte chunk of an operand image: (bin, column block, K chunk, row, chunk j).
 template <int NB, int PASSES>
 __global__ void das_prepare_tc_kernel(const double2 *__restrict__ csm, int M, int bin0, double gain, int remove_diag,
-                                      unsigned char *__restrict__ op, int NKC, int NBLK) {
+                                      unsigned char *__restrict__ op, int NKC, int NBLK,
+                                      const float *__restrict__ bin_scale) {
     using CF = TcCfg<NB, PASSES>;
     const int row = blockIdx.x * blockDim.x + threadIdx.x;       // 0 .. 2NB-1
     if (row >= CF::UMMA_N) return;
@@ -567,6 +788,7 @@ __global__ void das_prepare_tc_kernel(const double2 *__restrict__ csm, int M, in
     const bool imag_row = row & 1;                                // rows alternate Re T / Im T of column n
     const int n = nbk * NB + (row >> 1);
     unsigned char *tile = op + ((size_t(fi) * NBLK + nbk) * NKC + kc) * size_t(CF::NSPLIT * CF::B_TILE);
+    if (PASSES == 4) gain *= double(bin_scale[fi]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float v[4];
@@ -582,6 +804,18 @@ __global__ void das_prepare_tc_kernel(const double2 *__restrict__ csm, int M, in
             // real rows: (Re L, Im L) ; imaginary rows: (Im L, -Re L)
             v[2 * e] = float(imag_row ? li : lr);
             v[2 * e + 1] = float(imag_row ? -lr : li);
+        }
+        if (PASSES == 4) {
+            // row = [g1 of the chunk's 16 mics | g2 of the 16 mics] (FP16): the 2 mics of this j are 8 bytes
+            // at byte offset 8*j of each 64-byte part
+            const __half2 a1 = __floats2half2_rn(v[0], v[1]), b1 = __floats2half2_rn(v[2], v[3]);
+            const float2 af = __half22float2(a1), bfl = __half22float2(b1);
+            const uint2 g1 = make_uint2(pack_f16(a1), pack_f16(b1));
+            const uint2 g2 = make_uint2(pack_f16(__floats2half2_rn(v[0] - af.x, v[1] - af.y)),
+                                        pack_f16(__floats2half2_rn(v[2] - bfl.x, v[3] - bfl.y)));
+            *reinterpret_cast<uint2 *>(tile + sw128_offset(row, j >> 1) + 8 * (j & 1)) = g1;
+            *reinterpret_cast<uint2 *>(tile + sw128_offset(row, 4 + (j >> 1)) + 8 * (j & 1)) = g2;
+            continue;
         }
         const int off = sw128_offset(row, j);
         const float4 hi = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
@@ -606,7 +840,15 @@ template <int PASSES> int64_t images_bytes(int M, int nbins) {
     const int NKC = (M + KCH - 1) / KCH;
     const int nb = tc_nb(M), NBLK = (M + nb - 1) / nb;
     const int64_t btile = 2 * nb * 128;
-    return int64_t(nbins) * NBLK * NKC * (PASSES == 1 ? 1 : 2) * btile;
+    return int64_t(nbins) * NBLK * NKC * ((PASSES == 1 || PASSES == 4) ? 1 : 2) * btile;
+}
+// operand buffer = [images][one distance table of 128 x Mk floats per persistent CTA][per-bin scales]
+inline int64_t tables_bytes(int M) { return int64_t(MAX_CTAS) * TILE_G * ((M + KCH - 1) / KCH) * KCH * 4; }
+template <int PASSES> float *tables_ptr(const void *op, int M, int nbins) {
+    return reinterpret_cast<float *>((unsigned char *)op + images_bytes<PASSES>(M, nbins));
+}
+template <int PASSES> float *scales_ptr(const void *op, int M, int nbins) {
+    return reinterpret_cast<float *>((unsigned char *)op + images_bytes<PASSES>(M, nbins) + tables_bytes(M));
 }
 
 template <int NB, int PASSES>
@@ -615,8 +857,13 @@ int launch_prepare(const void *csm, int M, int bin0, int nbins, int remove_diag,
     const int NKC = (M + KCH - 1) / KCH, NBLK = (M + NB - 1) / NB;
     const double gain = remove_diag ? double(M) / double(M - 1) : 1.0;
     dim3 grid((CF::UMMA_N + 127) / 128, NKC * NBLK, nbins);
+    float *scales = scales_ptr<PASSES>(op, M, nbins);
+    if (PASSES == 4) {
+        das_bin_scale_kernel<<<nbins, 256, 0, st>>>((const double2 *)csm, M, bin0, gain, remove_diag, scales);
+        B2_LAUNCH_OK("b2_das_prepare(scale)");
+    }
     das_prepare_tc_kernel<NB, PASSES><<<grid, 128, 0, st>>>((const double2 *)csm, M, bin0, gain, remove_diag,
-                                                            (unsigned char *)op, NKC, NBLK);
+                                                            (unsigned char *)op, NKC, NBLK, scales);
     B2_LAUNCH_OK("b2_das_prepare(tc)");
     return B2_OK;
 }
@@ -653,8 +900,9 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
     const int64_t units = ntiles * nsplit;
     const int nblocks = int(units < cap ? units : cap);
     B2_CUDA_OK(cudaMemsetAsync(map_out, 0, size_t(G) * sizeof(double), st));
-    float *scratch = reinterpret_cast<float *>((unsigned char *)op + images_bytes<PASSES>(M, nbins));
-    kern<<<nblocks, TC_THREADS, CF::SMEM, st>>>((const unsigned char *)op, scratch, M, nbins, (const double *)freqs,
+    float *scratch = tables_ptr<PASSES>(op, M, nbins);
+    kern<<<nblocks, TC_THREADS, CF::SMEM, st>>>((const unsigned char *)op, scratch, scales_ptr<PASSES>(op, M, nbins), M, nbins,
+                                                (const double *)freqs,
                                                 (const double *)weights, 1.0 / c, (const double *)mic, center[0],
                                                 center[1], center[2], (const double *)grid, G, steering,
                                                 clamp_negative, (double *)map_out, (double *)per_bin, int(ntiles), nsplit);
@@ -663,16 +911,25 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
 }
 
 template <int PASSES> int64_t operand_bytes(int M, int nbins) {
-    const int NKC = (M + KCH - 1) / KCH;
-    // operand images + one distance table of 128 x Mk floats per persistent CTA
-    return images_bytes<PASSES>(M, nbins) + int64_t(MAX_CTAS) * TILE_G * NKC * KCH * 4;
+    return images_bytes<PASSES>(M, nbins) + tables_bytes(M) + ((int64_t(nbins) * 4 + 255) & ~int64_t(255));
 }
 
 }  // namespace
 
+#ifdef B2_MAP_PROFILE
+extern "C" int b2_debug_map_profile(unsigned long long *out) {
+    cudaMemcpyFromSymbol(out, g_map_prof, sizeof(unsigned long long) * 8);
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_map_prof, z, sizeof(z));
+    return 0;
+}
+#endif
+
 int64_t b2_das_tc_operand_bytes(int M, int nbins, int mode) {
     if (M > MAX_MICS) { b2_set_error("tensor-core map kernel supports at most %d microphones", MAX_MICS); return B2_EUNSUPPORTED; }
-    return mode == B2_MAP_TC_TF32 ? operand_bytes<1>(M, nbins) : operand_bytes<3>(M, nbins);
+    if (mode == B2_MAP_TC_TF32) return operand_bytes<1>(M, nbins);
+    if (mode == B2_MAP_TC_F16X3) return operand_bytes<4>(M, nbins);
+    return operand_bytes<3>(M, nbins);
 }
 
 #define B2_TC_DISPATCH(FN, ...)                                                      \
@@ -682,6 +939,10 @@ int64_t b2_das_tc_operand_bytes(int M, int nbins, int mode) {
             if (nb_ == 32) return FN<32, 3>(__VA_ARGS__);                            \
             if (nb_ == 64) return FN<64, 3>(__VA_ARGS__);                            \
             return FN<128, 3>(__VA_ARGS__);                                          \
+        } else if (mode == B2_MAP_TC_F16X3) {                                        \
+            if (nb_ == 32) return FN<32, 4>(__VA_ARGS__);                            \
+            if (nb_ == 64) return FN<64, 4>(__VA_ARGS__);                            \
+            return FN<128, 4>(__VA_ARGS__);                                          \
         } else if (mode == B2_MAP_TC_MIXED) {                                        \
             if (nb_ == 32) return FN<32, 2>(__VA_ARGS__);                            \
             if (nb_ == 64) return FN<64, 2>(__VA_ARGS__);                            \

@@ -48,7 +48,7 @@ def _count(n: int = 1):
 
 _PREC = {"fp64": N.F64, "fp32": N.F32}
 _MAP_MODES = {"simt_f64": N.MAP_SIMT_F64, "simt_f32": N.MAP_SIMT_F32, "tf32": N.MAP_TC_TF32,
-              "tf32x3": N.MAP_TC_TF32X3, "mixed": N.MAP_TC_MIXED}
+              "tf32x3": N.MAP_TC_TF32X3, "mixed": N.MAP_TC_MIXED, "f16x3": N.MAP_TC_F16X3}
 
 
 def _torch():
@@ -67,7 +67,7 @@ def tc_map_available() -> bool:
 def resolve_map_mode(mode: str | None = None) -> int:
     mode = (mode or config.map_mode).lower()
     if mode == "auto":
-        return N.MAP_TC_MIXED if tc_map_available() else N.MAP_SIMT_F32
+        return N.MAP_TC_F16X3 if tc_map_available() else N.MAP_SIMT_F32
     if mode not in _MAP_MODES:
         raise ValueError(f"unknown map mode {mode!r}")
     return _MAP_MODES[mode]

@@ -48,6 +48,8 @@ extern "C" {
 #define B2_MAP_TC_TF32 2   /* tcgen05 tensor cores, single-pass TF32, fp32 accumulate       */
 #define B2_MAP_TC_TF32X3 3 /* tcgen05 tensor cores, split-TF32 (3 products), fp32 accumulate */
 #define B2_MAP_TC_MIXED 4  /* tcgen05: TF32 main product + one BF16 product for both corrections */
+#define B2_MAP_TC_F16X3 5  /* tcgen05: operands split into two FP16 halves (22 bits), 3 FP16 products,
+                              per-bin / per-grid-point power-of-two scaling, fp32 accumulate     */
 
 int b2_version(void);
 const char *b2_last_error(void);

@@ -4,7 +4,7 @@ sys.path.insert(0, ".")
 from dsptoolbox_b200 import engine, _native as N
 
 M, G, F = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-mode = {"mixed": N.MAP_TC_MIXED, "tf32x3": N.MAP_TC_TF32X3, "tf32": N.MAP_TC_TF32, "simt_f32": N.MAP_SIMT_F32, "simt_f64": N.MAP_SIMT_F64}[sys.argv[4]]
+mode = {"mixed": N.MAP_TC_MIXED, "f16x3": N.MAP_TC_F16X3, "tf32x3": N.MAP_TC_TF32X3, "tf32": N.MAP_TC_TF32, "simt_f32": N.MAP_SIMT_F32, "simt_f64": N.MAP_SIMT_F64}[sys.argv[4]]
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 a = torch.randn((F, M, 4), device="cuda", dtype=torch.complex128, generator=g)

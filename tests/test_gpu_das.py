@@ -17,7 +17,7 @@ from oracle import restatement as R  # noqa: E402
 from parity import assert_map_close  # noqa: E402
 
 BF = dsp.beamforming
-MODES = ["simt_f64", "simt_f32"] + (["mixed", "tf32x3", "tf32"] if engine.tc_map_available() else [])
+MODES = ["simt_f64", "simt_f32"] + (["f16x3", "mixed", "tf32x3", "tf32"] if engine.tc_map_available() else [])
 # Single-pass TF32 rounds both operands to 11 significant bits: its error is ~5e-4 / sqrt(#terms)
 # of the coherent maximum, i.e. OUTSIDE the 1e-4 contract for small arrays.  It is an opt-in
 # speed mode (never the default); the tests only bound it.  Every other mode meets the contract.
@@ -251,7 +251,7 @@ def test_golden_cleansc(golden_dir):
         quiet_map(BF.BeamformerCleanSC(sig, ma, grid, st), 2000.0, 3, 5, 1.5)
 
 
-@pytest.mark.parametrize("mode", [m for m in MODES if m in ("mixed", "tf32x3")])
+@pytest.mark.parametrize("mode", [m for m in MODES if m in ("f16x3", "mixed", "tf32x3")])
 @pytest.mark.parametrize("M", [300, 520])
 def test_many_microphones_against_oracle(mode, M):
     """More than two 128-column blocks (3 and 5) and a microphone count off the 16-mic chunk: beyond the

@@ -84,7 +84,7 @@ def test_csm_full_size_properties(recording, csm):
     assert torch.allclose(spec_energy, time_energy, rtol=1e-10)
 
 
-@pytest.mark.parametrize("mode", ["mixed", "tf32x3"])
+@pytest.mark.parametrize("mode", ["f16x3", "mixed", "tf32x3"])
 def test_map_full_band_subsample_against_oracle(recording, csm, mode):
     """2048 bins x 256 mics (configs[4]) on 16 384 grid points of the 100^3 grid; 24 seeded points
     are recomputed by the oracle from the same CSM."""
