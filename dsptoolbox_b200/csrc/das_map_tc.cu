@@ -17,9 +17,9 @@
 // in TMEM as fp32.  L is lower triangular: K chunks (16 microphones) entirely above the diagonal
 // are skipped, and a chunk that straddles it only touches its first w = 16, 32, ... columns, so
 // the MMA is issued with N = 2w and only the first 2w operand rows are fetched.  Chunks are
-// walked widest, narrowest, second widest, ... so that the first MMA of an accumulator (the one
-// that overwrites instead of accumulating) is the widest and tensor-heavy and synthesis-heavy
-// chunks alternate.
+// walked from the last one down, so that the first MMA of an accumulator (the one that overwrites
+// instead of accumulating) is the widest; two neighbouring column blocks share their A tiles
+// (walk_pair below).
 // The epilogue warps read D back with tcgen05.ld, re-synthesise H[g, n] and reduce
 //     P[g, f] = sum_n Re(T[g, n] H[g, n]),   clamp,   map[g] += w_f P[g, f]
 // while the next column block accumulates into the second TMEM buffer.
@@ -68,8 +68,8 @@ constexpr int G4 = MPT / 4;                   // ... as groups of 4 (16 bytes of
 constexpr int NGEN = TILE_G * TPR;            // synthesis threads
 constexpr int NEPI = 256;                     // epilogue threads
 constexpr int W_EPI0 = NGEN / 32;             // first epilogue warp
-constexpr int W_MMA = W_EPI0 + NEPI / 32;     // MMA issue warp; the loader warp follows
-constexpr int TC_THREADS = NGEN + NEPI + 64;
+constexpr int W_MMA = W_EPI0 + NEPI / 32;     // two MMA issue warps (one per accumulator stream); the loader warp follows
+constexpr int TC_THREADS = NGEN + NEPI + 96;
 
 constexpr int MAX_CTAS = 160;                 // scratch tables are sized for this many persistent CTAs
 constexpr int MAX_MICS = 1024;
@@ -95,7 +95,15 @@ template <int NB, int PASSES> struct TcCfg {
 #ifdef B2_NSA
     static constexpr int NSA = B2_NSA;
 #else
-    static constexpr int NSA = NSA_RAW > 6 ? 6 : NSA_RAW;
+    static constexpr int NSA = NSA_RAW > 10 ? 10 : NSA_RAW;
+#endif
+    // With a deep A ring, two neighbouring column blocks share the synthesised A tiles (see walk_pair);
+    // GS = how many chunks the second block's stream lags behind (their tiles are held in the ring).
+    static constexpr bool SHARE = NSA >= 6;
+#ifdef B2_LAG
+    static constexpr int GS = B2_LAG;
+#else
+    static constexpr int GS = NSA - 2;
 #endif
     static constexpr int TMEM_COLS = 2 * UMMA_N;                       // two accumulator buffers
     static constexpr int SMEM = 1024 /*align slack*/ + NSA * A_STAGE + NSB * B_STAGE + 2 * TILE_G * 4 + 256;
@@ -111,6 +119,33 @@ __device__ unsigned long long g_map_prof[8];
 #else
 #define PROF_T0()
 #define PROF_ADD(slot, cond)
+#endif
+
+#ifdef B2_MAP_TRACE
+// Debug: event trace of CTA 0 for the bins [B2_TRACE_BIN0, B2_TRACE_BIN0 + 2): {role, event, index, clock}
+#ifndef B2_TRACE_BIN0
+#define B2_TRACE_BIN0 20
+#endif
+__device__ long long g_trace[4 * 2 * 1024];     // [role][record]{(ev << 16) | idx, clock}
+#define TRACE(role, ev, idx, bin)                                                              \
+    do {                                                                                       \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (bin) >= B2_TRACE_BIN0 && (bin) < B2_TRACE_BIN0 + 2 && trace_n < 1024) { \
+            g_trace[((role) * 1024 + trace_n) * 2] = ((long long)(ev) << 16) | (long long)(idx);                \
+            g_trace[((role) * 1024 + trace_n) * 2 + 1] = clock64();                            \
+            ++trace_n;                                                                         \
+        }                                                                                      \
+    } while (0)
+#else
+#define TRACE(role, ev, idx, bin)
+#endif
+
+#ifdef B2_DEBUG_HANG
+__device__ unsigned int g_abort, g_nhang, g_hang[256], g_snapped, g_snap[16];
+__device__ unsigned int g_prog[16];      // progress counters of CTA 0: [0] synth chunks [1] epilogue accumulators
+                                         // [2] issue warp 0 steps [3] issue warp 1 steps [4] loader tiles, [8+] = 100*role + stage
+#define DBG_PROG(slot, v) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_prog[slot] = (v); } while (0)
+#else
+#define DBG_PROG(slot, v)
 #endif
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -132,6 +167,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done;
+#ifdef B2_DEBUG_HANG
+    uint32_t spins = 0;
+    unsigned long long t_begin;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+#endif
     do {
         asm volatile(
             "{\n\t"
@@ -142,6 +182,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity), "r"(0x989680u)
             : "memory");
+#ifdef B2_DEBUG_HANG
+        // debug build: a barrier that stays closed for ~1 s is recorded and every waiter gives up, so the
+        // kernel ends (with garbage results) and the host can print who was stuck where
+        if (!done && ((++spins & 63) == 0)) {
+            unsigned long long t_now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+            const bool aborting = *(volatile unsigned int *)&g_abort != 0;
+            if (aborting && t_now - t_begin < 100000000ull) break;
+            if (aborting || t_now - t_begin > 500000000ull) {   // this one wait has lasted 0.5 s (0.1 s when aborting)
+                if ((threadIdx.x & 31) == 0) {
+                    const unsigned int k = atomicAdd(&g_nhang, 1u);
+                    if (k < 64) { g_hang[4 * k] = blockIdx.x; g_hang[4 * k + 1] = threadIdx.x >> 5; g_hang[4 * k + 2] = addr; g_hang[4 * k + 3] = parity; }
+                }
+                if (!aborting && (threadIdx.x & 31) == 0 && atomicCAS(&g_snapped, 0u, 1u) == 0u)
+                    for (int q = 0; q < 16; ++q) g_snap[q] = *(volatile unsigned int *)&g_prog[q];
+                __threadfence();
+                *(volatile unsigned int *)&g_abort = 1;
+                break;
+            }
+        }
+#endif
     } while (!done);
 }
 // non-blocking probe of a phase
@@ -265,6 +326,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::f16 MMA whose A operand is kept in / taken from the collector buffer: the next MMA with the same
+// A slice (and another B) does not read A from shared memory again
+__device__ __forceinline__ void umma_f16_afill(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_alastuse(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {   // lo_elem first in memory
     __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);
     return *reinterpret_cast<uint32_t *>(&v);
@@ -362,18 +445,25 @@ __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
 }
 
 // ---------------------------------------------------------------- the kernel
-// Order in which the K chunks [kc0, NKC) of one accumulator are walked: widest, narrowest, second
-// widest, second narrowest, ...  (chunk width = number of columns it can reach, growing with kc).
-// The first chunk (the one whose MMA overwrites the accumulator) is the widest, and wide (tensor-
-// heavy) and narrow (synthesis-heavy) chunks alternate, so the A ring only has to absorb the
-// imbalance of one pair of chunks.
-__device__ __forceinline__ int chunk_at(int i, int kc0, int NKC) {
-#ifdef B2_CHUNK_DESCENDING
-    (void)kc0;
-    return NKC - 1 - i;                                     // A/B-test build: plain descending walk
-#else
-    return (i & 1) ? kc0 + (i >> 1) : NKC - 1 - (i >> 1);
-#endif
+// Order of the tensor-core work of one bin for a PAIR of neighbouring column blocks (b0, b1 = b0 + 1).
+// Chunks are walked downwards from the last one (kc = NKC-1: the widest, its MMA overwrites the
+// accumulator).  Chunks kc >= kcB feed both blocks, chunks kcA <= kc < kcB feed b0 only.  The two
+// accumulators are fed as two skewed streams: step i multiplies chunk NKC-1-i into b1 (first use of its A
+// tile) and chunk NKC-1-(i-LAG) into b0 (last use, frees the tile).  So every steering tile is
+// synthesised ONCE per bin although both blocks need it, the tensor pipe sees a steady mix of both
+// streams, and the accumulator of b0 is not touched during the first LAG steps -- which is what gives the
+// epilogue time to drain it from the previous bin.  A lone block is the case kcB = NKC.
+//   fn(kc, target /*1: b1, 0: b0*/, first_use_of_A_tile, last_use_of_A_tile)
+template <class F>
+__device__ __forceinline__ void walk_pair(int NKC, int kcA, int kcB, int LAG, F &&fn) {
+    const int n1 = NKC - kcB;                 // steps of the b1 stream (0 for a lone block)
+    const int n0 = NKC - kcA;                 // steps of the b0 stream
+    const int lag = n1 < LAG ? n1 : LAG;
+    for (int i = 0; i < n0 + lag; ++i) {
+        if (i < n1) fn(NKC - 1 - i, 1, true, false);
+        const int j = i - lag;
+        if (j >= 0) fn(NKC - 1 - j, 0, j >= n1, true);
+    }
 }
 
 // work unit -> (tile of 128 grid points, contiguous range of bins); units are dealt round-robin
@@ -401,18 +491,28 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef B2_MAP_TRACE
+    int trace_n = 0;
+#endif
     const int NKC = (M + KCH - 1) / KCH;          // K chunks
     const int Mk = NKC * KCH;
     const int NBLK = (M + NB - 1) / NB;           // column blocks
     const int akind = amp_kind(steering);
     float *tab = scratch + size_t(blockIdx.x) * TILE_G * Mk;
+    // column blocks are processed in pairs that share their A tiles (CF::SHARE), else one by one
+    constexpr bool SHARE = CF::SHARE;
+    constexpr int GS = CF::GS;
+    const int NPAIR = SHARE ? (NBLK + 1) / 2 : NBLK;
+    auto pair_b0 = [&](int p) { return SHARE ? 2 * p : p; };
+    auto pair_b1 = [&](int p) { return (SHARE && 2 * p + 1 < NBLK) ? 2 * p + 1 : -1; };
+    auto first_chunk = [&](int blk) { return (blk * NB) / KCH; };          // first K chunk that reaches block blk
 
     // A ring stage: [A_hi][A_corr?]; B ring stage: [B_hi][B_corr?]
     auto a_tile = [&](int s, int split) { return smem + s * CF::A_STAGE + split * A_TILE; };
     auto b_tile = [&](int s, int split) { return smem + NSA * CF::A_STAGE + s * CF::B_STAGE + split * CF::B_TILE; };
 
     if (tid == 0) {
-        for (int s = 0; s < NSA; ++s) { mbar_init(&fullA[s], NGEN / 32); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < NSA; ++s) { mbar_init(&fullA[s], NGEN / 32); mbar_init(&emptyA[s], 2); }   // both issue warps release
         for (int s = 0; s < NSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEPI / 32); }
         fence_barrier_init();
@@ -449,27 +549,29 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             // Two register buffers alternate (the chunk loop is flat and unrolled by two); rotating one
             // buffer into the other would make the compiler wait for the newest load at the top of the body.
             float4 r_a[G4], r_b[G4];
-            int pf_nbk = 0, pf_ci = 0;                       // cursor of the next chunk to prefetch
+            // cursor of the next chunk to prefetch: every pair walks kc = NKC-1 ... first chunk of its block b0
+            int pf_p = 0, pf_kc = NKC - 1;
             auto prefetch = [&](float4 *dst) {
-                const int kc0p = (pf_nbk * NB) / KCH;
-                const int kc = chunk_at(pf_ci, kc0p, NKC);
 #pragma unroll
                 for (int gi = 0; gi < G4; ++gi)
-                    dst[gi] = __ldcg(reinterpret_cast<const float4 *>(tabp + (kc * 4 + gi) * (TILE_G * 4)));
-                if (++pf_ci == NKC - kc0p) { pf_ci = 0; if (++pf_nbk == NBLK) pf_nbk = 0; }
+                    dst[gi] = __ldcg(reinterpret_cast<const float4 *>(tabp + (pf_kc * 4 + gi) * (TILE_G * 4)));
+                if (pf_kc == first_chunk(pair_b0(pf_p))) { pf_kc = NKC - 1; if (++pf_p == NPAIR) pf_p = 0; }
+                else --pf_kc;
             };
             prefetch(r_a);
             prefetch(r_b);
             int chunks_per_bin = 0;
-            for (int nbk = 0; nbk < NBLK; ++nbk) chunks_per_bin += NKC - (nbk * NB) / KCH;
+            for (int p = 0; p < NPAIR; ++p) chunks_per_bin += NKC - first_chunk(pair_b0(p));
             const int total = (f_end - f_begin) * chunks_per_bin;
             int fi = f_begin, cib = 0;                       // bin of the current chunk, its index inside the bin
             float bf = float(freqs[fi] * inv_c);
             {
                 {
+                    // one chunk: synthesise MPT microphones of this row, wait for the ring slot, store, signal
                     auto chunk_body = [&](float4 (&r_cur)[G4]) {
                         // probe the ring slot now so that the barrier round trip overlaps the arithmetic
                         const bool slot_free = mbar_test(&emptyA[sa], pha ^ 1);
+                        if (warp == 0) TRACE(0, 0, cib, fi - f_begin);
                         float rr[MPT];
 #pragma unroll
                         for (int gi = 0; gi < G4; ++gi) {
@@ -511,6 +613,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                         else if (akind == AMP_R) synth(std::integral_constant<int, AMP_R>{});
                         else synth(std::integral_constant<int, AMP_ONE>{});
                         if (!slot_free) { PROF_T0(); mbar_wait(&emptyA[sa], pha ^ 1); PROF_ADD(0, blockIdx.x == 0 && tid == 0); }
+                        if (warp == 0) TRACE(0, slot_free ? 1 : 2, cib, fi - f_begin);
                         const uint32_t ahi = a_base + sa * CF::A_STAGE;
                         const uint32_t alo = ahi + (CF::NSPLIT - 1) * A_TILE;
                         if (PASSES != 4) {
@@ -536,7 +639,11 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&fullA[sa]);
+                        if (warp == 0) TRACE(0, 3, cib, fi - f_begin);
                         if (++sa == NSA) { sa = 0; pha ^= 1; }
+#ifdef B2_DEBUG_HANG
+                        if (warp == 0) { DBG_PROG(0, g_prog[0] + 1); }
+#endif
                         prefetch(r_cur);                     // the chunk after next uses this buffer again
                         if (++cib == chunks_per_bin) {
                             cib = 0;
@@ -570,7 +677,9 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             for (int fi = f_begin; fi < f_end; ++fi) {
                 const float bf = float(freqs[fi] * inv_c);
                 float p0 = 0.f, p1 = 0.f;
-                for (int nbk = 0; nbk < NBLK; ++nbk, ++acc_it) {
+                for (int t = 0; t < NBLK; ++t, ++acc_it) {
+                    // accumulators complete in the order b1, b0 within a pair (see walk_pair)
+                    const int nbk = !SHARE ? t : ((t & 1) ? t - 1 : (t + 1 < NBLK ? t + 1 : t));
                     const int buf = acc_it & 1;
                     // this warp's groups of 8 columns (microphones) of the block: col0, col0 + 8, ...
                     const int col0 = half * CG_PER_HALF * 32;
@@ -584,7 +693,9 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                         ra = __ldcg(reinterpret_cast<const float4 *>(tabq));
                         rb = __ldcg(reinterpret_cast<const float4 *>(tabq + TILE_G * 4));
                     }
+                    if (ew == 0) TRACE(1, 0, nbk, fi - f_begin);
                     { PROF_T0(); mbar_wait(&tfull[buf], (acc_it >> 1) & 1); PROF_ADD(5, blockIdx.x == 0 && ew == 0 && lane == 0); }
+                    if (ew == 0) TRACE(1, 1, nbk, fi - f_begin);
                     tc_fence_after();
                     const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N + 2 * col0;
 #pragma unroll 1
@@ -616,6 +727,8 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[buf]);
+                    if (ew == 0) TRACE(1, 2, nbk, fi - f_begin);
+                    if (ew == 0) DBG_PROG(1, acc_it + 1);
                 }
                 // combine the two column halves of this row
                 float *pp = part + (fi & 1) * TILE_G;
@@ -633,37 +746,76 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             // launcher and every unit adds its weighted partial sum
             if (half == 0 && g < G) atomicAdd(map_out + g, acc_map);
         }
-    } else if (warp == W_MMA) {
+    } else if (warp == W_MMA || warp == W_MMA + 1) {
         // =========================== MMA issue ===========================
+        // Two issue warps, one per accumulator stream of a pair (warp W_MMA: block b0, warp W_MMA+1: block
+        // b1): a single issue thread needs ~800 cycles of dependent instructions per step (three barrier
+        // waits, descriptors, elect, 6 MMAs, commits) and was the pacing resource of the kernel.  Both warps
+        // walk the same step sequence; each acts on the steps of its own stream.  Every A tile is released by
+        // BOTH warps (emptyA counts 2): the warp that does not multiply a tile arrives on it directly.
+        const int my = warp - W_MMA;
         // The whole warp walks the loop, so every address, descriptor and flag is warp-uniform and lives in
         // uniform registers; one elected lane issues the tcgen05 instructions.  (Running the loop inside an
         // `if (lane == 0)` made every tcgen05.mma cost ~13 instructions of register shuffling, and the issue
         // thread -- not the tensor pipe -- set the pace of the kernel: time grew linearly with the number of
         // MMA instructions, 110 cycles each.)
-        const uint32_t a0 = desc_lo(smem_u32(smem)), b0 = desc_lo(smem_u32(smem) + NSA * CF::A_STAGE);
-        uint32_t sa = 0, pha = 0, sb = 0, phb = 0, acc_it = 0;
+        const uint32_t a0 = desc_lo(smem_u32(smem)), b0d = desc_lo(smem_u32(smem) + NSA * CF::A_STAGE);
+        uint32_t seqA = 0;                                   // A tiles consumed so far (ring sequence number)
+        uint32_t sb = 0, phb = 0, acc_it = 0;
         for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
             B2_UNIT_DECODE
             (void)tile;
             for (int fi = f_begin; fi < f_end; ++fi) {
-                for (int nbk = 0; nbk < NBLK; ++nbk, ++acc_it) {
-                    const uint32_t buf = acc_it & 1;
-                    { PROF_T0(); mbar_wait(&tempty[buf], ((acc_it >> 1) & 1) ^ 1); PROF_ADD(3, blockIdx.x == 0 && lane == 0); }
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * UMMA_N;
-                    const int kc0 = (nbk * NB) / KCH;
-                    const int nch = NKC - kc0;
-                    for (int ci = 0; ci < nch; ++ci) {
-                        const int kc = chunk_at(ci, kc0, NKC);
+                for (int p = 0; p < NPAIR; ++p) {
+                    const int blk0 = pair_b0(p), blk1 = pair_b1(p);
+                    const int kcA = first_chunk(blk0), kcB = blk1 >= 0 ? first_chunk(blk1) : NKC;
+                    // accumulators are handed out round-robin in completion order: b1 (if any), then b0
+                    const uint32_t acc1 = acc_it, acc0 = acc_it + (blk1 >= 0 ? 1u : 0u);
+                    acc_it = acc0 + 1;
+                    const uint32_t seq0 = seqA;                  // ring sequence number of chunk NKC-1
+                    seqA += uint32_t(NKC - kcA);
+                    walk_pair(NKC, kcA, kcB, GS, [&](int kc, int tgt, bool first_use, bool last_use) {
+                        (void)last_use;
+                        DBG_PROG(2 + my, g_prog[2 + my] + 1);
+                        if (tgt != my) {
+                            // the other warp's step: this warp only has to release a tile it never multiplies
+                            // (a b0-only chunk seen by the b1 warp) -- after the tile's phase is complete, so
+                            // that the arrival cannot land in an earlier phase
+                            if (my == 1 && first_use) {
+                                const uint32_t seq = seq0 + uint32_t(NKC - 1 - kc);
+                                const uint32_t sa = seq % NSA, pha = (seq / NSA) & 1;
+                                mbar_wait(&fullA[sa], pha);
+                                if (elect_one_sync()) mbar_arrive(&emptyA[sa]);
+                                __syncwarp();
+                            }
+                            // The B tile of the step is not used by this warp, but its barrier is still
+                            // waited for: a warp that skipped ahead by a whole round of the ring would
+                            // otherwise mistake an older phase of the same parity for its own tile.
+                            mbar_wait(&fullB[sb], phb);
+                            if (++sb == NSB) { sb = 0; phb ^= 1; }
+                            return;
+                        }
+                        const uint32_t acc = tgt ? acc1 : acc0;
+                        const uint32_t buf = acc & 1;
+                        TRACE(2 + my, 0, kc, fi - f_begin);
+                        if (kc == NKC - 1) {                     // first MMA of this accumulator: buffer drained?
+                            PROF_T0(); mbar_wait(&tempty[buf], ((acc >> 1) & 1) ^ 1); PROF_ADD(3, blockIdx.x == 0 && lane == 0 && my == 0);
+                        }
+                        const uint32_t d_tmem = tmem_base + buf * UMMA_N;
+                        const int kbase = tgt ? kcB : kcA;
                         // columns of this block that chunk kc can reach (lower triangle): w, N = 2w
-                        const int w = min(NB, KCH * (kc - kc0 + 1));
-                        { PROF_T0(); mbar_wait(&fullB[sb], phb); PROF_ADD(7, blockIdx.x == 0 && lane == 0); }
-                        { PROF_T0(); mbar_wait(&fullA[sa], pha); PROF_ADD(2, blockIdx.x == 0 && lane == 0); }
+                        const int w = min(NB, KCH * (kc - kbase + 1));
+                        const uint32_t seq = seq0 + uint32_t(NKC - 1 - kc);
+                        const uint32_t sa = seq % NSA, pha = (seq / NSA) & 1;
+                        { PROF_T0(); mbar_wait(&fullB[sb], phb); PROF_ADD(7, blockIdx.x == 0 && lane == 0 && my == 0); }
+                        { PROF_T0(); mbar_wait(&fullA[sa], pha); PROF_ADD(2, blockIdx.x == 0 && lane == 0 && my == 0); }
                         tc_fence_after();
+                        TRACE(2 + my, 1, kc, fi - f_begin);
+                        DBG_PROG(8 + my, 1000 * kc + 10 * tgt + 1);
                         // low words of the operand descriptors: first image, second (correction) image
-                        const uint32_t a1 = a0 + sa * (CF::A_STAGE >> 4), b1 = b0 + sb * (CF::B_STAGE >> 4);
+                        const uint32_t a1 = a0 + sa * (CF::A_STAGE >> 4), b1 = b0d + sb * (CF::B_STAGE >> 4);
                         const uint32_t a2 = a1 + (CF::NSPLIT - 1) * (A_TILE >> 4), b2 = b1 + (CF::NSPLIT - 1) * (CF::B_TILE >> 4);
-                        const uint32_t first = ci > 0 ? 1u : 0u;           // 0: the first MMA overwrites the accumulator
+                        const uint32_t first = kc != NKC - 1 ? 1u : 0u;    // 0: the first MMA overwrites the accumulator
                         if (elect_one_sync()) {
                             if (PASSES == 4) {
                                 // row = [f1 | f2] (A) resp. [g1 | g2] (B), 64 B each = 2 K-steps of 16 halfs:
@@ -672,8 +824,9 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
 #pragma unroll
                                 for (uint32_t ks = 0; ks < 2; ++ks) {
                                     const uint32_t adv = ks * 2;               // (32 B) >> 4
-                                    umma_bf16(d_tmem, desc64(a1 + adv), desc64(b1 + adv), idh, ks > 0 ? 1u : first);
-                                    umma_bf16(d_tmem, desc64(a1 + adv), desc64(b1 + 4 + adv), idh, 1u);
+                                    // the f1 slice of A is read from shared memory once for both products
+                                    umma_f16_afill(d_tmem, desc64(a1 + adv), desc64(b1 + adv), idh, ks > 0 ? 1u : first);
+                                    umma_f16_alastuse(d_tmem, desc64(a1 + adv), desc64(b1 + 4 + adv), idh, 1u);
                                     umma_bf16(d_tmem, desc64(a1 + 4 + adv), desc64(b1 + adv), idh, 1u);
                                 }
                             } else {
@@ -691,42 +844,46 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                                         umma_bf16(d_tmem, desc64(a2 + adv), desc64(b2 + adv), idesc_bf16(TILE_G, 2 * w), 1u);
                                 }
                             }
-                            umma_commit(&emptyA[sa]);                     // free both stages when the MMAs retire
+                            // tcgen05.commit: the barriers are signalled when the MMAs issued so far retire
+                            umma_commit(&emptyA[sa]);                      // this warp is done with the A tile
                             umma_commit(&emptyB[sb]);
-                            if (ci == nch - 1) umma_commit(&tfull[buf]);  // accumulator complete -> epilogue
+                            if (kc == kbase) umma_commit(&tfull[buf]);     // accumulator complete -> epilogue
                         }
                         __syncwarp();
-                        if (++sa == NSA) { sa = 0; pha ^= 1; }
+                        TRACE(2 + my, 2, kc, fi - f_begin);
+                        DBG_PROG(8 + my, 1000 * kc + 10 * tgt + 2);
                         if (++sb == NSB) { sb = 0; phb ^= 1; }
-                    }
+                    });
                 }
             }
         }
     } else {
         // =========================== B operand loader (one thread) ===========================
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t sb = 0, phb = 0;
             const size_t bin_bytes = size_t(NBLK) * NKC * CF::NSPLIT * CF::B_TILE;
             for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
-            B2_UNIT_DECODE
+                B2_UNIT_DECODE
+                (void)tile;
                 for (int fi = f_begin; fi < f_end; ++fi) {
-                    for (int nbk = 0; nbk < NBLK; ++nbk) {
-                        const int kc0 = (nbk * NB) / KCH;
-                        for (int ci = 0; ci < NKC - kc0; ++ci, ++it) {
-                            const int kc = chunk_at(ci, kc0, NKC);
-                            const int s = it % NSB;
-                            const int w = min(NB, KCH * (kc - kc0 + 1));
-#ifdef B2_EXPERIMENT_BDIV
-                            const uint32_t bytes = uint32_t(2 * w) * 128 / B2_EXPERIMENT_BDIV;   // timing experiment only (wrong results)
-#else
+                    for (int p = 0; p < NPAIR; ++p) {
+                        const int blk0 = pair_b0(p), blk1 = pair_b1(p);
+                        const int kcA = first_chunk(blk0), kcB = blk1 >= 0 ? first_chunk(blk1) : NKC;
+                        // the tiles are consumed in exactly the order of the MMA warp's walk
+                        walk_pair(NKC, kcA, kcB, GS, [&](int kc, int tgt, bool, bool) {
+                            const int blk = tgt ? blk1 : blk0;
+                            const int w = min(NB, KCH * (kc - (tgt ? kcB : kcA) + 1));
                             const uint32_t bytes = uint32_t(2 * w) * 128;          // first 2w rows of each image
+                            mbar_wait(&emptyB[sb], phb ^ 1);
+                            const unsigned char *src = op + size_t(fi) * bin_bytes + (size_t(blk) * NKC + kc) * (CF::NSPLIT * CF::B_TILE);
+                            mbar_arrive_expect_tx(&fullB[sb], CF::NSPLIT * bytes);
+                            bulk_g2s(b_tile(sb, 0), src, bytes, &fullB[sb]);
+                            if (CF::NSPLIT == 2) bulk_g2s(b_tile(sb, 1), src + CF::B_TILE, bytes, &fullB[sb]);
+                            if (++sb == NSB) { sb = 0; phb ^= 1; }
+#ifdef B2_DEBUG_HANG
+                            if (blockIdx.x == 0) g_prog[4] += 1;
 #endif
-                            mbar_wait(&emptyB[s], ((it / NSB) & 1) ^ 1);
-                            const unsigned char *src = op + size_t(fi) * bin_bytes + (size_t(nbk) * NKC + kc) * (CF::NSPLIT * CF::B_TILE);
-                            mbar_arrive_expect_tx(&fullB[s], CF::NSPLIT * bytes);
-                            bulk_g2s(b_tile(s, 0), src, bytes, &fullB[s]);
-                            if (CF::NSPLIT == 2) bulk_g2s(b_tile(s, 1), src + CF::B_TILE, bytes, &fullB[s]);
-                        }
+                        });
                     }
                 }
             }
@@ -915,6 +1072,35 @@ template <int PASSES> int64_t operand_bytes(int M, int nbins) {
 }
 
 }  // namespace
+
+#ifdef B2_DEBUG_HANG
+extern "C" int b2_debug_hang_report(unsigned int *out) {      // out[0] = count, then 4 words per record
+    unsigned int n = 0, z = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_nhang, 4);
+    out[0] = n;
+    cudaMemcpyFromSymbol(out + 1, g_hang, sizeof(unsigned int) * 240);
+    cudaMemcpyFromSymbol(out + 241, g_snap, sizeof(unsigned int) * 16);
+    unsigned int zz[16] = {0};
+    cudaMemcpyToSymbol(g_prog, zz, sizeof(zz));
+    cudaMemcpyToSymbol(g_snap, zz, sizeof(zz));
+    cudaMemcpyToSymbol(g_snapped, &z, 4);
+    cudaMemcpyToSymbol(g_nhang, &z, 4);
+    cudaMemcpyToSymbol(g_abort, &z, 4);
+    return 0;
+}
+#endif
+
+#ifdef B2_MAP_TRACE
+extern "C" int b2_debug_trace(long long *out, int max_records) {      // copies [4 roles][1024]{tag, clock}
+    (void)max_records;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 4 * 2 * 1024);
+    static long long zeros[4 * 2 * 1024];
+    cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros));
+    return 4096;
+}
+#endif
 
 #ifdef B2_MAP_PROFILE
 extern "C" int b2_debug_map_profile(unsigned long long *out) {
