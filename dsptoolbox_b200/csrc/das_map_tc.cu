@@ -513,7 +513,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
 
     if (tid == 0) {
         for (int s = 0; s < NSA; ++s) { mbar_init(&fullA[s], NGEN / 32); mbar_init(&emptyA[s], 2); }   // both issue warps release
-        for (int s = 0; s < NSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+        for (int s = 0; s < NSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 2); }         // both issue warps release
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEPI / 32); }
         fence_barrier_init();
     }
@@ -751,8 +751,8 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         // Two issue warps, one per accumulator stream of a pair (warp W_MMA: block b0, warp W_MMA+1: block
         // b1): a single issue thread needs ~800 cycles of dependent instructions per step (three barrier
         // waits, descriptors, elect, 6 MMAs, commits) and was the pacing resource of the kernel.  Both warps
-        // walk the same step sequence; each acts on the steps of its own stream.  Every A tile is released by
-        // BOTH warps (emptyA counts 2): the warp that does not multiply a tile arrives on it directly.
+        // walk the same step sequence; each acts on the steps of its own stream.  Every A and B tile is released
+        // by BOTH warps (emptyA / emptyB count 2): the warp that does not multiply a tile arrives on it directly.
         const int my = warp - W_MMA;
         // The whole warp walks the loop, so every address, descriptor and flag is warp-uniform and lives in
         // uniform registers; one elected lane issues the tcgen05 instructions.  (Running the loop inside an
@@ -788,10 +788,15 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                                 if (elect_one_sync()) mbar_arrive(&emptyA[sa]);
                                 __syncwarp();
                             }
-                            // The B tile of the step is not used by this warp, but its barrier is still
-                            // waited for: a warp that skipped ahead by a whole round of the ring would
-                            // otherwise mistake an older phase of the same parity for its own tile.
+                            // The B tile of the step is not used by this warp, but the warp still waits for it
+                            // and releases it (emptyB counts 2): a stage is only recycled after BOTH warps have
+                            // passed it, so neither can get a whole ring round away from the other -- mbarrier
+                            // waits only know the parity of a phase, and a warp one round ahead (or two behind)
+                            // would mistake another phase for its own (scripts/sim_protocol.py reproduces the
+                            // deadlock that follows).
                             mbar_wait(&fullB[sb], phb);
+                            if (elect_one_sync()) mbar_arrive(&emptyB[sb]);
+                            __syncwarp();
                             if (++sb == NSB) { sb = 0; phb ^= 1; }
                             return;
                         }

@@ -20,7 +20,7 @@ def walk_pair(NKC, kcA, kcB, LAG):
         j = i - lag
         if j >= 0: yield (NKC - 1 - j, 0, j >= n1, True)
 
-def main(M, NB, NSA, NSB, LAG, nbins, share=True, seed=0):
+def main(M, NB, NSA, NSB, LAG, nbins, share=True, seed=0, emptyb_count=2, stall=0.5, quiet=False):
     KCH = 16
     NKC = (M + KCH - 1) // KCH
     NBLK = (M + NB - 1) // NB
@@ -29,7 +29,7 @@ def main(M, NB, NSA, NSB, LAG, nbins, share=True, seed=0):
     b1 = lambda p: (2 * p + 1) if (share and 2 * p + 1 < NBLK) else -1
     fc = lambda b: b * NB // KCH
     fullA = [Bar(1) for _ in range(NSA)]; emptyA = [Bar(2) for _ in range(NSA)]
-    fullB = [Bar(1) for _ in range(NSB)]; emptyB = [Bar(1) for _ in range(NSB)]
+    fullB = [Bar(1) for _ in range(NSB)]; emptyB = [Bar(emptyb_count) for _ in range(NSB)]
     tfull = [Bar(1), Bar(1)]; tempty = [Bar(1), Bar(1)]
     log = []
 
@@ -68,6 +68,9 @@ def main(M, NB, NSA, NSB, LAG, nbins, share=True, seed=0):
                         if my == 1 and fu:
                             while not fullA[sa].done(pha): yield (f"D{my} skip wait fullA", sa, pha, kc)
                             emptyA[sa].arrive()
+                        # skipped B tile: wait for it (keeps this warp inside the ring's current round) ...
+                        while not fullB[sb].done(phb): yield (f"D{my} skip wait fullB", sb, phb, kc)
+                        if emptyb_count == 2: emptyB[sb].arrive()      # ... and let the loader recycle it
                         sb += 1
                         if sb == NSB: sb = 0; phb ^= 1
                         yield None
@@ -97,23 +100,34 @@ def main(M, NB, NSA, NSB, LAG, nbins, share=True, seed=0):
     roles = {"synth": synth(), "loader": loader(), "D0": issuer(0), "D1": issuer(1), "epi": epilogue()}
     rng = random.Random(seed)
     state = {}
+    slow = {n: (rng.random() < 0.5) for n in roles}          # some roles are slow in this run
     while roles:
         progressed = False
         names = list(roles); rng.shuffle(names)
+        stalled = False
         for n in names:
+            if slow[n] and rng.random() < stall:
+                stalled = True
+                continue
             try:
                 r = next(roles[n])
             except StopIteration:
                 del roles[n]; progressed = True; continue
             if r is None: progressed = True
             state[n] = r
-        if not progressed:
-            print("DEADLOCK:", {n: state[n] for n in roles}); return False
-    print("ok"); return True
+        if not progressed and not stalled:
+            print("DEADLOCK:", {n: state.get(n) for n in roles}); return False
+    if not quiet: print("ok")
+    return True
 
 if __name__ == "__main__":
     a = sys.argv
     M, NB, NSA, NSB, LAG, nbins = (int(x) for x in a[1:7])
     share = len(a) < 8 or a[7] != "0"
-    for seed in range(5):
-        if not main(M, NB, NSA, NSB, LAG, nbins, share, seed): break
+    ebc = int(a[8]) if len(a) > 8 else 2
+    bad = 0
+    for seed in range(int(a[9]) if len(a) > 9 else 300):
+        if not main(M, NB, NSA, NSB, LAG, nbins, share, seed, ebc, 0.9, True):
+            bad += 1
+            if bad >= 3: break
+    print("deadlocks:", bad)
