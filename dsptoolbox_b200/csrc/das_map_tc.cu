@@ -49,6 +49,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -466,9 +467,11 @@ __device__ __forceinline__ void walk_pair(int NKC, int kcA, int kcB, int LAG, F 
     }
 }
 
-// work unit -> (tile of 128 grid points, contiguous range of bins); units are dealt round-robin
+// work unit -> (contiguous range of bins, tile of 128 grid points); units are dealt round-robin and ordered
+// bin-range-major: all CTAs work on the same range of bins at the same time, so the operand images of that
+// range (sized to fit the L2) are fetched from HBM once per launch instead of once per wave of tiles
 #define B2_UNIT_DECODE                                                        \
-    const int tile = unit / nsplit, upart = unit - tile * nsplit;            \
+    const int upart = unit / ntiles, tile = unit - upart * ntiles;           \
     const int f_begin = int(int64_t(nbins) * upart / nsplit);                \
     const int f_end = int(int64_t(nbins) * (upart + 1) / nsplit);
 
@@ -1047,9 +1050,13 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
     }
     const int64_t ntiles = (G + TILE_G - 1) / TILE_G;
     B2_REQUIRE(ntiles <= 0x7fffffff, B2_EINVAL, "b2_das_map: too many grid points");
-    // Persistent grid, one CTA per SM.  When the tiles do not fill the last round of CTAs evenly
-    // (e.g. 977 tiles on 148 SMs: 60 % of the SMs idle in round 7), the bins of every tile are split
-    // into up to 4 work units so that the tail shrinks; partial maps are combined with atomicAdd.
+    // Persistent grid, one CTA per SM.  The bins are split into nsplit ranges and a work unit is (bin range,
+    // tile); partial maps are combined with atomicAdd.  Two reasons to split:
+    //  * L2 reuse: a range whose operand images fit the L2 (~64 MB of its 126 MB) is streamed from HBM once
+    //    and then served from L2 to every tile.  Unsplit, the persistent CTAs drift apart over the 2048 bins
+    //    of their tiles and each re-reads the operand from HBM (ncu: 928 GB per launch at 10^6 points).
+    //  * tail: when the tiles do not fill the last round of CTAs evenly (e.g. 977 tiles on 148 SMs: 60 % of
+    //    the SMs idle in round 7), up to 4 ranges shrink the idle tail.
     int cap = num_sms < MAX_CTAS ? num_sms : MAX_CTAS;
     int nsplit = 1;
     double best = 0.0;
@@ -1058,6 +1065,20 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
         const int64_t rounds = (units + cap - 1) / cap;
         const double eff = double(units) / double(rounds * cap);
         if (eff > best + 0.01) { best = eff; nsplit = sp; }
+    }
+    {
+        static double chunk_mb = -1.0;
+        if (chunk_mb < 0.0) {                              // B2_MAP_L2_CHUNK_MB: tuning knob (0 disables)
+            const char *e = getenv("B2_MAP_L2_CHUNK_MB");
+            chunk_mb = e ? atof(e) : 64.0;
+        }
+        if (chunk_mb > 0.0 && ntiles > cap) {              // more than one wave of tiles: reuse pays
+            const double total_mb = double(images_bytes<PASSES>(M, nbins)) / 1048576.0;
+            int by_l2 = int(total_mb / chunk_mb + 0.999);
+            const int most = nbins / 32 > 0 ? nbins / 32 : 1;      // at least 32 bins per unit
+            if (by_l2 > most) by_l2 = most;
+            if (by_l2 > nsplit) nsplit = by_l2;
+        }
     }
     const int64_t units = ntiles * nsplit;
     const int nblocks = int(units < cap ? units : cap);
