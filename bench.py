@@ -15,7 +15,8 @@ stage 1 with one NCCL all-reduce, grid points for stage 2 with one all-gather): 
   e2e       the same step through the public host API: pinned host recording in, host map out
             (H2D of the samples and D2H of the result inside the timed region)
   roofline  dominant kernel (the map kernel): algorithmic flops 4*M^2*G*F / its CUDA-event time,
-            against the cuBLAS TF32 peak measured in this run (/3 for split-TF32)
+            against the cuBLAS GEMM peak measured in this run in the mode's arithmetic
+            (FP16 / 3 for the default FP16x3 mode, TF32 / 3 split-TF32, TF32 / 2 mixed)
   cpu_baseline  the oracle port with the reference's loop structure, timed here on a bounded sample
 """
 
@@ -466,8 +467,8 @@ def run_b200(args):
         pass
     roofline = {"kernel": f"das_map[{mode_name}]", "bound": "tensor", "achieved": achieved, "peak": tensor_peak,
                 "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": traffic,
-                "traffic_note": "dram__bytes_read+write of one launch (ncu --set full, profiles/); the 4.3 GB operand "
-                                "is re-streamed by each of the 53 tile waves -> 0.5 % of HBM bandwidth, compute-bound",
+                "traffic_note": "dram__bytes_read+write of one launch (ncu, profiles/map_kernel_traffic.json); the operand images "
+                                "are re-streamed from HBM per wave of tiles -> ~1 % of HBM bandwidth, compute-bound",
                 "algorithmic_flops_per_launch": alg_flops, "kernel_ms": ms_map_kernel,
                 "peak_source": f"cuBLAS {peak_kind.upper()} 8192^3 measured in this run: burst {peak_tf32_burst:.1f}, sustained {peak_tf32_sustained:.1f} TFLOP/s; used {peak_tf32:.1f}"
                                + (" / 3 (FP16x3: three FP16 tensor products per algorithmic product)" if mode == N.MAP_TC_F16X3 else "")

@@ -27,7 +27,8 @@ class Config:
     #: "fp64" = strict (fp64 FFT + fp64 tensor-core accumulation, meets rtol 1e-5 on any data),
     #: "fp32" = fast (fp32 FFT and spectra, fp64 accumulation).
     csm_precision: str = "fp64"
-    #: "auto", "simt_f64", "simt_f32", "tf32", "tf32x3", "mixed" (TF32 product + BF16 corrections)
+    #: "auto" (= "f16x3": two FP16 halves per operand, three tensor products), "mixed" (TF32 product + BF16
+    #: corrections), "tf32x3", "tf32" (single pass, outside the parity contract), "simt_f32", "simt_f64"
     map_mode: str = "auto"
     #: device spectra buffer budget in bytes; longer recordings are processed in frame chunks
     spectra_budget_bytes: int = 24 << 30
