@@ -361,9 +361,8 @@ __device__ __forceinline__ void sts128u(uint32_t saddr, uint4 v) {
 __host__ __device__ __forceinline__ int sw128_offset(int r, int j) { return (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4); }
 
 // ---------------------------------------------------------------- per-tile geometry table
-// tab[((m >> 2) * 128 + row) * 4 + (m & 3)] = r = |grid_row - mic_m| (fp32 of an fp64 result): the
-// bin-independent part of the steering phase.  The amplitude follows from r and three per-row
-// constants, |h| = c0 + c1 / r + c2 * r  (the four formulations of beamforming.py:1515-1703).
+// tab[((m >> 2) * 128 + row) * 4 + (m & 3)] = d = |grid_row - mic_m| - |grid_row - array centre| (fp32 of an
+// fp64 result): the bin-independent part of the steering phase.  The amplitude follows from r = r0 + d.
 __device__ __forceinline__ int tab_index(int m, int row) { return (((m >> 2) * TILE_G) + row) * 4 + (m & 3); }
 
 // The four formulations of beamforming.py:1515-1703 all have |h_m| = c_g * u(r_m) with ONE per-grid-point
@@ -380,9 +379,10 @@ __host__ __device__ inline int amp_kind(int steering) {
 __device__ __forceinline__ double row_table(float *__restrict__ tab, int row, int part, bool write, int64_t g,
                                             int64_t G, const double *__restrict__ grid,
                                             const double *__restrict__ mic, int M, int Mk, double cx0, double cy0,
-                                            double cz0, int steering, float *amp_scale) {
+                                            double cz0, int steering, float *amp_scale, float *r0_out) {
     const bool valid = g < G;
     double x = 0, y = 0, z = 0, c = 0.0;
+    float r0f = 1.0f;                     // fp32 distance grid point -> array centre (the reference's rt0)
     *amp_scale = 1.0f;
     if (valid) {
         x = grid[3 * g]; y = grid[3 * g + 1]; z = grid[3 * g + 2];
@@ -392,6 +392,7 @@ __device__ __forceinline__ double row_table(float *__restrict__ tab, int row, in
             s += 1.0 / (dx * dx + dy * dy + dz * dz);
         }
         const double r0 = das_distance(x, y, z, cx0, cy0, cz0);
+        r0f = float(r0);
         if (steering != B2_STEER_CLASSIC && r0 > 0.0 && r0 < 1e30) {
             int e = ilogb(r0);                                     // r0 = 2^e * [1, 2)
             e = e < -60 ? -60 : (e > 60 ? 60 : e);
@@ -409,23 +410,28 @@ __device__ __forceinline__ double row_table(float *__restrict__ tab, int row, in
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int m = m4 + i;
-                float v = 1.0f;
-                if (valid && m < M) v = float(das_distance(x, y, z, mic[3 * m], mic[3 * m + 1], mic[3 * m + 2]));
-                tab[tab_index(m, row)] = v;
+                // d = r_m - r0 (beamforming.py:1556 uses exactly this difference in the phase): bounded by the array
+                // aperture however far the grid point is, so the fp32 phase product q*d stays accurate; r_m itself
+                // (amplitude) is recovered as r0 + d.  Padding: d with r0 + d = 1.
+                double d = 1.0 - double(r0f);
+                if (valid && m < M) d = das_distance(x, y, z, mic[3 * m], mic[3 * m + 1], mic[3 * m + 2]) - double(r0f);
+                tab[tab_index(m, row)] = float(d);
             }
         }
     }
+    *r0_out = r0f;
     return c * c;
 }
 
-// h'[g, m] = u(r) exp(-i 2 pi q r), q = f / c in cycles per metre: returns (Re, Im).
-// The phase is reduced to a fraction of a cycle before the MUFU sincos.  q r < 2^9 cycles, so the
-// fp32 product carries an absolute phase error <= ~1e-4 rad per element -- the same size as the
-// fp32 rounding of r itself; being uncorrelated over microphones it changes the map by < 1e-6 of
-// its maximum (first-order phase perturbations cancel at a coherent peak).
+// h'[g, m] = u(r) exp(-i 2 pi q d), d = r - r0, q = f / c in cycles per metre: returns (Re, Im).  (The common
+// phase exp(+i 2 pi q r0) of a grid point cancels in h^H C h.)  The phase is reduced to a fraction of a cycle
+// before the MUFU sincos.  |q d| is at most a few tens of cycles (d is bounded by the array aperture), so the
+// fp32 product carries an absolute phase error of ~1e-5 rad per element; being uncorrelated over microphones
+// it changes the map by < 1e-6 of its maximum (first-order phase perturbations cancel at a coherent peak).
 template <int AMP>
-__device__ __forceinline__ float2 steer(float r, float q, float us = 1.0f) {
-    const float p = q * r;
+__device__ __forceinline__ float2 steer(float d, float q, float r0, float us = 1.0f) {
+    const float p = q * d;
+    const float r = r0 + d;
     const float rn = (p + 12582912.0f) - 12582912.0f;         // round to nearest integer (|p| < 2^22)
     const float fr = p - rn;
     float sn, cs;
@@ -542,7 +548,8 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             // the epilogue warps are done with the previous tile's table before it is overwritten
             asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");
             float us;                                     // power-of-two amplitude scale of this grid point
-            row_table(tab, r, part, true, int64_t(tile) * TILE_G + r, G, grid, mic, M, Mk, cx0, cy0, cz0, steering, &us);
+            float r0f;                                    // distance of this grid point to the array centre
+            row_table(tab, r, part, true, int64_t(tile) * TILE_G + r, G, grid, mic, M, Mk, cx0, cy0, cz0, steering, &us, &r0f);
             if (PASSES != 4) us = 1.0f;
             __threadfence_block();
             asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");
@@ -587,8 +594,8 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                             constexpr int AMP = decltype(amp_tag)::value;
 #pragma unroll
                             for (int j = 0; j < MPT / 2; ++j) {
-                                const float2 h0 = steer<AMP>(rr[2 * j], bf, us);
-                                const float2 h1 = steer<AMP>(rr[2 * j + 1], bf, us);
+                                const float2 h0 = steer<AMP>(rr[2 * j], bf, r0f, us);
+                                const float2 h1 = steer<AMP>(rr[2 * j + 1], bf, r0f, us);
                                 uint32_t *p1 = reinterpret_cast<uint32_t *>(&img1[j >> 1]) + 2 * (j & 1);
                                 uint32_t *p2 = reinterpret_cast<uint32_t *>(&img2[j >> 1]) + 2 * (j & 1);
                                 if (PASSES == 4) {           // img1 = first FP16 halves, img2 = second halves
@@ -673,7 +680,8 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             const int64_t g = int64_t(tile) * TILE_G + r;
             asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");
             float us;
-            double c2 = row_table(tab, r, 0, false, g, G, grid, mic, M, Mk, cx0, cy0, cz0, steering, &us);
+            float r0f;
+            double c2 = row_table(tab, r, 0, false, g, G, grid, mic, M, Mk, cx0, cy0, cz0, steering, &us, &r0f);
             if (PASSES == 4) c2 /= double(us);            // T carries the amplitude scale once (the epilogue's h does not)
             asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");   // table of this tile is complete
             double acc_map = 0.0;
@@ -716,7 +724,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 // padded microphones have all-zero operand rows, so T is 0 there: no bounds test
-                                const float2 h0 = steer<AMP>(rq[2 * j], bf), h1 = steer<AMP>(rq[2 * j + 1], bf);
+                                const float2 h0 = steer<AMP>(rq[2 * j], bf, r0f), h1 = steer<AMP>(rq[2 * j + 1], bf, r0f);
                                 p0 = fmaf(t[4 * j], h0.x, p0);
                                 p0 = fmaf(-t[4 * j + 1], h0.y, p0);
                                 p1 = fmaf(t[4 * j + 2], h1.x, p1);
