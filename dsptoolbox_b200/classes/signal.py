@@ -35,6 +35,7 @@ class Signal(MultichannelData):
         self.sampling_rate_hz = sampling_rate_hz
         self.time_data = time_data
         self.set_spectrum_parameters()
+        self.set_spectrogram_parameters()
 
     @staticmethod
     def from_time_data(time_data, sampling_rate_hz: int, constrain_amplitude: bool = True):
@@ -44,6 +45,8 @@ class Signal(MultichannelData):
     def _invalidate(self):
         self._csm_dirty = True
         self._csm_dev = None
+        self._spectrogram_dirty = True
+        self._spectrogram = None
 
     def _get_data(self):
         return self._time_data
@@ -182,5 +185,32 @@ class Signal(MultichannelData):
         freqs = np.fft.rfftfreq(p["window_length_samples"], 1 / self.sampling_rate_hz)
         return freqs, spec.cpu().numpy()
 
-    def get_spectrogram(self, *a, **k):
-        raise NotImplementedError("Signal.get_spectrogram is outside the accelerated path (SURVEY.md section 8f)")
+    # ---- spectrogram (next row f4) ---------------------------------------------------------------
+    def set_spectrogram_parameters(self, window_length_samples: int = 1024, window_type: Window = Window.Hann,
+                                   overlap_percent: float = 50.0, fft_length_samples: int | None = None,
+                                   detrend: bool = False, padding: bool = True,
+                                   scaling: SpectrumScaling = SpectrumScaling.FFTBackward):
+        """Parameters of the STFT, reference signal.py:706-773 (same names and defaults)."""
+        new = dict(window_length_samples=window_length_samples, window_type=window_type,
+                   overlap_percent=overlap_percent, fft_length_samples=fft_length_samples, detrend=detrend,
+                   padding=padding, scaling=scaling)
+        old = getattr(self, "_spectrogram_parameters", None)
+        if old is None or any(old[k] != new[k] for k in old):
+            self._spectrogram_parameters = new
+            self._spectrogram_dirty = True
+            self._spectrogram = None
+        return self
+
+    def get_spectrogram(self, force_computation: bool = False):
+        """(t_s, f_hz, spectrogram (frequency, time, channel)) -- reference signal.py:1009-1056 on the
+        framing / window / rFFT kernels of the Welch stage.  Host arrays, complex128 (float64 for the power
+        scalings); with `activate_cache` the result is kept until the data or the parameters change."""
+        p = self._spectrogram_parameters
+        if getattr(self, "_spectrogram", None) is None or force_computation or self._spectrogram_dirty:
+            res = _sm._stft(self.time_data, self.sampling_rate_hz, p["window_length_samples"], p["window_type"],
+                            p["overlap_percent"], p["fft_length_samples"], p["detrend"], p["padding"], p["scaling"])
+            self._spectrogram_dirty = False
+            if not self.activate_cache:
+                return res
+            self._spectrogram = res
+        return tuple(a.copy() for a in self._spectrogram)

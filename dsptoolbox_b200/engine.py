@@ -225,6 +225,54 @@ def csm_partial_sums(x, length: int, wl: int, step: int, window: np.ndarray, det
     return S, K_total
 
 
+def frame_spectra(x, length: int, wl: int, step: int, window: np.ndarray, detrend: bool, fft_scale: float,
+                  precision: str | None = None, device=None):
+    """Spectra of ALL frames, complex128 CUDA tensor (bins, frames, channels): the framing / window /
+    mean-removal / rFFT kernels of the Welch stage (K0, K1) without the averaging -- what the STFT
+    (reference `_stft`, _spectral_methods.py:176-282) keeps.  Frames follow helpers/other.py:181-213
+    (ceil(L/step) frames, zero-padded tail).  torch is only used to re-order the kernel's chunk-major
+    spectra [frames/16][bins][channels][16] into the reference's (bins, frames, channels).
+    """
+    torch = _torch()
+    lib = N.lib()
+    prec = _PREC[(precision or config.csm_precision).lower()]
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    M = int(x.shape[1])
+    K_total, _ = welch_frames(length, wl, step)
+    nb = wl // 2 + 1
+    rdt = torch.float64 if prec == N.F64 else torch.float32
+    cdt = torch.complex128 if prec == N.F64 else torch.complex64
+    st = N.stream_handle()
+    tile = max(16, N.check(lib.b2_welch_frame_tile(wl, prec), "b2_welch_frame_tile"))
+    bytes_per_frame = nb * M * (16 if prec == N.F64 else 8)
+    max_frames = max(tile, (config.spectra_budget_bytes // bytes_per_frame) // tile * tile)
+    win = torch.from_numpy(np.ascontiguousarray(window, dtype=np.float64)).to(device).to(rdt)
+    tw = _twiddles(wl, prec, device)
+    out = torch.empty((nb, K_total, M), dtype=torch.complex128, device=device)
+    kc = 0
+    while kc < K_total:
+        kn = min(K_total, kc + max_frames)
+        nfr = kn - kc
+        Kp = (nfr + tile - 1) // tile * tile
+        t0 = kc * step
+        t1 = min(length, (kn - 1) * step + wl)
+        Lp = (Kp - 1) * step + wl
+        Lp += (-Lp) % 4
+        xs, code, s_t, s_m = _as_device_block(x, t0, t1, device)
+        xc = torch.empty((M, Lp), dtype=rdt, device=device)
+        N.check(lib.b2_prepare_channels(N.ptr(xs), code, s_t, s_m, 0, t1 - t0, M, N.ptr(xc), Lp, prec, st),
+                "b2_prepare_channels")
+        _count()
+        X = torch.empty((Kp // 16, nb, M, 16), dtype=cdt, device=device)
+        N.check(lib.b2_welch_rfft(N.ptr(xc), Lp, M, wl, step, nfr, N.ptr(win), N.ptr(tw), int(bool(detrend)),
+                                  float(fft_scale), N.ptr(X), Kp, prec, st), "b2_welch_rfft")
+        _count()
+        out[:, kc:kn, :] = X.permute(1, 0, 3, 2).reshape(nb, Kp, M)[:, :nfr, :]
+        kc = kn
+        del xs, xc, X
+    return out
+
+
 def csm_finalize(S, n_frames: int, factor: float, halve_edges: bool, amplitude_sqrt: bool):
     """Average / scale / sqrt / mirror the summed spectra -> complex128 (nb, M, M) CUDA tensor."""
     torch = _torch()

@@ -133,3 +133,56 @@ def _welch(x, y, fs_hz: int, window_type, window_length_samples: int, overlap_pe
         idx = np.arange(ch)
         out = csm[:, idx + ch, idx].cpu().numpy()
     return out[:, 0] if flat else out
+
+
+# --------------------------------------------------------------------------- next row f4: STFT
+def stft_device(time_data, fs_hz: int, window_length_samples: int, window_type, overlap_percent: float,
+                fft_length_samples, detrend: bool, padding: bool, scaling: SpectrumScaling):
+    """STFT left on the device: (time_s, freqs_hz [numpy], stft CUDA tensor (frequency, time, channel)),
+    complex128, or float64 for the power scalings -- reference `_stft`, _spectral_methods.py:176-282.
+    Framing, window, mean removal and the real FFT are the kernels of the Welch stage; the scaling
+    epilogue of :266-277 runs as a few element-wise device operations."""
+    import torch
+
+    valid_window_sizes = [int(2 ** p) for p in range(4, 17)]
+    assert window_length_samples in valid_window_sizes, (
+        "Window length should be a power of 2 between [16, 65536] or [2**4, 2**16]")
+    assert overlap_percent >= 0 and overlap_percent < 100, "overlap_percent should be between 0 and 100"
+    if fft_length_samples is not None and fft_length_samples != window_length_samples:
+        raise NotImplementedError("an FFT length different from the window length is not part of the B200 path")
+    spec = window_type.to_scipy_format() if isinstance(window_type, Window) else window_type
+    from scipy.signal.windows import get_window
+
+    window = get_window(spec, window_length_samples, fftbins=True)
+    overlap_samples = int(overlap_percent / 100 * window_length_samples + 0.5)      # rounded, unlike _welch (:248)
+    step = window_length_samples - overlap_samples
+    if not check_COLA(window, nperseg=len(window), noverlap=overlap_samples):
+        warn("Selected window type and overlap do not meet the constant overlap and add constraint! "
+             "Results might be distorted")
+    if not hasattr(time_data, "shape") or len(time_data.shape) != 2:
+        time_data = np.atleast_2d(np.asarray(time_data))
+    if padding:
+        if isinstance(time_data, torch.Tensor):
+            time_data = torch.nn.functional.pad(time_data, (0, 0, overlap_samples, overlap_samples))
+        else:
+            time_data = np.pad(np.asarray(time_data), ((overlap_samples, overlap_samples), (0, 0)))
+    length = int(time_data.shape[0])
+    stft = engine.frame_spectra(time_data, length, window_length_samples, step, window, detrend,
+                                scaling.fft_scale(window_length_samples))
+    if scaling.has_physical_units():
+        stft[0] /= 2 ** 0.5
+        stft[-1] /= 2 ** 0.5                       # the length is a power of two, i.e. even (:268)
+        factor = float(np.squeeze(scaling.get_scaling_factor(window_length_samples, fs_hz, window)))
+        if not scaling.is_amplitude_scaling():
+            stft = stft.real ** 2 + stft.imag ** 2
+        stft = stft * factor
+    time_s = np.linspace(0, length / fs_hz, stft.shape[1])
+    return time_s, np.fft.rfftfreq(window_length_samples, 1 / fs_hz), stft
+
+
+def _stft(x, fs_hz: int, window_length_samples: int, window_type, overlap_percent: float,
+          fft_length_samples, detrend: bool, padding: bool, scaling: SpectrumScaling):
+    """Drop-in for reference _spectral_methods.py:176-282: host arrays (time_s, freqs_hz, stft)."""
+    t, f, st = stft_device(x, fs_hz, window_length_samples, window_type, overlap_percent, fft_length_samples,
+                           detrend, padding, scaling)
+    return t, f, st.cpu().numpy()

@@ -58,7 +58,50 @@ def ref_map(dsp, x, fs, wl, mic_pos, grid, formulation, fc, frac, remove_diag, c
     return m, np.asarray(bf.f_range_hz)
 
 
+STFT_CASES = [  # (wl, window, overlap %, fft_length, detrend, padding, scaling)
+    (256, "Hann", 50.0, None, False, True, "FFTBackward"),
+    (256, "Hann", 75.0, None, True, True, "PowerSpectralDensity"),
+    (128, "Hamming", 50.0, None, False, False, "AmplitudeSpectrum"),
+    (512, "Blackman", 66.0, None, True, False, "PowerSpectrum"),
+    (64, "Hann", 0.0, None, False, True, "FFTOrthogonal"),
+    (256, "Hann", 50.0, None, True, True, "AmplitudeSpectralDensity"),
+    (128, "Hann", 50.0, None, False, True, "FFTForward"),
+    (128, "Hann", 50.0, 256, False, True, "PowerSpectralDensity"),     # zero-padded FFT (oracle only)
+    (256, "Hann", 50.0, 128, True, False, "FFTBackward"),               # cropped frames (oracle only)
+]
+
+
+def stft_golden(dsp):
+    """Next row f4: `_stft` (standard/_spectral_methods.py:176-282) through Signal.get_spectrogram."""
+    import warnings
+    rng = np.random.default_rng(77)
+    fs = 8000
+    x = rng.standard_normal((3000, 3)) * np.array([1.0, 0.3, 2.0]) + np.array([0.5, 0.0, -1.0])
+    out = dict(x=x, fs=fs, n_cases=len(STFT_CASES))
+    for i, (wl, win, ov, nfft, det, pad, sc) in enumerate(STFT_CASES):
+        s = dsp.Signal(None, x.copy(), fs)
+        s.set_spectrogram_parameters(window_length_samples=wl, window_type=getattr(dsp.Window, win), overlap_percent=ov,
+                                     fft_length_samples=nfft, detrend=det, padding=pad,
+                                     scaling=getattr(dsp.SpectrumScaling, sc))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t, f, st = s.get_spectrogram()
+        to, fo, so = R.stft(x, fs, wl, win.lower(), ov, nfft, det, pad, sc)
+        err = rel_to_max(so, st)
+        print(f"F{i} stft wl={wl} {win} ov={ov} n={nfft} detrend={det} pad={pad} {sc}: shape {st.shape} {st.dtype} "
+              f"oracle-vs-ref {err:.2e}")
+        assert so.shape == st.shape and so.dtype == st.dtype and err < 1e-13
+        assert np.allclose(to, t, rtol=0, atol=1e-15) and np.allclose(fo, f, rtol=0, atol=1e-12)
+        out[f"params_{i}"] = np.array([wl, ov, -1 if nfft is None else nfft, int(det), int(pad)], dtype=np.float64)
+        out[f"names_{i}"] = np.array([win, sc])
+        out[f"t_{i}"], out[f"f_{i}"], out[f"stft_{i}"] = t, f, st
+    np.savez_compressed(os.path.join(GOLDEN, "stft_small.npz"), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "stft":        # regenerate only the STFT fixture
+        stft_golden(ref_loader.load())
+        return
     os.makedirs(GOLDEN, exist_ok=True)
     dsp = ref_loader.load()
     W = dsp.Window
@@ -216,6 +259,7 @@ def main():
         csm_idx=idx, csm_vals=c1[idx[:, 0], idx[:, 1], idx[:, 2]],
         csm_bins=np.array([1, 85, 512]), csm_full_bins=c1[[1, 85, 512]],
         csm_diag_bin85=np.diagonal(c1[85]).copy(), map=m1, f_range=fr1)
+    stft_golden(dsp)
     print("golden vectors written to", GOLDEN)
 
 

@@ -198,6 +198,48 @@ def csm_welch(x, fs, wl=1024, window="hann", overlap_percent=50, detrend=True,
     return np.fft.rfftfreq(wl, 1 / fs), out
 
 
+# --------------------------------------------------------------------------- next row f4: STFT
+def stft_step(wl: int, overlap_percent: float) -> tuple[int, int]:
+    """_spectral_methods.py:248-249: NOTE the overlap is rounded here (+0.5), unlike `_welch`."""
+    overlap_samples = int(overlap_percent / 100 * wl + 0.5)
+    return overlap_samples, wl - overlap_samples
+
+
+def stft(x, fs, wl=1024, window="hann", overlap_percent=50.0, fft_length=None, detrend=False,
+         padding=True, scaling="fftbackward"):
+    """`_stft` (_spectral_methods.py:176-282) -> (time_s, freqs_hz, stft (frequency, time, channel)).
+
+    Frames like Welch's (zero-padded tail, window THEN mean removal), optional zero padding of
+    `overlap_samples` at both ends, rfft of length `fft_length` (crop or zero-pad) with the scaling's
+    norm; physical scalings: DC (and Nyquist for even lengths) divided by sqrt(2), |.|^2 for the
+    power scalings, times the scaling factor.  The frequency vector uses the WINDOW length (:281).
+    """
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    n = wl if fft_length is None else int(fft_length)
+    w = welch_window(window, wl)
+    overlap_samples, step = stft_step(wl, overlap_percent)
+    if padding:
+        z = np.zeros((overlap_samples, x.shape[1]))
+        x = np.concatenate([z, x, z], axis=0)
+    fr = framed(x, wl, step)
+    fr *= w[:, None, None]
+    if detrend:
+        fr -= np.mean(fr, axis=0)
+    out = np.fft.rfft(fr, axis=0, n=n, norm=fft_norm(scaling))
+    sc = scaling.lower()
+    if sc in PHYSICAL_SCALINGS:
+        out[0] /= 2**0.5
+        if n % 2 == 0:
+            out[-1] /= 2**0.5
+        if sc not in AMPLITUDE_SCALINGS:
+            out = np.abs(out) ** 2.0
+        out = out * scaling_factor(sc, n, fs, w)
+    time_s = np.linspace(0, x.shape[0] / fs, out.shape[1])
+    return time_s, np.fft.rfftfreq(wl, 1 / fs), out
+
+
 # --------------------------------------------------------------------------- stage 2
 def distance_matrix(x: np.ndarray, y: np.ndarray) -> np.ndarray:
     """helpers/other.py:131-153 (expansion formula, NOT direct differences)."""

@@ -138,3 +138,25 @@ def test_get_spectrum_welch(golden_dir, scaling):
     x = g["x"]
     so = np.stack([R.welch_pair(x[:, i], None, int(g["fs"]), "hann", int(g["wl"]), 50, True, scaling) for i in range(x.shape[1])], axis=1)
     assert rel_to_max(so, g["spectrum_" + scaling]) < 1e-13
+
+
+def _stft_cases(golden_dir):
+    g = np.load(os.path.join(golden_dir, "stft_small.npz"))
+    for i in range(int(g["n_cases"])):
+        wl, ov, nfft, det, pad = g[f"params_{i}"]
+        win, sc = (str(v) for v in g[f"names_{i}"])
+        yield g, i, int(wl), win.lower(), float(ov), (None if nfft < 0 else int(nfft)), bool(det), bool(pad), sc
+
+
+def test_stft_next_row(golden_dir):
+    """Next row f4: the oracle's `stft` against the reference's Signal.get_spectrogram for every scaling family,
+    padding / detrend on and off, rounded overlaps, and FFT lengths that zero-pad or crop the frames."""
+    n = 0
+    for g, i, wl, win, ov, nfft, det, pad, sc in _stft_cases(golden_dir):
+        t, f, st = R.stft(g["x"], int(g["fs"]), wl, win, ov, nfft, det, pad, sc)
+        ref = g[f"stft_{i}"]
+        assert st.shape == ref.shape and st.dtype == ref.dtype
+        assert np.max(np.abs(st - ref)) <= 1e-13 * np.max(np.abs(ref))
+        assert np.array_equal(f, g[f"f_{i}"]) and np.allclose(t, g[f"t_{i}"], rtol=0, atol=1e-15)
+        n += 1
+    assert n == 9

@@ -46,3 +46,24 @@ def test_steering_vectors():
         h = dsp.beamforming.SteeringVector(getattr(dsp.beamforming.SteeringVectorType, name)).get_vector(k, g, ma)
         ho = R.steering_vector(k, g.coordinates, ma.coordinates, name)
         assert np.allclose(h, ho, rtol=1e-13, atol=0)
+
+
+def test_stft_random():
+    """Next row f4: oracle `stft` vs the real `_stft` (through Signal.get_spectrogram) on fresh random input."""
+    import warnings
+    dsp = ref_loader.load()
+    rng = np.random.default_rng(123)
+    x = rng.standard_normal((2500, 2)) + 0.3
+    for wl, win, ov, nfft, det, pad, sc in [(128, "Hann", 60.0, None, True, True, "PowerSpectrum"),
+                                             (256, "Hamming", 33.0, None, False, False, "FFTBackward"),
+                                             (64, "Hann", 50.0, 128, True, True, "AmplitudeSpectralDensity")]:
+        s = dsp.Signal(None, x.copy(), 16000)
+        s.set_spectrogram_parameters(window_length_samples=wl, window_type=getattr(dsp.Window, win), overlap_percent=ov,
+                                     fft_length_samples=nfft, detrend=det, padding=pad,
+                                     scaling=getattr(dsp.SpectrumScaling, sc))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t, f, st = s.get_spectrogram()
+        to, fo, so = R.stft(x, 16000, wl, win.lower(), ov, nfft, det, pad, sc)
+        assert so.shape == st.shape and np.max(np.abs(so - st)) <= 1e-13 * np.max(np.abs(st))
+        assert np.allclose(to, t, rtol=0, atol=1e-15) and np.array_equal(fo, f)
