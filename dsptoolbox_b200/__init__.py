@@ -12,9 +12,12 @@ hand-written CUDA behind the C ABI of include/b2dsp.h.  There is no CPU fallback
 """
 
 from . import beamforming  # noqa: F401
+from . import transfer_functions  # noqa: F401
 from .classes import Signal  # noqa: F401
+from .classes.spectrum import Spectrum  # noqa: F401
 from .engine import config  # noqa: F401
 from .standard.enums import SpectrumMethod, SpectrumScaling, Window  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["Signal", "SpectrumMethod", "SpectrumScaling", "Window", "beamforming", "config"]
+__all__ = ["Signal", "Spectrum", "SpectrumMethod", "SpectrumScaling", "Window", "beamforming", "config",
+           "transfer_functions"]

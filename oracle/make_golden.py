@@ -98,9 +98,54 @@ def stft_golden(dsp):
     np.savez_compressed(os.path.join(GOLDEN, "stft_small.npz"), **out)
 
 
+TF_CASES = [  # (mode, shared one-channel input, window length, overlap %, detrend, scaling)
+    ("H1", False, 256, 50, True, "FFTBackward"),
+    ("H2", False, 256, 50, True, "FFTBackward"),
+    ("H3", False, 256, 50, True, "FFTBackward"),
+    ("H1", True, 128, 75, False, "PowerSpectralDensity"),
+    ("H2", True, 512, 50, True, "AmplitudeSpectrum"),
+    ("H3", True, 256, 25, True, "PowerSpectrum"),
+]
+
+
+def tf_golden(dsp):
+    """Next row f3: `compute_transfer_function` (transfer_functions/transfer_functions.py:419-536)."""
+    import warnings
+    from scipy.signal import lfilter
+    rng = np.random.default_rng(2024)
+    fs = 16000
+    L, ch = 6000, 3
+    xin = rng.standard_normal((L, ch))
+    # outputs: each input through a short FIR plus uncorrelated noise (coherence < 1)
+    firs = [np.array([1.0, 0.5, -0.25]), np.array([0.2, 0.0, 0.9, 0.1]), np.array([-0.7, 0.3])]
+    yout = np.stack([lfilter(firs[c], [1.0], xin[:, c]) for c in range(ch)], 1) + 0.2 * rng.standard_normal((L, ch))
+    yshared = np.stack([lfilter(firs[c], [1.0], xin[:, 0]) for c in range(ch)], 1) + 0.2 * rng.standard_normal((L, ch))
+    out = dict(x_in=xin, y_out=yout, y_shared=yshared, fs=fs, n_cases=len(TF_CASES))
+    for i, (mode, shared, wl, ov, det, sc) in enumerate(TF_CASES):
+        sin = dsp.Signal(None, (xin[:, :1] if shared else xin).copy(), fs)
+        sin.set_spectrum_parameters(overlap_percent=ov, detrend=det, scaling=getattr(dsp.SpectrumScaling, sc))
+        sout = dsp.Signal(None, (yshared if shared else yout).copy(), fs)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            spec = dsp.transfer_functions.compute_transfer_function(
+                sout, sin, wl, getattr(dsp.transfer_functions.TransferFunctionType, mode))
+        fo, tfo, coho = R.transfer_function(yshared if shared else yout, xin[:, :1] if shared else xin, fs, wl, "hann",
+                                            ov, det, sc, mode)
+        e1, e2 = rel_to_max(tfo, spec.spectral_data), rel_to_max(coho, spec.coherence)
+        print(f"G{i} {mode} shared={shared} wl={wl} ov={ov} detrend={det} {sc}: tf oracle-vs-ref {e1:.2e} coherence {e2:.2e}")
+        assert e1 < 1e-12 and e2 < 1e-12 and np.array_equal(fo, spec.frequency_vector_hz)
+        out[f"params_{i}"] = np.array([int(shared), wl, ov, int(det)], dtype=np.float64)
+        out[f"names_{i}"] = np.array([mode, sc])
+        out[f"tf_{i}"], out[f"coh_{i}"], out[f"f_{i}"] = spec.spectral_data, spec.coherence, spec.frequency_vector_hz
+    np.savez_compressed(os.path.join(GOLDEN, "transfer_functions.npz"), **out)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "stft":        # regenerate only the STFT fixture
         stft_golden(ref_loader.load())
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "tf":          # regenerate only the transfer-function fixture
+        tf_golden(ref_loader.load())
         return
     os.makedirs(GOLDEN, exist_ok=True)
     dsp = ref_loader.load()
@@ -260,6 +305,7 @@ def main():
         csm_bins=np.array([1, 85, 512]), csm_full_bins=c1[[1, 85, 512]],
         csm_diag_bin85=np.diagonal(c1[85]).copy(), map=m1, f_range=fr1)
     stft_golden(dsp)
+    tf_golden(dsp)
     print("golden vectors written to", GOLDEN)
 
 

@@ -198,6 +198,44 @@ def csm_welch(x, fs, wl=1024, window="hann", overlap_percent=50, detrend=True,
     return np.fft.rfftfreq(wl, 1 / fs), out
 
 
+# --------------------------------------------------------------------------- next row f3: H1/H2/H3
+def transfer_function(x_out, x_in, fs, wl, window="hann", overlap_percent=50, detrend=True,
+                      scaling="fftbackward", mode="h2"):
+    """`compute_transfer_function` (transfer_functions/transfer_functions.py:419-536) with the reference's own
+    loop: per output channel the auto-spectra G_xx, G_yy and the cross-spectra G_xy = _welch(x, y) (and
+    G_yx = _welch(y, x) for H2), then H1 = G_xy/G_xx, H2 = G_yy/G_yx, H3 = G_xy/|G_xy| sqrt(G_yy/G_xx) and the
+    coherence |G_xy|^2/G_xx/G_yy.  A one-channel input serves all outputs.  -> (f, tf (nb, ch), coherence)."""
+    x_out = np.asarray(x_out, dtype=np.float64)
+    x_in = np.asarray(x_in, dtype=np.float64)
+    if x_in.ndim == 1:
+        x_in = x_in[:, None]
+    if x_out.ndim == 1:
+        x_out = x_out[:, None]
+    n_out = x_out.shape[1]
+    shared_input = x_in.shape[1] == 1
+    nb = wl // 2 + 1
+    tf = np.zeros((nb, n_out), dtype=np.complex128)
+    coherence = np.zeros((nb, n_out))
+    mode = mode.lower()
+    args = (fs, window, wl, overlap_percent, detrend, scaling)
+    for n in range(n_out):
+        xi = x_in[:, 0 if shared_input else n]
+        y = x_out[:, n]
+        g_xx = welch_pair(xi, None, *args)
+        g_yy = welch_pair(y, None, *args)
+        g_xy = welch_pair(xi, y, *args)
+        if mode == "h1":
+            tf[:, n] = g_xy / g_xx
+        elif mode == "h2":
+            tf[:, n] = g_yy / welch_pair(y, xi, *args)
+        elif mode == "h3":
+            tf[:, n] = g_xy / np.abs(g_xy) * (g_yy / g_xx) ** 0.5
+        else:
+            raise ValueError("Unsupported transfer function type")
+        coherence[:, n] = np.abs(g_xy) ** 2 / g_xx / g_yy
+    return np.fft.rfftfreq(wl, 1 / fs), tf, coherence
+
+
 # --------------------------------------------------------------------------- next row f4: STFT
 def stft_step(wl: int, overlap_percent: float) -> tuple[int, int]:
     """_spectral_methods.py:248-249: NOTE the overlap is rounded here (+0.5), unlike `_welch`."""

@@ -160,3 +160,17 @@ def test_stft_next_row(golden_dir):
         assert np.array_equal(f, g[f"f_{i}"]) and np.allclose(t, g[f"t_{i}"], rtol=0, atol=1e-15)
         n += 1
     assert n == 9
+
+
+def test_transfer_functions_next_row(golden_dir):
+    """Next row f3: the oracle's H1 / H2 / H3 + coherence against the reference's compute_transfer_function."""
+    g = np.load(os.path.join(golden_dir, "transfer_functions.npz"))
+    for i in range(int(g["n_cases"])):
+        shared, wl, ov, det = g[f"params_{i}"]
+        mode, sc = (str(v) for v in g[f"names_{i}"])
+        y = g["y_shared"] if shared else g["y_out"]
+        x = g["x_in"][:, :1] if shared else g["x_in"]
+        f, tf, coh = R.transfer_function(y, x, int(g["fs"]), int(wl), "hann", float(ov), bool(det), sc, mode)
+        assert np.array_equal(f, g[f"f_{i}"])
+        assert np.max(np.abs(tf - g[f"tf_{i}"])) <= 1e-12 * np.max(np.abs(g[f"tf_{i}"]))
+        assert np.max(np.abs(coh - g[f"coh_{i}"])) <= 1e-12 * np.max(np.abs(g[f"coh_{i}"]))
