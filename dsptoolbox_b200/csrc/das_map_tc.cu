@@ -250,20 +250,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
-    uint32_t *r = reinterpret_cast<uint32_t *>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     uint32_t *r = reinterpret_cast<uint32_t *>(v);
@@ -575,97 +561,93 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             const int total = (f_end - f_begin) * chunks_per_bin;
             int fi = f_begin, cib = 0;                       // bin of the current chunk, its index inside the bin
             float bf = float(freqs[fi] * inv_c);
-            {
-                {
-                    // one chunk: synthesise MPT microphones of this row, wait for the ring slot, store, signal
-                    auto chunk_body = [&](float4 (&r_cur)[G4]) {
-                        // probe the ring slot now so that the barrier round trip overlaps the arithmetic
-                        const bool slot_free = mbar_test(&emptyA[sa], pha ^ 1);
-                        if (warp == 0) TRACE(0, 0, cib, fi - f_begin);
-                        float rr[MPT];
+            // one chunk: synthesise MPT microphones of this row, wait for the ring slot, store, signal
+            auto chunk_body = [&](float4 (&r_cur)[G4]) {
+                // probe the ring slot now so that the barrier round trip overlaps the arithmetic
+                const bool slot_free = mbar_test(&emptyA[sa], pha ^ 1);
+                if (warp == 0) TRACE(0, 0, cib, fi - f_begin);
+                float rr[MPT];
 #pragma unroll
-                        for (int gi = 0; gi < G4; ++gi) {
-                            rr[4 * gi] = r_cur[gi].x; rr[4 * gi + 1] = r_cur[gi].y;
-                            rr[4 * gi + 2] = r_cur[gi].z; rr[4 * gi + 3] = r_cur[gi].w;
-                        }
-                        float4 hi4[MPT / 2], lo4[MPT / 2];   // TF32 images: 2 microphones per 16 bytes
-                        uint4 img1[G4], img2[G4];            // 16-bit images: 4 microphones per 16 bytes
-                        auto synth = [&](auto amp_tag) {
-                            constexpr int AMP = decltype(amp_tag)::value;
-#pragma unroll
-                            for (int j = 0; j < MPT / 2; ++j) {
-                                const float2 h0 = steer<AMP>(rr[2 * j], bf, r0f, us);
-                                const float2 h1 = steer<AMP>(rr[2 * j + 1], bf, r0f, us);
-                                uint32_t *p1 = reinterpret_cast<uint32_t *>(&img1[j >> 1]) + 2 * (j & 1);
-                                uint32_t *p2 = reinterpret_cast<uint32_t *>(&img2[j >> 1]) + 2 * (j & 1);
-                                if (PASSES == 4) {           // img1 = first FP16 halves, img2 = second halves
-                                    const __half2 a1 = __floats2half2_rn(h0.x, h0.y), b1 = __floats2half2_rn(h1.x, h1.y);
-                                    const float2 af = __half22float2(a1), bfl = __half22float2(b1);
-                                    p1[0] = pack_f16(a1);
-                                    p1[1] = pack_f16(b1);
-                                    p2[0] = pack_f16(__floats2half2_rn(h0.x - af.x, h0.y - af.y));
-                                    p2[1] = pack_f16(__floats2half2_rn(h1.x - bfl.x, h1.y - bfl.y));
-                                    continue;
-                                }
-                                if (PASSES == 1) hi4[j] = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
-                                else hi4[j] = make_float4(trunc_tf32(h0.x), trunc_tf32(h0.y), trunc_tf32(h1.x), trunc_tf32(h1.y));
-                                if (PASSES == 3)   // residuals are exact in fp32; the tensor core keeps their top 11 bits
-                                    lo4[j] = make_float4(h0.x - hi4[j].x, h0.y - hi4[j].y, h1.x - hi4[j].z, h1.y - hi4[j].w);
-                                if (PASSES == 2) {           // img1 = bf16 residuals, img2 = bf16 values
-                                    p1[0] = pack_bf16(h0.x - hi4[j].x, h0.y - hi4[j].y);
-                                    p1[1] = pack_bf16(h1.x - hi4[j].z, h1.y - hi4[j].w);
-                                    p2[0] = pack_bf16(h0.x, h0.y);
-                                    p2[1] = pack_bf16(h1.x, h1.y);
-                                }
-                            }
-                        };
-                        if (akind == AMP_RINV) synth(std::integral_constant<int, AMP_RINV>{});
-                        else if (akind == AMP_R) synth(std::integral_constant<int, AMP_R>{});
-                        else synth(std::integral_constant<int, AMP_ONE>{});
-                        if (!slot_free) { PROF_T0(); mbar_wait(&emptyA[sa], pha ^ 1); PROF_ADD(0, blockIdx.x == 0 && tid == 0); }
-                        if (warp == 0) TRACE(0, slot_free ? 1 : 2, cib, fi - f_begin);
-                        const uint32_t ahi = a_base + sa * CF::A_STAGE;
-                        const uint32_t alo = ahi + (CF::NSPLIT - 1) * A_TILE;
-                        if (PASSES != 4) {
-#pragma unroll
-                            for (int j = 0; j < MPT / 2; ++j) {
-                                const int off = sw128_offset(r, part * (MPT / 2) + j);
-                                sts128(ahi + off, hi4[j]);
-                                if (PASSES == 3) sts128(alo + off, lo4[j]);
-                            }
-                        }
-                        if (PASSES == 2 || PASSES == 4) {
-                            // 16-bit image row = [img1 of the chunk's 16 mics | img2 of the 16 mics]: a group of 4 mics
-                            // is 16 bytes = 16-byte chunk (part * G4 + gi) of each 64-byte half.  In FP16x3 mode it is
-                            // the only image of the stage (alo == ahi).
-#pragma unroll
-                            for (int gi = 0; gi < G4; ++gi) {
-                                sts128u(alo + sw128_offset(r, part * G4 + gi), img1[gi]);
-                                sts128u(alo + sw128_offset(r, 4 + part * G4 + gi), img2[gi]);
-                            }
-                        }
-                        // generic-proxy writes -> visible to the MMA (async proxy); one arrival per warp
-                        // (32 same-address arrivals serialise in the shared-memory atomic unit)
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&fullA[sa]);
-                        if (warp == 0) TRACE(0, 3, cib, fi - f_begin);
-                        if (++sa == NSA) { sa = 0; pha ^= 1; }
-#ifdef B2_DEBUG_HANG
-                        if (warp == 0) { DBG_PROG(0, g_prog[0] + 1); }
-#endif
-                        prefetch(r_cur);                     // the chunk after next uses this buffer again
-                        if (++cib == chunks_per_bin) {
-                            cib = 0;
-                            if (++fi < f_end) bf = float(freqs[fi] * inv_c);
-                        }
-                    };
-                    int i = 0;
-#pragma unroll 1
-                    for (; i + 1 < total; i += 2) { chunk_body(r_a); chunk_body(r_b); }
-                    if (i < total) chunk_body(r_a);
+                for (int gi = 0; gi < G4; ++gi) {
+                    rr[4 * gi] = r_cur[gi].x; rr[4 * gi + 1] = r_cur[gi].y;
+                    rr[4 * gi + 2] = r_cur[gi].z; rr[4 * gi + 3] = r_cur[gi].w;
                 }
-            }
+                float4 hi4[MPT / 2], lo4[MPT / 2];   // TF32 images: 2 microphones per 16 bytes
+                uint4 img1[G4], img2[G4];            // 16-bit images: 4 microphones per 16 bytes
+                auto synth = [&](auto amp_tag) {
+                    constexpr int AMP = decltype(amp_tag)::value;
+#pragma unroll
+                    for (int j = 0; j < MPT / 2; ++j) {
+                        const float2 h0 = steer<AMP>(rr[2 * j], bf, r0f, us);
+                        const float2 h1 = steer<AMP>(rr[2 * j + 1], bf, r0f, us);
+                        uint32_t *p1 = reinterpret_cast<uint32_t *>(&img1[j >> 1]) + 2 * (j & 1);
+                        uint32_t *p2 = reinterpret_cast<uint32_t *>(&img2[j >> 1]) + 2 * (j & 1);
+                        if (PASSES == 4) {           // img1 = first FP16 halves, img2 = second halves
+                            const __half2 a1 = __floats2half2_rn(h0.x, h0.y), b1 = __floats2half2_rn(h1.x, h1.y);
+                            const float2 af = __half22float2(a1), bfl = __half22float2(b1);
+                            p1[0] = pack_f16(a1);
+                            p1[1] = pack_f16(b1);
+                            p2[0] = pack_f16(__floats2half2_rn(h0.x - af.x, h0.y - af.y));
+                            p2[1] = pack_f16(__floats2half2_rn(h1.x - bfl.x, h1.y - bfl.y));
+                            continue;
+                        }
+                        if (PASSES == 1) hi4[j] = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
+                        else hi4[j] = make_float4(trunc_tf32(h0.x), trunc_tf32(h0.y), trunc_tf32(h1.x), trunc_tf32(h1.y));
+                        if (PASSES == 3)   // residuals are exact in fp32; the tensor core keeps their top 11 bits
+                            lo4[j] = make_float4(h0.x - hi4[j].x, h0.y - hi4[j].y, h1.x - hi4[j].z, h1.y - hi4[j].w);
+                        if (PASSES == 2) {           // img1 = bf16 residuals, img2 = bf16 values
+                            p1[0] = pack_bf16(h0.x - hi4[j].x, h0.y - hi4[j].y);
+                            p1[1] = pack_bf16(h1.x - hi4[j].z, h1.y - hi4[j].w);
+                            p2[0] = pack_bf16(h0.x, h0.y);
+                            p2[1] = pack_bf16(h1.x, h1.y);
+                        }
+                    }
+                };
+                if (akind == AMP_RINV) synth(std::integral_constant<int, AMP_RINV>{});
+                else if (akind == AMP_R) synth(std::integral_constant<int, AMP_R>{});
+                else synth(std::integral_constant<int, AMP_ONE>{});
+                if (!slot_free) { PROF_T0(); mbar_wait(&emptyA[sa], pha ^ 1); PROF_ADD(0, blockIdx.x == 0 && tid == 0); }
+                if (warp == 0) TRACE(0, slot_free ? 1 : 2, cib, fi - f_begin);
+                const uint32_t ahi = a_base + sa * CF::A_STAGE;
+                const uint32_t alo = ahi + (CF::NSPLIT - 1) * A_TILE;
+                if (PASSES != 4) {
+#pragma unroll
+                    for (int j = 0; j < MPT / 2; ++j) {
+                        const int off = sw128_offset(r, part * (MPT / 2) + j);
+                        sts128(ahi + off, hi4[j]);
+                        if (PASSES == 3) sts128(alo + off, lo4[j]);
+                    }
+                }
+                if (PASSES == 2 || PASSES == 4) {
+                    // 16-bit image row = [img1 of the chunk's 16 mics | img2 of the 16 mics]: a group of 4 mics
+                    // is 16 bytes = 16-byte chunk (part * G4 + gi) of each 64-byte half.  In FP16x3 mode it is
+                    // the only image of the stage (alo == ahi).
+#pragma unroll
+                    for (int gi = 0; gi < G4; ++gi) {
+                        sts128u(alo + sw128_offset(r, part * G4 + gi), img1[gi]);
+                        sts128u(alo + sw128_offset(r, 4 + part * G4 + gi), img2[gi]);
+                    }
+                }
+                // generic-proxy writes -> visible to the MMA (async proxy); one arrival per warp
+                // (32 same-address arrivals serialise in the shared-memory atomic unit)
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&fullA[sa]);
+                if (warp == 0) TRACE(0, 3, cib, fi - f_begin);
+                if (++sa == NSA) { sa = 0; pha ^= 1; }
+#ifdef B2_DEBUG_HANG
+                if (warp == 0) { DBG_PROG(0, g_prog[0] + 1); }
+#endif
+                prefetch(r_cur);                     // the chunk after next uses this buffer again
+                if (++cib == chunks_per_bin) {
+                    cib = 0;
+                    if (++fi < f_end) bf = float(freqs[fi] * inv_c);
+                }
+            };
+            int i = 0;
+#pragma unroll 1
+            for (; i + 1 < total; i += 2) { chunk_body(r_a); chunk_body(r_b); }
+            if (i < total) chunk_body(r_a);
         }
     } else if (warp < W_MMA) {
         // =========================== epilogue: TMEM -> P[g,f] -> map ===========================
