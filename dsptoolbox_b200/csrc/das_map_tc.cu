@@ -270,13 +270,9 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 
 // K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start>>4 | LBO(=1)<<16 | SBO(=1024B>>4)<<32 | version(=1)<<46 | layout SWIZZLE_128B(=2)<<61
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-    return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(64) << 32) | (uint64_t(1) << 46) |
-           (uint64_t(2) << 61);
-}
-// The same descriptor as (constant high word, low word): low = start>>4 | LBO<<16, so that stepping through
-// stages and K slices is 32-bit arithmetic.
+//   start>>4 | LBO(=1)<<16 | SBO(=1024B>>4)<<32 | version(=1)<<46 | layout SWIZZLE_128B(=2)<<61
+// kept as (constant high word, low word = start>>4 | LBO<<16), so that stepping through ring stages and K
+// slices is 32-bit arithmetic on the low word.
 constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return (uint64_t(DESC_HI) << 32) | lo; }
