@@ -151,3 +151,57 @@ def test_beamformer_constructor_checks():
         dsp.beamforming.BeamformerDASFrequency(s, ma, ma, st)                 # grid must be a Grid
     with pytest.raises(AssertionError):
         dsp.beamforming.BeamformerDASFrequency(dsp.Signal(None, rng.standard_normal((500, 3)), 8000), ma, g, st)
+
+
+def test_spectrogram_parameters_and_stft_argument_checks():
+    """reference signal.py:706-773 (names, defaults, state flag) and the asserts of _stft (:234-240); everything
+    checked here fails before any device work, so it runs without a GPU."""
+    from dsptoolbox_b200.standard._spectral_methods import _stft
+    s = dsp.Signal(None, np.random.default_rng(0).standard_normal((2000, 2)), 8000)
+    p = s._spectrogram_parameters
+    assert p == dict(window_length_samples=1024, window_type=dsp.Window.Hann, overlap_percent=50.0,
+                     fft_length_samples=None, detrend=False, padding=True, scaling=dsp.SpectrumScaling.FFTBackward)
+    s._spectrogram_dirty = False
+    assert s.set_spectrogram_parameters() is s and not s._spectrogram_dirty            # unchanged -> still valid
+    s.set_spectrogram_parameters(window_length_samples=256, detrend=True)
+    assert s._spectrogram_dirty and s._spectrogram_parameters["window_length_samples"] == 256
+    x = s.time_data
+    with pytest.raises(AssertionError):
+        _stft(x, 8000, 100, dsp.Window.Hann, 50.0, None, False, True, dsp.SpectrumScaling.FFTBackward)
+    with pytest.raises(AssertionError):
+        _stft(x, 8000, 8, dsp.Window.Hann, 50.0, None, False, True, dsp.SpectrumScaling.FFTBackward)       # < 2**4
+    with pytest.raises(AssertionError):
+        _stft(x, 8000, 256, dsp.Window.Hann, 100.0, None, False, True, dsp.SpectrumScaling.FFTBackward)
+    with pytest.raises(NotImplementedError):
+        _stft(x, 8000, 256, dsp.Window.Hann, 50.0, 512, False, True, dsp.SpectrumScaling.FFTBackward)
+
+
+def test_spectrum_holder_and_transfer_function_argument_checks():
+    """reference classes/spectrum.py:139-260, 871-885 (field validation) and the asserts of
+    compute_transfer_function (transfer_functions.py:453-466), all raised before any device work."""
+    from dsptoolbox_b200.transfer_functions import TransferFunctionType, compute_transfer_function
+    f = np.linspace(0, 4000, 9)
+    sp = dsp.Spectrum(f, np.ones((3, 9)) + 0j)                       # transposed input is turned
+    assert sp.spectral_data.shape == (9, 3) and sp.number_of_channels == 3 and sp.number_frequency_bins == 9
+    sp.set_coherence(np.zeros((9, 3)))
+    with pytest.raises(AssertionError):
+        sp.set_coherence(np.zeros((9, 2)))
+    with pytest.raises(AssertionError):
+        sp.set_coherence(np.zeros((9, 3)) + 0j)
+    with pytest.raises(AssertionError):
+        dsp.Spectrum(f[::-1], np.ones((9, 1)))                        # not ascending
+    with pytest.raises(AssertionError):
+        dsp.Spectrum(f, -np.ones((9, 1)))                             # negative magnitude
+    with pytest.raises(AssertionError):
+        dsp.Spectrum(f, np.ones((7, 2)))                              # length mismatch
+    assert [m.name for m in TransferFunctionType] == ["H1", "H2", "H3"]
+    x = np.random.default_rng(0).standard_normal((4000, 2))
+    a, b = dsp.Signal(None, x, 8000), dsp.Signal(None, x[:3000], 8000)
+    with pytest.raises(AssertionError, match="lengths"):
+        compute_transfer_function(b, a, 256)
+    with pytest.raises(AssertionError, match="Sampling rates"):
+        compute_transfer_function(dsp.Signal(None, x, 16000), a, 256)
+    with pytest.raises(AssertionError, match="Channel number"):
+        compute_transfer_function(dsp.Signal(None, np.c_[x, x[:, :1]], 8000), a, 256)
+    with pytest.raises(ValueError):
+        compute_transfer_function(a, a, 256, "H1")
