@@ -1067,6 +1067,8 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
         }
     }
     const int64_t units = ntiles * nsplit;
+    B2_REQUIRE(units <= 0x7fffffff, B2_EINVAL, "b2_das_map: too many work units (%lld tiles x %d bin ranges)",
+               (long long)ntiles, nsplit);
     const int nblocks = int(units < cap ? units : cap);
     B2_CUDA_OK(cudaMemsetAsync(map_out, 0, size_t(G) * sizeof(double), st));
     float *scratch = tables_ptr<PASSES>(op, M, nbins);
