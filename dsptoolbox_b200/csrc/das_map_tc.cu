@@ -392,7 +392,7 @@ __device__ __forceinline__ double row_table(float *__restrict__ tab, int row, in
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int m = m4 + i;
-                // d = r_m - r0 (beamforming.py:1556 uses exactly this difference in the phase): bounded by the array
+                // d = r_m - r0 (beamforming.py:1557 etc. use exactly this difference in the phase): bounded by the array
                 // aperture however far the grid point is, so the fp32 phase product q*d stays accurate; r_m itself
                 // (amplitude) is recovered as r0 + d.  Padding: d with r0 + d = 1.
                 double d = 1.0 - double(r0f);
