@@ -72,6 +72,24 @@ def allreduce_sum_(t):
     return t
 
 
+def allreduce_lower_triangle_(S):
+    """Sum over ranks of the frame sums S (nb, M, M) of which only the lower triangle (row >= col) is valid:
+    the M(M+1)/2 valid entries per bin are packed, reduced and scattered back, which halves the all-reduce
+    payload (1.08 instead of 2.15 GB at M = 256, nb = 2049).  The upper triangle is left untouched (the
+    finalisation kernel never reads it).  Opt-in via `engine.config.pack_allreduce` until measured on NVLink."""
+    import torch
+
+    dist = _dist()
+    if world()[1] == 1:
+        return S
+    M = S.shape[-1]
+    rows, cols = torch.tril_indices(M, M, device=S.device)
+    packed = S[:, rows, cols].contiguous()
+    dist.all_reduce(torch.view_as_real(packed) if packed.is_complex() else packed, op=dist.ReduceOp.SUM)
+    S[:, rows, cols] = packed
+    return S
+
+
 def allgather_rows(local, counts: list[int]):
     """Concatenate per-rank 1-D tensors of (possibly unequal) lengths `counts` on every rank."""
     import torch
@@ -97,7 +115,8 @@ def get_csm_device_sharded(signal):
     wl = p["window_length_samples"]
     step = wl - int(p["overlap_percent"] / 100 * wl)
     k_total, _ = engine.welch_frames(signal.length_samples, wl, step)
-    return signal._compute_csm_device(frame_range=frame_shard(k_total, rank, nranks), reduce_fn=allreduce_sum_)
+    reduce_fn = allreduce_lower_triangle_ if engine.config.pack_allreduce else allreduce_sum_
+    return signal._compute_csm_device(frame_range=frame_shard(k_total, rank, nranks), reduce_fn=reduce_fn)
 
 
 class DistributedBeamformerDASFrequency(BeamformerDASFrequency):
@@ -127,5 +146,5 @@ def simulate_frame_sharding(n_frames: int, world_size: int) -> list[tuple[int, i
 
 
 __all__ = ["split_range", "frame_shard", "grid_shard", "shard_sample_range", "allreduce_sum_",
-           "allgather_rows", "get_csm_device_sharded", "DistributedBeamformerDASFrequency",
+           "allreduce_lower_triangle_", "allgather_rows", "get_csm_device_sharded", "DistributedBeamformerDASFrequency",
            "simulate_frame_sharding", "world", "np"]

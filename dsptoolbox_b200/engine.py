@@ -32,6 +32,8 @@ class Config:
     map_mode: str = "auto"
     #: device spectra buffer budget in bytes; longer recordings are processed in frame chunks
     spectra_budget_bytes: int = 24 << 30
+    #: multi-GPU: all-reduce only the valid lower triangle of the frame sums (half the payload)
+    pack_allreduce: bool = False
     #: last-call statistics (kernel times are only filled when `profile` is on)
     profile: bool = False
     stats: dict = field(default_factory=dict)

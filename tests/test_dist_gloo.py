@@ -65,7 +65,14 @@ def _worker(rank, world, port, x, wl, overlap, scaling, out):
         fr -= fr.mean(axis=0)
         X = np.fft.rfft(fr, axis=0, norm=R.fft_norm(scaling))               # (nb, k, M)
         S = torch.from_numpy(np.matmul(np.swapaxes(X, 1, 2), X.conj()))      # un-normalised partial sums
+        # the packed variant reduces only the valid lower triangle and must leave the rest alone
+        Sp = S.clone()
+        upper = torch.triu(torch.ones(M, M, dtype=torch.bool), 1)
+        Sp[:, upper] = 12345.0 + rank
+        Sp = bdist.allreduce_lower_triangle_(Sp)
         S = bdist.allreduce_sum_(S)
+        lower = ~upper
+        assert torch.equal(Sp[:, lower], S[:, lower]) and torch.all(Sp[:, upper] == 12345.0 + rank)
         csm = R._finish_welch(S.numpy() / K, scaling, wl, 8000, w)           # non-linear part AFTER the reduce
         # grid sharding + all-gather of unequal pieces
         G = 37
