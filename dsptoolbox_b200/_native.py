@@ -32,7 +32,7 @@ PROTOTYPES = {
                                     c_int64, c_int, c_void_p]),
     "b2_welch_rfft": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_int,
                               c_double, c_void_p, c_int64, c_int, c_void_p]),
-    "b2_csm_herk": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "b2_csm_herk": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "b2_csm_finalize": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_void_p]),
     "b2_welch_autopower": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_void_p]),
     "b2_auto_finalize": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_void_p]),

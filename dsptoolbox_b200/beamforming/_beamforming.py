@@ -38,6 +38,19 @@ class BasePoints:
         self.dim = spans
         self.ndim = len(spans)
         self._coordinates = new_r
+        self._coordinates_dev = None
+
+    def _device_coordinates(self, device=None):
+        """float64 (N, 3) CUDA copy of the coordinates, uploaded once and kept until they are reassigned
+        (the map kernel reads the grid from device memory on every call; 24 MB at 10^6 points)."""
+        import torch
+
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        cached = getattr(self, "_coordinates_dev", None)
+        if cached is None or cached.device != device:
+            cached = torch.from_numpy(np.ascontiguousarray(self._coordinates, dtype=np.float64)).to(device)
+            self._coordinates_dev = cached
+        return cached
 
     @property
     def extent(self) -> dict:

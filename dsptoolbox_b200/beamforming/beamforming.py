@@ -299,7 +299,7 @@ class BeamformerDASFrequency(BeamformerGridded):
         print("...Apply...")
         g0, g1 = self._grid_rows()
         out, pb = engine.das_map(op, self.mics.number_of_points, fsel, weights, self.c, self.mics._coordinates,
-                                 self.mics.array_center_coordinates, self.grid._coordinates[g0:g1],
+                                 self.mics.array_center_coordinates, self.grid._device_coordinates(csm_dev.device)[g0:g1],
                                  _steering_code(self.st_vec), remove_csm_diagonal, mode, per_bin=per_bin)
         self._per_bin_device = pb
         return self._gather_map(out)
@@ -336,10 +336,16 @@ class _QuadraticFormBeamformer(BeamformerGridded):
     def _per_bin_power(self, fsel, matrices, mode=None):
         """(G, F) float64 CUDA tensor of Re(h^H A_f h)."""
         mode = engine.resolve_map_mode(mode)
+        # The map kernel evaluates Re(h^H A h) from the lower triangle of A, i.e. it assumes A Hermitian.  The
+        # reference's full quadratic form equals h^H (A + A^H)/2 h for ANY A, so symmetrising first reproduces
+        # it also when a matrix function (SVD of a rank-deficient CSM, an ill-conditioned inverse) comes back
+        # visibly non-Hermitian.
+        matrices = 0.5 * (matrices + matrices.mH)
         op = engine.das_prepare(matrices.contiguous(), 0, len(fsel), False, mode)
         _, pb = engine.das_map(op, self.mics.number_of_points, fsel, np.ones(len(fsel)), self.c,
                                self.mics._coordinates, self.mics.array_center_coordinates,
-                               self.grid._coordinates, _steering_code(self.st_vec), False, mode, per_bin=True)
+                               self.grid._device_coordinates(matrices.device), _steering_code(self.st_vec), False,
+                               mode, per_bin=True)
         return pb
 
     def _finish(self, per_bin, fsel):

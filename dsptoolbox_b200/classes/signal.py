@@ -58,6 +58,28 @@ class Signal(MultichannelData):
 
     @time_data.setter
     def time_data(self, new_time_data):
+        if hasattr(new_time_data, "is_cuda"):
+            # a torch tensor (device-resident or pinned-host recording) is held as it is -- an extension of the
+            # reference, whose arrays are always numpy: same (time samples, channels) rule, same auto-transpose
+            td = new_time_data
+            assert td.ndim <= 2, (f"{td.ndim} are too many dimensions for time data. Dimensions should"
+                                  " be [time samples, channels]")
+            if td.ndim < 2:
+                td = td[..., None]
+            if td.shape[1] > td.shape[0]:
+                td = td.T
+            assert not td.is_complex(), "complex torch recordings are not supported"
+            self._amplitude_scale_factor = 1.0
+            if self.constrain_amplitude:
+                peak = float(td.abs().max())
+                if peak > 1.0:
+                    td = td / peak
+                    warn("Signal was over 0 dBFS, normalizing to 0 dBFS peak level was triggered")
+                    self._amplitude_scale_factor = 1.0 / peak
+            self._time_data = td
+            self.time_data_imaginary = None
+            self._invalidate()
+            return
         td = np.atleast_2d(new_time_data).squeeze()
         assert td.ndim <= 2, (f"{td.ndim} are too many dimensions for time data. Dimensions should"
                               " be [time samples, channels]")

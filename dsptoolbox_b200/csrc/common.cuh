@@ -37,6 +37,33 @@ void b2_set_error(const char *fmt, ...);
         }                                                                             \
     } while (0)
 
+// ------------------------------------------------------------------ per-device one-time setup
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are properties of a DEVICE, so a
+// process that drives several GPUs (or switches devices between calls) needs them once per device and
+// kernel instantiation.  A function-local `static DeviceOnce once;` + b2_device_once() does that; the
+// races between host threads are benign (the setup is idempotent).
+constexpr int B2_MAX_DEVICES = 64;
+struct DeviceOnce {
+    bool done[B2_MAX_DEVICES];
+    int sms[B2_MAX_DEVICES];
+};
+template <class Kern> int b2_device_once(DeviceOnce &once, Kern kern, int dynamic_smem, int *num_sms) {
+    int dev = 0;
+    B2_CUDA_OK(cudaGetDevice(&dev));
+    const bool cached = dev >= 0 && dev < B2_MAX_DEVICES;
+    if (!cached || !once.done[dev]) {
+        if (dynamic_smem > 0)
+            B2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dynamic_smem));
+        int sms = 0;
+        B2_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (cached) { once.sms[dev] = sms; once.done[dev] = true; }
+        if (num_sms) *num_sms = sms;
+        return B2_OK;
+    }
+    if (num_sms) *num_sms = once.sms[dev];
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------ complex helpers
 template <typename T> struct cx_of;
 template <> struct cx_of<float> { using type = float2; };

@@ -11,6 +11,9 @@
 //   Sr += Ar*Br^T + Ai*Bi^T          Si += Ai*Br^T + Ar*(-Bi)^T
 // Frames are streamed in chunks of 16 through a cp.async double buffer; the spectra layout
 // [frame chunk][bin][channel][16 frames] makes every 64-row tile one contiguous 16 KB run.
+// The sums are kept PACKED: S[f][j (j + 1) / 2 + i] for j >= i (row-major lower triangle, M (M + 1) / 2
+// complex128 values per bin) -- half the bytes of the square, and exactly the payload of the
+// multi-GPU all-reduce (dist.py), which therefore needs no pack / unpack pass.
 #include "common.cuh"
 
 namespace {
@@ -72,7 +75,8 @@ __device__ __forceinline__ void load_tile(unsigned char *dst, const cx<TIN> *__r
 
 template <typename TIN>
 __global__ void __launch_bounds__(HERK_THREADS)
-herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, double2 *__restrict__ S, int accumulate) {
+herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, int bin0, double2 *__restrict__ S,
+                 int accumulate) {
     using SM = HerkSmem<TIN>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -85,7 +89,7 @@ herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, doubl
     while (bj * (bj + 1) / 2 > p) --bj;
     const int bi = p - bj * (bj + 1) / 2;
     const bool diag = (bi == bj);
-    const int f = blockIdx.y;
+    const int f = bin0 + blockIdx.y;
     const int rowA0 = bj * BM, rowB0 = bi * BM;
     const cx<TIN> *Xf = X + int64_t(f) * M * KC;          // chunk 0 of this bin
     const int64_t chunk_stride = int64_t(nb) * M * KC;   // elements between frame chunks
@@ -147,11 +151,12 @@ herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, doubl
     }
 
     // ---- epilogue: C fragment (row = lane/4, cols 2*(lane%4)+{0,1}) ----
-    double2 *Sf = S + int64_t(f) * M * M;
+    double2 *Sf = S + int64_t(f) * (int64_t(M) * (M + 1) / 2);      // packed lower triangle of this bin
 #pragma unroll
     for (int jb = 0; jb < 4; ++jb) {
         const int j = rowA0 + wj * 32 + jb * 8 + (lane >> 2);
         if (j >= M) continue;
+        double2 *Srow = Sf + int64_t(j) * (j + 1) / 2;
 #pragma unroll
         for (int ib = 0; ib < 4; ++ib) {
             const int i0 = rowB0 + wi * 32 + ib * 8 + 2 * (lane & 3);
@@ -160,7 +165,7 @@ herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, doubl
                 const int i = i0 + e;
                 if (i < M && i <= j) {          // rows >= cols only: the rest is implied by Hermitian symmetry
                     double2 v = make_double2(sr[jb][ib][e], si[jb][ib][e]);
-                    double2 *dst = Sf + int64_t(j) * M + i;
+                    double2 *dst = Srow + i;
                     if (accumulate) { double2 o = *dst; v.x += o.x; v.y += o.y; }
                     *dst = v;
                 }
@@ -182,7 +187,8 @@ __device__ __forceinline__ double2 csqrt_principal(double2 z) {
     return make_double2(fabs(b) / (2.0 * t), copysign(t, b));
 }
 
-// K2e: one 32x32 tile of the lower triangle per CTA; mirrored tile written through smem.
+// K2e: one 32x32 tile of the lower triangle per CTA (read from the packed sums); mirrored tile written
+// through smem.
 __global__ void __launch_bounds__(256)
 csm_finalize_kernel(const double2 *__restrict__ S, int M, int nb, double inv_frames, double factor,
                     int halve_edges, int amplitude_sqrt, double2 *__restrict__ out) {
@@ -195,14 +201,14 @@ csm_finalize_kernel(const double2 *__restrict__ S, int M, int nb, double inv_fra
     const int f = blockIdx.y;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     const bool edge = halve_edges && (f == 0 || f == nb - 1);
-    const double2 *Sf = S + int64_t(f) * M * M;
+    const double2 *Sf = S + int64_t(f) * (int64_t(M) * (M + 1) / 2);
     double2 *of = out + int64_t(f) * M * M;
 #pragma unroll
     for (int r = 0; r < 32; r += 8) {
         const int j = tj * 32 + ty + r, i = ti * 32 + tx;
         double2 v = make_double2(0.0, 0.0);
         if (j < M && i < M && i <= j) {
-            v = Sf[int64_t(j) * M + i];
+            v = Sf[int64_t(j) * (j + 1) / 2 + i];
             // order of the reference: mean, *factor, /2 on the edge bins, sqrt
             v.x *= inv_frames; v.y *= inv_frames;
             v.x *= factor; v.y *= factor;
@@ -268,31 +274,31 @@ __global__ void auto_finalize_kernel(const double *__restrict__ P, int M, int nb
 }
 
 template <typename TIN>
-int launch_herk(const void *X, int M, int64_t Kp, int nb, void *S, int accumulate, cudaStream_t st) {
+int launch_herk(const void *X, int M, int64_t Kp, int nb, int bin0, int nbins, void *S, int accumulate, cudaStream_t st) {
     using SM = HerkSmem<TIN>;
     auto kern = herk_dmma_kernel<TIN>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        B2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES));
-        attr_done = true;
-    }
+    static DeviceOnce once;          // per instantiation and device
+    if (int rc = b2_device_once(once, kern, SM::BYTES, nullptr)) return rc;
     const int nbk = (M + BM - 1) / BM;
-    dim3 grid((unsigned)(nbk * (nbk + 1) / 2), (unsigned)nb);
-    kern<<<grid, HERK_THREADS, SM::BYTES, st>>>((const cx<TIN> *)X, M, Kp, nb, (double2 *)S, accumulate);
+    dim3 grid((unsigned)(nbk * (nbk + 1) / 2), (unsigned)nbins);
+    kern<<<grid, HERK_THREADS, SM::BYTES, st>>>((const cx<TIN> *)X, M, Kp, nb, bin0, (double2 *)S, accumulate);
     B2_LAUNCH_OK("b2_csm_herk");
     return B2_OK;
 }
 
 }  // namespace
 
-extern "C" int b2_csm_herk(const void *X_dev, int M, int64_t Kp, int nb, void *S_dev, int accumulate,
-                           int precision, void *stream) {
+extern "C" int b2_csm_herk(const void *X_dev, int M, int64_t Kp, int nb, int bin0, int nbins, void *S_dev,
+                           int accumulate, int precision, void *stream) {
     B2_REQUIRE(X_dev && S_dev, B2_EINVAL, "b2_csm_herk: null pointer");
-    B2_REQUIRE(M > 0 && nb > 0 && nb <= 65535, B2_EINVAL, "b2_csm_herk: bad M=%d / nb=%d", M, nb);
+    B2_REQUIRE(M > 0 && nb > 0, B2_EINVAL, "b2_csm_herk: bad M=%d / nb=%d", M, nb);
+    B2_REQUIRE(bin0 >= 0 && nbins >= 0 && bin0 + nbins <= nb && nbins <= 65535, B2_EINVAL,
+               "b2_csm_herk: bin range [%d, %d) outside [0, %d) (at most 65535 bins per call)", bin0, bin0 + nbins, nb);
     B2_REQUIRE(Kp > 0 && Kp % KC == 0, B2_EINVAL, "b2_csm_herk: Kp=%lld must be a positive multiple of %d", (long long)Kp, KC);
+    if (nbins == 0) return B2_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision == B2_F64) return launch_herk<double>(X_dev, M, Kp, nb, S_dev, accumulate, st);
-    if (precision == B2_F32) return launch_herk<float>(X_dev, M, Kp, nb, S_dev, accumulate, st);
+    if (precision == B2_F64) return launch_herk<double>(X_dev, M, Kp, nb, bin0, nbins, S_dev, accumulate, st);
+    if (precision == B2_F32) return launch_herk<float>(X_dev, M, Kp, nb, bin0, nbins, S_dev, accumulate, st);
     b2_set_error("b2_csm_herk: bad precision %d", precision);
     return B2_EINVAL;
 }

@@ -1025,15 +1025,9 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
                void *per_bin, cudaStream_t st) {
     using CF = TcCfg<NB, PASSES>;
     auto kern = das_map_tc_kernel<NB, PASSES>;
-    static bool attr_done = false;
-    static int num_sms = 0;
-    if (!attr_done) {
-        B2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
-        int dev = 0;
-        B2_CUDA_OK(cudaGetDevice(&dev));
-        B2_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
-    }
+    static DeviceOnce once;          // per instantiation and device
+    int num_sms = 0;
+    if (int rc = b2_device_once(once, kern, CF::SMEM, &num_sms)) return rc;
     const int64_t ntiles = (G + TILE_G - 1) / TILE_G;
     B2_REQUIRE(ntiles <= 0x7fffffff, B2_EINVAL, "b2_das_map: too many grid points");
     // Persistent grid, one CTA per SM.  The bins are split into nsplit ranges and a work unit is (bin range,
@@ -1053,11 +1047,8 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
         if (eff > best + 0.01) { best = eff; nsplit = sp; }
     }
     {
-        static double chunk_mb = -1.0;
-        if (chunk_mb < 0.0) {                              // B2_MAP_L2_CHUNK_MB: tuning knob (0 disables)
-            const char *e = getenv("B2_MAP_L2_CHUNK_MB");
-            chunk_mb = e ? atof(e) : 64.0;
-        }
+        const char *e = getenv("B2_MAP_L2_CHUNK_MB");      // tuning knob, read per launch (0 disables)
+        const double chunk_mb = e ? atof(e) : 64.0;
         if (chunk_mb > 0.0 && ntiles > cap) {              // more than one wave of tiles: reuse pays
             const double total_mb = double(images_bytes<PASSES>(M, nbins)) / 1048576.0;
             int by_l2 = int(total_mb / chunk_mb + 0.999);
@@ -1065,6 +1056,10 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
             if (by_l2 > most) by_l2 = most;
             if (by_l2 > nsplit) nsplit = by_l2;
         }
+    }
+    if (const char *e = getenv("B2_MAP_NSPLIT")) {         // test knob: force the number of bin ranges
+        const int forced = atoi(e);
+        if (forced >= 1) nsplit = forced < nbins ? forced : nbins;
     }
     const int64_t units = ntiles * nsplit;
     B2_REQUIRE(units <= 0x7fffffff, B2_EINVAL, "b2_das_map: too many work units (%lld tiles x %d bin ranges)",

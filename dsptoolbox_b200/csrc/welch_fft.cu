@@ -357,11 +357,8 @@ int launch_rfft(const void *xc, int64_t Lp, int M, int step, int64_t nframes, co
                 const void *tw, int detrend, double scale, void *X, int64_t Kp, cudaStream_t st) {
     using G = Geo<T, LOG2NC>;
     auto kern = welch_rfft_kernel<T, LOG2NC>;
-    static bool attr_done = false;   // per instantiation
-    if (!attr_done) {
-        B2_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
-        attr_done = true;
-    }
+    static DeviceOnce once;          // per instantiation and device
+    if (int rc = b2_device_once(once, kern, G::SMEM, nullptr)) return rc;
     B2_REQUIRE(Kp % G::FR == 0, B2_EINVAL, "b2_welch_rfft: Kp=%lld must be a multiple of %d", (long long)Kp, G::FR);
     int vec_ok = (step % 2 == 0) && (Lp % 2 == 0) && (reinterpret_cast<uintptr_t>(xc) % (2 * sizeof(T)) == 0) &&
                  (reinterpret_cast<uintptr_t>(window) % (2 * sizeof(T)) == 0);

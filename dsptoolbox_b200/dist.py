@@ -3,8 +3,9 @@ gloo in the CPU tests).
 
 Stage 1 -- Welch frames are sharded: rank r owns the contiguous frame range
 `frame_shard(K, r, R)`, reads only the samples those frames touch (a halo of wl - step samples
-overlaps the neighbour), accumulates the UN-normalised sums S_f^(r), and ONE all-reduce(sum)
-over NVLink gives every rank the full sum.  The non-linear finalisation (mean, scaling,
+overlaps the neighbour), accumulates the UN-normalised sums S_f^(r) as a PACKED lower triangle, and an
+all-reduce(sum) over NVLink -- issued per bin range so that it overlaps the rank-K update of the next range --
+gives every rank the full sum.  The non-linear finalisation (mean, scaling,
 element-wise sqrt, mirroring) runs after the reduction on every rank, so all ranks hold the
 full CSM for stage 2.
 Stage 2 -- grid points are sharded (`grid_shard`); the only communication is the final
@@ -19,6 +20,8 @@ from __future__ import annotations
 import numpy as np
 
 from .beamforming.beamforming import BeamformerDASFrequency
+from .classes.signal import Signal
+from .standard import _spectral_methods as _sm
 
 
 # --------------------------------------------------------------------------- index math
@@ -63,31 +66,26 @@ def world() -> tuple[int, int]:
 
 def allreduce_sum_(t):
     """In-place sum over ranks of a real or complex tensor (complex goes as interleaved reals)."""
-    import torch
-
-    dist = _dist()
-    if world()[1] == 1:
-        return t
-    dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t, op=dist.ReduceOp.SUM)
+    h = allreduce_sum_async_(t)
+    if h is not None:
+        h.wait()
     return t
 
 
-def allreduce_lower_triangle_(S):
-    """Sum over ranks of the frame sums S (nb, M, M) of which only the lower triangle (row >= col) is valid:
-    the M(M+1)/2 valid entries per bin are packed, reduced and scattered back, which halves the all-reduce
-    payload (1.08 instead of 2.15 GB at M = 256, nb = 2049).  The upper triangle is left untouched (the
-    finalisation kernel never reads it).  Opt-in via `engine.config.pack_allreduce` until measured on NVLink."""
+def allreduce_sum_async_(t):
+    """Start the in-place sum over ranks of `t` and return the work handle (None on a single rank).
+
+    This is the `reduce_fn` of `engine.csm_partial_sums`: it is called once per bin range of the PACKED
+    frame sums (the M(M+1)/2 valid entries per bin -- 1.08 GB instead of the 2.15 GB square at M = 256,
+    nb = 2049), right after the rank-K update of that range was enqueued.  NCCL orders the collective after
+    the work already on the current stream and runs it on its own stream, so the reduction of range i
+    overlaps the update of range i+1; `handle.wait()` makes the current stream wait for the result."""
     import torch
 
     dist = _dist()
     if world()[1] == 1:
-        return S
-    M = S.shape[-1]
-    rows, cols = torch.tril_indices(M, M, device=S.device)
-    packed = S[:, rows, cols].contiguous()
-    dist.all_reduce(torch.view_as_real(packed) if packed.is_complex() else packed, op=dist.ReduceOp.SUM)
-    S[:, rows, cols] = packed
-    return S
+        return None
+    return dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t, op=dist.ReduceOp.SUM, async_op=True)
 
 
 def allgather_rows(local, counts: list[int]):
@@ -106,6 +104,49 @@ def allgather_rows(local, counts: list[int]):
 
 
 # --------------------------------------------------------------------------- front-ends
+class ShardedSignal(Signal):
+    """A `Signal` of which this rank only holds the rows [row_offset, row_offset + len(rows)) -- the samples
+    its Welch frames touch (`frame_shard` + `shard_sample_range`) -- of a recording of `total_length` samples.
+    `rows` is a (samples, channels) numpy array (pinned or pageable) or torch tensor (host or device).
+    `length_samples` reports the whole recording, so the frame arithmetic is that of the unsharded signal;
+    `get_csm*` must be driven through `get_csm_device_sharded` / `DistributedBeamformerDASFrequency`."""
+
+    def __init__(self, rows, row_offset: int, total_length: int, sampling_rate_hz: int, activate_cache: bool = False):
+        assert len(rows.shape) == 2, "rows must have the shape (time samples, channels)"
+        assert 0 <= row_offset and row_offset + rows.shape[0] <= total_length, "rows outside the recording"
+        self.constrain_amplitude = False
+        self.activate_cache = activate_cache
+        self.sampling_rate_hz = sampling_rate_hz
+        self._time_data = rows
+        self.time_data_imaginary = None
+        self._amplitude_scale_factor = 1.0
+        self._row_offset, self._total_length = int(row_offset), int(total_length)
+        self._invalidate()
+        self.set_spectrum_parameters()
+        self.set_spectrogram_parameters()
+
+    @property
+    def number_of_channels(self) -> int:
+        return int(self._time_data.shape[1])
+
+    @property
+    def length_samples(self) -> int:
+        return self._total_length
+
+    def _compute_csm_device(self, frame_range=None, reduce_fn=None):
+        p = self._spectrum_parameters
+        rank, nranks = world()
+        if frame_range is None:
+            wl = p["window_length_samples"]
+            step = wl - int(p["overlap_percent"] / 100 * wl)
+            k_total = -(-self._total_length // step)
+            frame_range, reduce_fn = frame_shard(k_total, rank, nranks), allreduce_sum_async_
+        return _sm.csm_welch_device(self._time_data, self.sampling_rate_hz, p["window_length_samples"],
+                                    p["window_type"], p["overlap_percent"], p["detrend"], p["average"], p["scaling"],
+                                    frame_range=frame_range, reduce_fn=reduce_fn, total_length=self._total_length,
+                                    row_offset=self._row_offset)
+
+
 def get_csm_device_sharded(signal):
     """Frame-sharded `Signal.get_csm_device()`: every rank returns the full (f, csm)."""
     from . import engine
@@ -115,8 +156,7 @@ def get_csm_device_sharded(signal):
     wl = p["window_length_samples"]
     step = wl - int(p["overlap_percent"] / 100 * wl)
     k_total, _ = engine.welch_frames(signal.length_samples, wl, step)
-    reduce_fn = allreduce_lower_triangle_ if engine.config.pack_allreduce else allreduce_sum_
-    return signal._compute_csm_device(frame_range=frame_shard(k_total, rank, nranks), reduce_fn=reduce_fn)
+    return signal._compute_csm_device(frame_range=frame_shard(k_total, rank, nranks), reduce_fn=allreduce_sum_async_)
 
 
 class DistributedBeamformerDASFrequency(BeamformerDASFrequency):
@@ -145,6 +185,6 @@ def simulate_frame_sharding(n_frames: int, world_size: int) -> list[tuple[int, i
     return shards
 
 
-__all__ = ["split_range", "frame_shard", "grid_shard", "shard_sample_range", "allreduce_sum_",
-           "allreduce_lower_triangle_", "allgather_rows", "get_csm_device_sharded", "DistributedBeamformerDASFrequency",
-           "simulate_frame_sharding", "world", "np"]
+__all__ = ["split_range", "frame_shard", "grid_shard", "shard_sample_range", "allreduce_sum_", "allreduce_sum_async_",
+           "allgather_rows", "get_csm_device_sharded", "ShardedSignal", "DistributedBeamformerDASFrequency",
+           "simulate_frame_sharding", "world"]

@@ -32,8 +32,12 @@ class Config:
     map_mode: str = "auto"
     #: device spectra buffer budget in bytes; longer recordings are processed in frame chunks
     spectra_budget_bytes: int = 24 << 30
-    #: multi-GPU: all-reduce only the valid lower triangle of the frame sums (half the payload)
-    pack_allreduce: bool = False
+    #: multi-GPU: the packed frame sums are all-reduced in this many bin ranges, each reduction
+    #: overlapping the rank-K update of the next range (1 = one blocking all-reduce at the end)
+    reduce_ranges: int = 8
+    #: host recordings above this size are uploaded in frame chunks on a copy stream, so that the
+    #: upload of chunk i+1 overlaps K0/K1/K2 of chunk i (0 disables the chunking)
+    h2d_chunk_bytes: int = 768 << 20
     #: last-call statistics (kernel times are only filled when `profile` is on)
     profile: bool = False
     stats: dict = field(default_factory=dict)
@@ -70,7 +74,11 @@ def tc_map_available() -> bool:
 def resolve_map_mode(mode: str | None = None) -> int:
     mode = (mode or config.map_mode).lower()
     if mode == "auto":
-        return N.MAP_TC_F16X3 if tc_map_available() else N.MAP_SIMT_F32
+        if not tc_map_available():
+            # a library without the tcgen05 kernel is a broken build, not something to paper over with the
+            # 50x slower CUDA-core kernel (ask for "simt_f32" / "simt_f64" explicitly if that is what you want)
+            raise N.NativeError("libb2dsp.so was built without the tensor-core map kernel (das_map_tc.cu)")
+        return N.MAP_TC_F16X3
     if mode not in _MAP_MODES:
         raise ValueError(f"unknown map mode {mode!r}")
     return _MAP_MODES[mode]
@@ -153,21 +161,65 @@ class _Timer:
 
 
 # --------------------------------------------------------------------------- stage 1
+def packed_size(M: int) -> int:
+    """Entries of the packed lower triangle of an M x M Hermitian matrix: (j, i), j >= i, at j(j+1)/2 + i."""
+    return M * (M + 1) // 2
+
+
+def unpack_lower(S, M: int):
+    """(nb, M, M) complex128 tensor whose lower triangle holds the packed sums `S` (nb, M(M+1)/2); the strict
+    upper triangle is zero.  Debug / test helper -- the kernels consume the packed form directly."""
+    torch = _torch()
+    rows, cols = torch.tril_indices(M, M, device=S.device)          # row-major: index j(j+1)/2 + i
+    out = torch.zeros((S.shape[0], M, M), dtype=S.dtype, device=S.device)
+    out[:, rows, cols] = S
+    return out
+
+
+def _frame_chunks(k0: int, k1: int, tile: int, max_frames: int, host_bytes: int) -> list[tuple[int, int]]:
+    """Frame ranges processed one after the other: bounded by the spectra budget and, for host recordings,
+    small enough (config.h2d_chunk_bytes) that the upload of one range overlaps the kernels of the previous."""
+    n = k1 - k0
+    per = max_frames
+    if host_bytes > 0 and config.h2d_chunk_bytes > 0 and host_bytes > config.h2d_chunk_bytes:
+        parts = -(-host_bytes // config.h2d_chunk_bytes)
+        frames_per_part = -(-n // parts)
+        per = min(per, max(tile, -(-frames_per_part // tile) * tile))
+    out, kc = [], k0
+    while kc < k1:
+        kn = min(k1, kc + per)
+        out.append((kc, kn))
+        kc = kn
+    return out
+
+
 def csm_partial_sums(x, length: int, wl: int, step: int, window: np.ndarray, detrend: bool,
                      fft_scale: float, frame_range: tuple[int, int] | None = None,
-                     precision: str | None = None, device=None, row_offset: int = 0, diag_only: bool = False):
+                     precision: str | None = None, device=None, row_offset: int = 0, diag_only: bool = False,
+                     reduce_fn=None):
     """Un-normalised per-bin sums S_f = sum_k X_k X_k^H over the frames in `frame_range`.
 
-    Returns (S, n_frames_total): S is a complex128 CUDA tensor (nb, M, M) whose lower triangle
-    (row >= col) is valid.  Partial sums of disjoint frame ranges add up to the full sum, which
-    is what makes the stage frame-shardable.  `x` may hold only the rows
-    [row_offset, row_offset + x.shape[0]) of the recording of `length` samples (a rank's shard).
+    Returns (S, n_frames_total): S is a complex128 CUDA tensor (nb, M(M+1)/2) holding the PACKED lower
+    triangle (row >= col, see `packed_size` / `unpack_lower`).  Partial sums of disjoint frame ranges add up
+    to the full sum, which is what makes the stage frame-shardable.  `x` may hold only
+    the rows [row_offset, row_offset + x.shape[0]) of the recording of `length` samples (a rank's shard).
     With `diag_only` only the auto-spectra are accumulated: S is then float64 (nb, M).
+
+    `reduce_fn(t) -> handle | None` (dist.py) sums a slice of S over the ranks IN PLACE and may return an
+    object with `.wait()`: the bins are processed in `config.reduce_ranges` ranges and the reduction of one
+    range is started as soon as its rank-K update is enqueued, so it overlaps the update of the next range.
     """
     torch = _torch()
     lib = N.lib()
     prec = _PREC[(precision or config.csm_precision).lower()]
-    device = device or torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(device):
+        return _csm_partial_sums(torch, lib, prec, device, x, length, wl, step, window, detrend, fft_scale,
+                                 frame_range, row_offset, diag_only, reduce_fn)
+
+
+def _csm_partial_sums(torch, lib, prec, device, x, length, wl, step, window, detrend, fft_scale, frame_range,
+                      row_offset, diag_only, reduce_fn):
     M = int(x.shape[1])
     K_total, _ = welch_frames(length, wl, step)
     k0, k1 = frame_range if frame_range is not None else (0, K_total)
@@ -175,33 +227,59 @@ def csm_partial_sums(x, length: int, wl: int, step: int, window: np.ndarray, det
     nb = wl // 2 + 1
     rdt = torch.float64 if prec == N.F64 else torch.float32
     cdt = torch.complex128 if prec == N.F64 else torch.complex64
-    st = N.stream_handle()
+    cur = torch.cuda.current_stream()
+    st = cur.cuda_stream
     timer = _Timer()
 
     tile = N.check(lib.b2_welch_frame_tile(wl, prec), "b2_welch_frame_tile")
     tile = max(16, tile)
     bytes_per_frame = nb * M * (16 if prec == N.F64 else 8)
     max_frames = max(tile, (config.spectra_budget_bytes // bytes_per_frame) // tile * tile)
+    on_host = not (isinstance(x, torch.Tensor) and x.device.type == "cuda")
+    itemsize = x.element_size() if isinstance(x, torch.Tensor) else int(getattr(getattr(x, "dtype", None), "itemsize", 8))
+    host_bytes = (k1 - k0) * step * M * itemsize if on_host else 0
+    chunks = _frame_chunks(k0, k1, tile, max_frames, host_bytes)
 
     win = torch.from_numpy(np.ascontiguousarray(window, dtype=np.float64)).to(device).to(rdt)
     tw = _twiddles(wl, prec, device)
     S = (torch.empty((nb, M), dtype=torch.float64, device=device) if diag_only
-         else torch.empty((nb, M, M), dtype=torch.complex128, device=device))
-    first = True
+         else torch.empty((nb, packed_size(M)), dtype=torch.complex128, device=device))
     timer.mark("start")
-    kc = k0
     if k1 == k0:
         S.zero_()
-    while kc < k1:
-        kn = min(k1, kc + max_frames)
-        nfr = kn - kc
-        Kp = (nfr + tile - 1) // tile * tile
+
+    def rows_of(c):
+        kc, kn = c
         t0 = kc * step
         t1 = min(length, (kn - 1) * step + wl)           # samples beyond `length` are the zero padding
+        assert t0 >= row_offset and t1 - row_offset <= x.shape[0], "frame range reads samples outside this shard"
+        return t0, t1
+
+    # the upload of chunk i+1 is issued (on a copy stream) right after the kernels of chunk i were enqueued
+    copy_stream = torch.cuda.Stream(device=device) if (on_host and len(chunks) > 1) else None
+
+    def upload(c):
+        t0, t1 = rows_of(c)
+        if copy_stream is None:
+            return _as_device_block(x, t0 - row_offset, t1 - row_offset, device), None
+        with torch.cuda.stream(copy_stream):
+            blk = _as_device_block(x, t0 - row_offset, t1 - row_offset, device)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return blk, ev
+
+    pending = []                                         # handles of the overlapped reductions
+    nxt = upload(chunks[0]) if chunks else None
+    for ci, (kc, kn) in enumerate(chunks):
+        (xs, code, s_t, s_m), ev = nxt
+        if ev is not None:
+            cur.wait_event(ev)
+            xs.record_stream(cur)
+        nfr = kn - kc
+        Kp = (nfr + tile - 1) // tile * tile
+        t0, t1 = rows_of((kc, kn))
         Lp = (Kp - 1) * step + wl
         Lp += (-Lp) % 4
-        assert t0 >= row_offset and t1 - row_offset <= x.shape[0], "frame range reads samples outside this shard"
-        xs, code, s_t, s_m = _as_device_block(x, t0 - row_offset, t1 - row_offset, device)
         timer.mark("h2d")
         xc = torch.empty((M, Lp), dtype=rdt, device=device)
         N.check(lib.b2_prepare_channels(N.ptr(xs), code, s_t, s_m, 0, t1 - t0, M, N.ptr(xc), Lp, prec, st),
@@ -213,17 +291,32 @@ def csm_partial_sums(x, length: int, wl: int, step: int, window: np.ndarray, det
                                   float(fft_scale), N.ptr(X), Kp, prec, st), "b2_welch_rfft")
         _count()
         timer.mark("k1_rfft")
+        acc = 0 if ci == 0 else 1
+        last = ci == len(chunks) - 1
         if diag_only:
-            N.check(lib.b2_welch_autopower(N.ptr(X), M, Kp, nb, N.ptr(S), 0 if first else 1, prec, st), "b2_welch_autopower")
+            N.check(lib.b2_welch_autopower(N.ptr(X), M, Kp, nb, N.ptr(S), acc, prec, st), "b2_welch_autopower")
+            _count()
         else:
-            N.check(lib.b2_csm_herk(N.ptr(X), M, Kp, nb, N.ptr(S), 0 if first else 1, prec, st), "b2_csm_herk")
-        _count()
+            nr = max(1, min(int(config.reduce_ranges), nb)) if (reduce_fn is not None and last) else 1
+            for r in range(nr):
+                b0, b1 = nb * r // nr, nb * (r + 1) // nr
+                N.check(lib.b2_csm_herk(N.ptr(X), M, Kp, nb, b0, b1 - b0, N.ptr(S), acc, prec, st), "b2_csm_herk")
+                _count()
+                if reduce_fn is not None and last:
+                    pending.append(reduce_fn(S[b0:b1]))
         timer.mark("k2_herk")
-        first = False
-        kc = kn
+        if ci + 1 < len(chunks):
+            nxt = upload(chunks[ci + 1])
         del xs, xc, X
+    if reduce_fn is not None:
+        if not chunks or diag_only:
+            pending.append(reduce_fn(S))
+        for h in pending:
+            if h is not None:
+                h.wait()
+        timer.mark("allreduce_tail")
     config.stats["csm"] = dict(times_ms=timer.report(), frames=k1 - k0, frames_total=K_total, M=M, nb=nb,
-                               precision="fp64" if prec == N.F64 else "fp32")
+                               precision="fp64" if prec == N.F64 else "fp32", frame_chunks=len(chunks))
     return S, K_total
 
 
@@ -275,11 +368,13 @@ def frame_spectra(x, length: int, wl: int, step: int, window: np.ndarray, detren
     return out
 
 
-def csm_finalize(S, n_frames: int, factor: float, halve_edges: bool, amplitude_sqrt: bool):
-    """Average / scale / sqrt / mirror the summed spectra -> complex128 (nb, M, M) CUDA tensor."""
+def csm_finalize(S, M: int, n_frames: int, factor: float, halve_edges: bool, amplitude_sqrt: bool):
+    """Average / scale / sqrt / mirror the packed summed spectra (nb, M(M+1)/2) -> complex128 (nb, M, M)
+    CUDA tensor."""
     torch = _torch()
-    nb, M, _ = S.shape
-    out = torch.empty_like(S)
+    nb = S.shape[0]
+    assert S.shape[1] == packed_size(M), "packed sums do not match the channel count"
+    out = torch.empty((nb, M, M), dtype=torch.complex128, device=S.device)
     N.check(N.lib().b2_csm_finalize(N.ptr(S), M, nb, 1.0 / float(n_frames), float(factor), int(bool(halve_edges)),
                                     int(bool(amplitude_sqrt)), N.ptr(out), N.stream_handle()), "b2_csm_finalize")
     _count()
@@ -311,20 +406,40 @@ def das_prepare(csm_dev, bin0: int, nbins: int, remove_diag: bool, mode: int):
     return op
 
 
+_const_cache: dict = {}
+
+
+def _device_const(arr, device):
+    """float64 device copy of a SMALL host array (bin frequencies, Simpson weights, microphone positions),
+    cached by content so that repeated map calls do not re-upload them from pageable memory."""
+    torch = _torch()
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    if a.nbytes > (1 << 18):
+        return torch.from_numpy(a).to(device)
+    key = (a.shape, a.tobytes(), str(device))
+    t = _const_cache.get(key)
+    if t is None:
+        if len(_const_cache) >= 64:
+            _const_cache.pop(next(iter(_const_cache)))
+        t = _const_cache[key] = torch.from_numpy(a).to(device)
+    return t
+
+
 def das_map(op, M: int, freqs: np.ndarray, weights: np.ndarray, c: float, mic_xyz: np.ndarray,
             center_xyz: np.ndarray, grid_xyz, steering: int, clamp_negative: bool, mode: int,
             per_bin: bool = False):
     """Run K3 over all rows of `grid_xyz` ((G,3) numpy or CUDA float64 tensor).
 
-    Returns (map [G] float64 CUDA tensor, per-bin [G, F] tensor or None).
+    Returns (map [G] float64 CUDA tensor, per-bin [G, F] tensor or None).  `op` (from `das_prepare`) also
+    holds the kernel's per-CTA scratch tables: it must not be shared by two launches in flight at once.
     """
     torch = _torch()
     lib = N.lib()
     device = op.device
     nbins = len(freqs)
-    f_dev = torch.from_numpy(np.ascontiguousarray(freqs, dtype=np.float64)).to(device)
-    w_dev = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64)).to(device)
-    mic_dev = torch.from_numpy(np.ascontiguousarray(mic_xyz, dtype=np.float64)).to(device)
+    f_dev = _device_const(freqs, device)
+    w_dev = _device_const(weights, device)
+    mic_dev = _device_const(mic_xyz, device)
     if isinstance(grid_xyz, torch.Tensor):
         g_dev = grid_xyz.to(device=device, dtype=torch.float64).contiguous()
     else:
@@ -332,9 +447,12 @@ def das_map(op, M: int, freqs: np.ndarray, weights: np.ndarray, c: float, mic_xy
     G = g_dev.shape[0]
     out = torch.empty(G, dtype=torch.float64, device=device)
     pb = torch.empty((G, nbins), dtype=torch.float64, device=device) if per_bin else None
-    N.check(lib.b2_das_map(N.ptr(op), M, nbins, N.ptr(f_dev), N.ptr(w_dev), float(c), N.ptr(mic_dev),
-                           N.vec3(center_xyz), N.ptr(g_dev), G, steering, int(bool(clamp_negative)),
-                           N.ptr(out), N.ptr(pb), mode, N.stream_handle()), "b2_das_map")
+    if G == 0:                        # an empty grid shard (more ranks than grid points) contributes nothing
+        return out, pb
+    with torch.cuda.device(device):
+        N.check(lib.b2_das_map(N.ptr(op), M, nbins, N.ptr(f_dev), N.ptr(w_dev), float(c), N.ptr(mic_dev),
+                               N.vec3(center_xyz), N.ptr(g_dev), G, steering, int(bool(clamp_negative)),
+                               N.ptr(out), N.ptr(pb), mode, N.stream_handle()), "b2_das_map")
     _count()
     return out, pb
 

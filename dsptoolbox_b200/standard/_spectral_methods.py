@@ -68,17 +68,17 @@ def csm_welch_device(time_data, sampling_rate_hz, window_length_samples, window_
     recording of `total_length` samples.
     """
     _validate(window_length_samples, overlap_percent, average)
-    if not hasattr(time_data, "shape") or len(time_data.shape) != 2:
-        time_data = np.atleast_2d(np.asarray(time_data))
+    if not hasattr(time_data, "shape"):
+        time_data = np.asarray(time_data)
+    # the reference indexes time_data[:, channel] (_spectral_methods.py:351-356): anything but (time, channel) fails there
+    assert len(time_data.shape) == 2, "time data must have the shape (time samples, channels)"
     window, step = _window_and_step(window_type, window_length_samples, overlap_percent)
     fft_scale, factor, halve, amp = _scaling_terms(scaling, window_length_samples, sampling_rate_hz, window)
     S, n_frames = engine.csm_partial_sums(
         time_data, int(total_length if total_length is not None else time_data.shape[0]),
         window_length_samples, step, window, detrend, fft_scale, frame_range=frame_range,
-        row_offset=row_offset)
-    if reduce_fn is not None:
-        S = reduce_fn(S)
-    csm = engine.csm_finalize(S, n_frames, factor, halve, amp)
+        row_offset=row_offset, reduce_fn=reduce_fn)
+    csm = engine.csm_finalize(S, int(time_data.shape[1]), n_frames, factor, halve, amp)
     f = np.fft.rfftfreq(window_length_samples, 1 / sampling_rate_hz)
     return f, csm
 
@@ -159,8 +159,11 @@ def stft_device(time_data, fs_hz: int, window_length_samples: int, window_type, 
     if not check_COLA(window, nperseg=len(window), noverlap=overlap_samples):
         warn("Selected window type and overlap do not meet the constant overlap and add constraint! "
              "Results might be distorted")
-    if not hasattr(time_data, "shape") or len(time_data.shape) != 2:
-        time_data = np.atleast_2d(np.asarray(time_data))
+    if not hasattr(time_data, "shape"):
+        time_data = np.asarray(time_data)
+    if len(time_data.shape) == 1:          # one channel given flat: (time,) -> (time, 1)
+        time_data = time_data[:, None]
+    assert len(time_data.shape) == 2, "time data must have the shape (time samples, channels)"
     if padding:
         if isinstance(time_data, torch.Tensor):
             time_data = torch.nn.functional.pad(time_data, (0, 0, overlap_samples, overlap_samples))

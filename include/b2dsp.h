@@ -15,6 +15,9 @@
  *   - all *_dev pointers are DEVICE pointers on the current CUDA device; the library does no
  *     allocation and no synchronisation: kernels are enqueued on `stream` (a cudaStream_t
  *     passed as void*, 0 = default stream) and the caller owns every buffer.
+ *   - re-entrant across streams and devices: per-device kernel attributes are set up on the
+ *     first call on each device (keyed by cudaGetDevice()); the only shared state is the
+ *     thread-local error string.
  *   - precision: B2_F64 = strict (fp64 FFT, fp64 tensor-core DMMA accumulation);
  *                B2_F32 = fast   (fp32 FFT, fp32 spectra).
  *   - complex numbers are interleaved (re, im).
@@ -89,19 +92,22 @@ int b2_welch_rfft(const void *xc_dev, int64_t Lp, int M, int wl, int step, int64
                   const void *window_dev, const void *twiddle_dev, int detrend,
                   double fft_scale, void *X_out_dev, int64_t Kp, int precision, void *stream);
 
-/* K2: per-bin Hermitian rank-K accumulation S_f (+)= X_f X_f^H, lower block triangle.
+/* K2: per-bin Hermitian rank-K accumulation S_f (+)= X_f X_f^H of the bins [bin0, bin0 + nbins).
  * Replaces the M(M+1)/2 `_welch` calls of _csm_welch (_spectral_methods.py:351-369) and the
  * frame sum of np.mean (:152); the division by the frame count happens in b2_csm_finalize
- * so partial sums of frame shards can be all-reduced first.
+ * so partial sums of frame shards can be all-reduced first -- bin range by bin range, which is
+ * what lets the reduction of one range overlap the accumulation of the next.
  *   X_dev   spectra in the [Kp/16][nb][M][16] layout written by b2_welch_rfft
- *   S_dev   [nb][M][M] complex128 sums; entries with row >= col are valid on return
+ *   S_dev   PACKED lower triangle, [nb][M(M+1)/2] complex128: S_f[j][i] (j >= i) at
+ *           f*M(M+1)/2 + j(j+1)/2 + i.  The pointer is the base of the whole [nb] buffer.
  *   accumulate  0: overwrite, 1: add to the existing sums */
-int b2_csm_herk(const void *X_dev, int M, int64_t Kp, int nb, void *S_dev, int accumulate,
-                int precision, void *stream);
+int b2_csm_herk(const void *X_dev, int M, int64_t Kp, int nb, int bin0, int nbins, void *S_dev,
+                int accumulate, int precision, void *stream);
 
 /* K2e: averaging, physical scaling, DC/Nyquist halving, element-wise principal complex
  * sqrt, Hermitian mirroring.  Replaces _welch (_spectral_methods.py:152,164-171) and
- * _csm_welch (:355-369).  csm_out_dev: [nb][M][M] complex128, fully populated. */
+ * _csm_welch (:355-369).  S_dev: packed sums as above; csm_out_dev: [nb][M][M] complex128,
+ * fully populated. */
 int b2_csm_finalize(const void *S_dev, int M, int nb, double inv_frames, double factor,
                     int halve_edges, int amplitude_sqrt, void *csm_out_dev, void *stream);
 

@@ -4,9 +4,10 @@ TEST INFRASTRUCTURE ONLY (see oracle/restatement.py).  The reference imports sou
 sounddevice, matplotlib and seaborn at module scope (classes/signal.py:9-11,
 audio_io/audio_io.py:18, beamforming/_beamforming.py:6-7, plots/plots.py:5-9); none of the
 hot path's arithmetic lives there, so MagicMock stand-ins are enough.
-/root/reference only exists in the build container -- `available()` is False on the GPU box
-and everything that needs the real reference is skipped there (the committed golden
-vectors under tests/golden/ carry its outputs instead).
+/root/reference only exists in the build container.  `oracle/install_reference.py` installs the same
+unmodified package into baseline/_ref/ (git-ignored, but it travels with gpurun), so the GPU box can
+run the real reference too: the roots are tried in the order $B2DSP_REFERENCE_ROOT, /root/reference,
+<repo>/baseline/_ref.  The committed golden vectors under tests/golden/ carry its outputs as well.
 """
 
 from __future__ import annotations
@@ -15,7 +16,9 @@ import os
 import sys
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("B2DSP_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ROOTS = [r for r in (os.environ.get("B2DSP_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")) if r]
+REFERENCE_ROOT = next((r for r in _ROOTS if os.path.isdir(os.path.join(r, "dsptoolbox"))), _ROOTS[0])
 _STUBS = (
     "soundfile", "sounddevice", "seaborn", "matplotlib", "matplotlib.pyplot",
     "matplotlib.figure", "matplotlib.axes", "matplotlib.ticker", "matplotlib.colormaps",

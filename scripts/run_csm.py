@@ -14,6 +14,6 @@ from scipy.signal.windows import get_window
 w = get_window("hann", wl, fftbins=True)
 for _ in range(reps):
     S, K = engine.csm_partial_sums(x, L, wl, wl // 2, w, True, 1.0)
-    csm = engine.csm_finalize(S, K, 1.0, False, True)
+    csm = engine.csm_finalize(S, M, K, 1.0, False, True)
     torch.cuda.synchronize()
     print(engine.config.stats["csm"]["times_ms"])

@@ -65,14 +65,16 @@ def _worker(rank, world, port, x, wl, overlap, scaling, out):
         fr -= fr.mean(axis=0)
         X = np.fft.rfft(fr, axis=0, norm=R.fft_norm(scaling))               # (nb, k, M)
         S = torch.from_numpy(np.matmul(np.swapaxes(X, 1, 2), X.conj()))      # un-normalised partial sums
-        # the packed variant reduces only the valid lower triangle and must leave the rest alone
-        Sp = S.clone()
-        upper = torch.triu(torch.ones(M, M, dtype=torch.bool), 1)
-        Sp[:, upper] = 12345.0 + rank
-        Sp = bdist.allreduce_lower_triangle_(Sp)
+        # the product reduces the PACKED lower triangle bin range by bin range with asynchronous handles
+        # (engine.csm_partial_sums + dist.allreduce_sum_async_): same protocol here on the oracle's sums
+        rows, cols = torch.tril_indices(M, M)
+        Sp = S[:, rows, cols].contiguous()
+        nb = Sp.shape[0]
+        handles = [bdist.allreduce_sum_async_(Sp[nb * r // 3: nb * (r + 1) // 3]) for r in range(3)]
+        for h in handles:
+            h.wait()
         S = bdist.allreduce_sum_(S)
-        lower = ~upper
-        assert torch.equal(Sp[:, lower], S[:, lower]) and torch.all(Sp[:, upper] == 12345.0 + rank)
+        assert torch.equal(Sp, S[:, rows, cols])
         csm = R._finish_welch(S.numpy() / K, scaling, wl, 8000, w)           # non-linear part AFTER the reduce
         # grid sharding + all-gather of unequal pieces
         G = 37

@@ -136,17 +136,33 @@ def test_frame_chunking_and_sharding_are_exact_partitions():
     full, K = engine.csm_partial_sums(x, 20000, 256, 128, w, True, 1.0)
     parts = [engine.csm_partial_sums(x, 20000, 256, 128, w, True, 1.0, frame_range=r)[0]
              for r in ((0, 50), (50, 51), (51, K))]
+    assert full.shape == (129, engine.packed_size(9))       # packed lower triangle: (j, i), j >= i, at j(j+1)/2 + i
     tot = (parts[0] + parts[1] + parts[2]).cpu().numpy()
     fu = full.cpu().numpy()
+    assert np.max(np.abs(tot - fu)) <= 1e-12 * np.abs(fu).max()
+    # the packed layout against the oracle's un-normalised sums
+    Xo = R.channel_spectra(x, 256, "hann", 50, True, "fftbackward")                    # (nb, K, M)
+    So = np.matmul(np.swapaxes(Xo, 1, 2), Xo.conj())
+    un = engine.unpack_lower(full, 9).cpu().numpy()
     low = np.tril(np.ones((9, 9), bool))
-    assert np.max(np.abs(tot[:, low] - fu[:, low])) <= 1e-12 * np.abs(fu[:, low]).max()
+    assert np.max(np.abs(un[1:][:, low] - So[1:][:, low])) <= 1e-12 * np.abs(So).max()
+    assert np.all(un[:, ~low] == 0)
     old = engine.config.spectra_budget_bytes
     try:
         engine.config.spectra_budget_bytes = 129 * 9 * 16 * 40          # forces several chunks of 32 frames
         ch, _ = engine.csm_partial_sums(x, 20000, 256, 128, w, True, 1.0)
     finally:
         engine.config.spectra_budget_bytes = old
-    assert np.max(np.abs(ch.cpu().numpy()[:, low] - fu[:, low])) <= 1e-12 * np.abs(fu[:, low]).max()
+    assert np.max(np.abs(ch.cpu().numpy() - fu)) <= 1e-12 * np.abs(fu).max()
+    # host recordings are uploaded in frame chunks on a copy stream (overlapping the kernels): same sums
+    oldc = engine.config.h2d_chunk_bytes
+    try:
+        engine.config.h2d_chunk_bytes = 20000 * 9 * 8 // 5
+        hc, _ = engine.csm_partial_sums(x, 20000, 256, 128, w, True, 1.0)
+        assert engine.config.stats["csm"]["frame_chunks"] >= 4
+    finally:
+        engine.config.h2d_chunk_bytes = oldc
+    assert np.max(np.abs(hc.cpu().numpy() - fu)) <= 1e-12 * np.abs(fu).max()
 
 
 def test_fast_precision_mode():

@@ -213,6 +213,28 @@ def test_golden_mvdr_functional(golden_dir, mode, form):
         print(mode, form, tag, e1, e2)
 
 
+def test_per_bin_power_of_non_hermitian_matrices():
+    """The reference evaluates the FULL quadratic form Re(h^H A h) (beamforming.py:1199-1208, 1290-1300), which
+    only sees the Hermitian part of A; the map kernel reads the lower triangle.  Matrix functions of a
+    rank-deficient / ill-conditioned CSM (SVD with u != v on the null space, an inverse) come back visibly
+    non-Hermitian, so `_per_bin_power` symmetrises first: checked with arbitrary complex matrices."""
+    rng = np.random.default_rng(21)
+    M, F = 24, 5
+    pos = synth.disc_array(M, 0.4, seed=5)
+    mic = synth.positions_to_xyz(pos)
+    sig = dsp.Signal(None, rng.standard_normal((4000, M)), 16000)
+    g = rng.uniform(-0.4, 0.4, (300, 3)) * np.array([1, 1, 0]) + np.array([0, 0, 0.8])
+    grid = BF.Grid(dict(x=g[:, 0], y=g[:, 1], z=g[:, 2]))
+    bf = BF.BeamformerFunctional(sig, BF.MicArray(pos), grid, BF.SteeringVector())
+    A = rng.standard_normal((F, M, M)) + 1j * rng.standard_normal((F, M, M))         # no symmetry at all
+    fsel = np.array([1000.0, 1500.0, 2000.0, 2500.0, 3000.0])
+    h = R.steering_vector(fsel * 2 * np.pi / 343.0, g, mic, "truelocation")
+    want = R._quadratic_form(h, A)                                                    # (G, F)
+    for mode, tol in (("simt_f64", 1e-11), ("f16x3" if engine.tc_map_available() else "simt_f32", 1e-4)):
+        got = bf._per_bin_power(fsel, torch.from_numpy(A).cuda(), mode=mode).cpu().numpy()
+        assert np.max(np.abs(got - want)) <= tol * np.abs(want).max(), mode
+
+
 def test_golden_orthogonal(golden_dir):
     """BeamformerOrthogonal (reference beamforming.py:1010-1124) against golden maps of the real reference."""
     g = np.load(os.path.join(golden_dir, "das_small.npz"))

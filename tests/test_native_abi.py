@@ -47,7 +47,7 @@ def test_host_only_entry_points():
     with pytest.raises(NotImplementedError):
         _native.check(lib.b2_welch_frame_tile(1 << 17, _native.F32))
     # argument validation happens before any CUDA call
-    assert lib.b2_csm_herk(None, 4, 16, 3, None, 0, 0, None) == _native.E_INVAL
+    assert lib.b2_csm_herk(None, 4, 16, 3, 0, 3, None, 0, 0, None) == _native.E_INVAL
     with pytest.raises(AssertionError):
         _native.check(lib.b2_das_prepare(None, 4, 3, 0, 1, 1, None, 0, None))
     assert lib.b2_das_operand_bytes(64, 20, _native.MAP_SIMT_F32) == 20 * 64 * 64 * 8
