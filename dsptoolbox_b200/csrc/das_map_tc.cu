@@ -9,10 +9,10 @@
 //     T[g, n] = sum_{m >= n} conj(H[g, m]) L_f[m, n]            (L = 2*tril(C,-1) + diag(C))
 //
 // is a real GEMM  D[128 x 2NB] = A[128 x 2M] * B^T  with
-//     A[g, 2m+{0,1}]   = (Re, Im) of H[g, m] = a_gm exp(-i k_f r_gm)   synthesised by 4 warps
-//                        straight into the 128B-swizzled K-major shared-memory operand tile,
-//     B[2n,     2m+{0,1}] = ( Re L[m,n],  Im L[m,n])                    -> D[:, 2n]     = Re T
-//     B[2n + 1, 2m+{0,1}] = ( Im L[m,n], -Re L[m,n])                    -> D[:, 2n + 1] = Im T
+//     A[g, 2m+{0,1}]   = (Re, Im) of H[g, m] = a_gm exp(-i k_f r_gm)   synthesised straight into the
+//                        128B-swizzled K-major shared-memory operand tile,
+//     B[2n,     2m+{0,1}] = ( Re L[m,n],  Im L[m,n])                    -> D[:, 2n]     =  Re T
+//     B[2n + 1, 2m+{0,1}] = (-Im L[m,n],  Re L[m,n])                    -> D[:, 2n + 1] = -Im T
 // (operand images pre-swizzled by b2_das_prepare and streamed with cp.async.bulk), accumulated
 // in TMEM as fp32.  L is lower triangular: K chunks (16 microphones) entirely above the diagonal
 // are skipped, and a chunk that straddles it only touches its first w = 16, 32, ... columns, so
@@ -20,9 +20,33 @@
 // walked from the last one down, so that the first MMA of an accumulator (the one that overwrites
 // instead of accumulating) is the widest; two neighbouring column blocks share their A tiles
 // (walk_pair below).
-// The epilogue warps read D back with tcgen05.ld, re-synthesise H[g, n] and reduce
-//     P[g, f] = sum_n Re(T[g, n] H[g, n]),   clamp,   map[g] += w_f P[g, f]
-// while the next column block accumulates into the second TMEM buffer.
+//
+// There is NO separate epilogue role.  Columns [16 kc, 16 kc + 16) of T are final as soon as chunk kc
+// itself has been multiplied in (chunks are walked downwards, L is lower triangular), so the thread that
+// synthesised H[g, m] for the 16 microphones of chunk kc keeps those values in registers and, when the
+// tensor core has retired that chunk's own step (mbarrier `tdone`), reads (Re T, -Im T) of exactly those
+// microphones from TMEM with tcgen05.ld and accumulates
+//     P[g, f] = sum_n Re(T[g, n] H[g, n]),   then per bin: clamp,   map[g] += w_f P[g, f]
+// -- every steering element is synthesised once per bin instead of once for the operand and once more for
+// the reduction.
+//
+// Warp roles: NG groups of 4 synthesis+reduction warps (a group covers the 128 TMEM lanes; warp w owns lanes
+// 32 (w % 4) ...), 2 MMA issue warps (one per accumulator stream; the first also owns the TMEM allocation),
+// 1 operand loader warp.  The groups take the chunks ROUND-ROBIN: group j synthesises the whole tile of
+// chunks j, j + NG, ... (16 microphones per thread).  Every per-chunk hand-shake (ring slot wait, proxy
+// fence, barrier arrival, tdone wait, TMEM load) is a serial latency of the warp that executes it; with
+// every warp taking part in every chunk (the first two generations of this kernel) that latency, ~1400
+// cycles, WAS the chunk period -- whatever the number of warps or of microphones per thread.  Round-robin
+// groups give each warp NG chunk periods for it and 4x more arithmetic per hand-shake.
+// Pipelines: two shared-memory rings with full/empty mbarriers -- A (synthesis -> MMA) and B (loader -> MMA),
+// both released by tcgen05.commit --, one `tdone` mbarrier per A ring slot (MMA -> reduction of that chunk's
+// columns) and one `tempty` mbarrier per TMEM accumulator (all its columns read -> the next bin may overwrite
+// it).  The bin-independent part of the steering vector (the distance difference r0 - r_m of every (grid
+// point, microphone) pair of the tile) is computed once per work unit in fp64 and parked in an L2-resident
+// scratch table, so the per-bin work is one phase product, one sincos, one rcp and the operand split, in
+// packed fp32 arithmetic (FMUL2 / FADD2 / FFMA2) two microphones at a time.
+// scripts/sim_protocol.py models the barrier protocol.
+//
 // Split-TF32 (PASSES = 3): every operand is split x = hi + lo (both TF32-exact) and
 // hi*hi + lo*hi + hi*lo is accumulated, which restores ~fp32 accuracy.
 // Mixed mode (PASSES = 2): hi*hi stays a TF32 product, but the two correction products only need
@@ -30,22 +54,11 @@
 // the TF32 rate: the second operand image of a stage holds, per row, [bf16(x - hi) | bf16(x)] for
 // A and [bf16(y) | bf16(y - hi)] for B, so that sum_k A2[k] B2[k] = lo_A*y + x*lo_B.  Tensor work
 // drops from 3 to 2 TF32-equivalents per product at ~2^-20 relative accuracy.
-// FP16x3 mode (PASSES = 4): both operands are split into two FP16 halves x = f1 + f2 (22 significant
-// bits) and f1*g1 + f1*g2 + f2*g1 is accumulated as three kind::f16 products: 1.5 TF32-equivalents
-// of tensor work and -- what matters more, because the kernel is bound by shared-memory bandwidth
-// (every operand byte is written once and read once per product) -- operand rows of 128 B per 16
-// microphones instead of 256 B.  FP16's narrow exponent is handled by exact power-of-two scalings:
-// one per bin for L (max |L| -> [2^11, 2^12)) and one per grid point for the amplitude u(r), both
-// divided out of the finished power in fp64.
-//
-// Warp roles: 4*TPR steering-synthesis warps (TPR threads per grid point), 8 epilogue warps (two per
-// TMEM lane quadrant), 1 MMA issue + TMEM allocation warp, 1 operand loader warp.
-// Pipelines: two shared-memory rings with full/empty mbarriers -- A (synthesis -> MMA, 3+ stages) and
-// B (loader -> MMA, 2-3 stages), both released by tcgen05.commit -- and TMEM full/empty mbarriers
-// (MMA -> epilogue).  The bin-independent part of the steering vector
-// (distance r and amplitude a of every (grid point, microphone) pair of the tile) is computed
-// once per tile in fp64 and parked in an L2-resident scratch table, so the per-bin work is one
-// compensated phase product, one sincos and the TF32 split.
+// FP16x3 mode (PASSES = 4, the default): both operands are split into two FP16 halves x = f1 + f2 (22
+// significant bits) and f1*g1 + f1*g2 + f2*g1 is accumulated as three kind::f16 products: 1.5
+// TF32-equivalents of tensor work and operand rows of 128 B per 16 microphones instead of 256 B.  FP16's
+// narrow exponent is handled by exact power-of-two scalings: one per bin for L (max |L| -> [2^11, 2^12))
+// and one per grid point for the amplitude u(r), both divided out of the finished power in fp64.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -60,20 +73,21 @@ namespace {
 constexpr int TILE_G = 128;
 constexpr int KCH = 16;                       // microphones per K chunk = 32 reals = one 128 B row
 constexpr int A_TILE = TILE_G * 128;          // bytes of one A operand image
-#ifndef B2_TPR
-#define B2_TPR 2
+#ifndef B2_NG
+#define B2_NG 4
 #endif
-constexpr int TPR = B2_TPR;                   // synthesis threads per grid point (1, 2 or 4)
-constexpr int MPT = KCH / TPR;                // microphones of a chunk per synthesis thread
-constexpr int G4 = MPT / 4;                   // ... as groups of 4 (16 bytes of the distance table)
-constexpr int NGEN = TILE_G * TPR;            // synthesis threads
-constexpr int NEPI = 256;                     // epilogue threads
-constexpr int W_EPI0 = NGEN / 32;             // first epilogue warp
-constexpr int W_MMA = W_EPI0 + NEPI / 32;     // two MMA issue warps (one per accumulator stream); the loader warp follows
-constexpr int TC_THREADS = NGEN + NEPI + 96;
+static_assert(B2_NG >= 1 && B2_NG <= 4, "1..4 groups of 4 warps");
+
+#ifndef B2_ISSUE3
+#define B2_ISSUE3 0
+#endif
+// issue warp of a step: 1 = stream of block b1; the stream of block b0 is either all warp 0's, or (B2_ISSUE3) split
+// into warp 2 (the chunks shared with b1) and warp 0 (the triangle of b0)
+__device__ __forceinline__ int step_owner(int tgt, int kc, int kcB) { return tgt ? 1 : ((B2_ISSUE3 && kc >= kcB) ? 2 : 0); }
 
 constexpr int MAX_CTAS = 160;                 // scratch tables are sized for this many persistent CTAs
 constexpr int MAX_MICS = 1024;
+constexpr int PROG_MAX = 320;                 // chunk positions per bin (M = 1024, unpaired blocks: 64 + 56 + ... + 8 = 288)
 
 __host__ __device__ constexpr int tc_nb(int M) { return M <= 32 ? 32 : (M <= 64 ? 64 : 128); }
 
@@ -87,10 +101,12 @@ template <int NB, int PASSES> struct TcCfg {
     // chunk) and a deep ring is what lets them overlap instead of waiting for each other.
     static constexpr int A_STAGE = NSPLIT * A_TILE;
     static constexpr int B_STAGE = NSPLIT * B_TILE;
+    // B ring: the loader can only run NSB tiles ahead of the slowest issue warp, and a 32 KB tile needs ~1000
+    // cycles from L2 -- with 3 stages the issue warps waited ~360 cycles per step for B (role profile, r2).
 #ifdef B2_NSB
     static constexpr int NSB = B2_NSB;
 #else
-    static constexpr int NSB = B_STAGE >= 64 * 1024 ? 2 : 3;
+    static constexpr int NSB = B_STAGE >= 64 * 1024 ? 2 : 4;
 #endif
     static constexpr int NSA_RAW = (224 * 1024 - NSB * B_STAGE) / A_STAGE;
 #ifdef B2_NSA
@@ -106,73 +122,64 @@ template <int NB, int PASSES> struct TcCfg {
 #else
     static constexpr int GS = NSA - 2;
 #endif
+    // Synthesis/reduction warp groups (chunks are dealt round-robin).  Before a group synthesises chunk i it passes
+    // the chunks (i - 2 NG, i - NG] of the event stream, waiting on `tdone` of its own chunk i - NG and of any block's
+    // lowest chunk in that range.  mbarrier waits only see the PARITY of a phase, so the ring slot of a chunk it
+    // still has to wait for must not be able to complete a further use meanwhile: chunk c + NSA is only
+    // synthesised after chunk i when c + NSA > i, i.e. NSA >= 2 NG (scripts/sim_protocol.py checks the protocol).
+    static constexpr int NG = 2 * B2_NG <= NSA ? B2_NG : (NSA >= 4 ? NSA / 2 : 1);
+    static constexpr int NGEN = TILE_G * NG;                           // warp w owns TMEM lanes 32 (w % 4) ...
+    static constexpr int NS_WARPS = NGEN / 32;
+    static constexpr int W_MMA = NS_WARPS;            // three MMA issue warps (see the issue role); the loader warp follows
+    static constexpr int THREADS = NGEN + 128;
+    static constexpr int PARTIAL_ROWS = NG > 1 ? NG - 1 : 1;           // per-bin partial sums handed to the first group
     static constexpr int TMEM_COLS = 2 * UMMA_N;                       // two accumulator buffers
-    static constexpr int SMEM = 1024 /*align slack*/ + NSA * A_STAGE + NSB * B_STAGE + 2 * TILE_G * 4 + 256;
+    static constexpr int NBARS = 3 * NSA + 4 * NSB + 4;
+    static constexpr int SMEM = NSA * A_STAGE + NSB * B_STAGE + PARTIAL_ROWS * TILE_G * 4 + PROG_MAX * 2 + NBARS * 8 + 16;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 #ifdef B2_MAP_PROFILE
-// Debug instrumentation: cycles each role spends blocked on its barriers (CTA 0 only).
-// [0] synthesis wait empty  [1] synthesis total  [2] mma wait full  [3] mma wait tmem-empty  [4] mma total
-// [5] epilogue wait tmem-full  [6] epilogue total  [7] mma wait B ring full
-__device__ unsigned long long g_map_prof[8];
-#define PROF_T0() const long long _t0 = clock64()
-#define PROF_ADD(slot, cond) do { if (cond) atomicAdd(&g_map_prof[slot], (unsigned long long)(clock64() - _t0)); } while (0)
+// Debug instrumentation (variant build only): clock64 cycles CTA 0 spends per role and activity.
+//  issue warp w (0: b0 lower, 1: b1, 2: b0 upper), slots 8 w + { 0 total, 1 wait tempty / tinit, 2 wait fullB, 3 wait fullA,
+//                                                   4 issue + commits, 5 extra A releases, 6 steps }
+//  synthesis group 0 / warp 0: 24 + { 0 total, 1 wait tdone, 2 TMEM load + FMAs, 3 wait emptyA, 4 synthesis + stores, 5 fence + arrive,
+//                                     6 own chunks, 7 per-unit table }
+__device__ unsigned long long g_map_prof[32];
+#define PROF_DECL long long _pt = 0
+#define PROF_T0() _pt = clock64()
+#define PROF_ADD(slot, cond) do { if (cond) { const long long _n = clock64(); atomicAdd(&g_map_prof[slot], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
+#define PROF_CNT(slot, cond) do { if (cond) atomicAdd(&g_map_prof[slot], 1ull); } while (0)
 #else
+#define PROF_DECL
 #define PROF_T0()
 #define PROF_ADD(slot, cond)
-#endif
-
-#ifdef B2_MAP_TRACE
-// Debug: event trace of CTA 0 for the bins [B2_TRACE_BIN0, B2_TRACE_BIN0 + 2): {role, event, index, clock}
-#ifndef B2_TRACE_BIN0
-#define B2_TRACE_BIN0 20
-#endif
-__device__ long long g_trace[4 * 2 * 1024];     // [role][record]{(ev << 16) | idx, clock}
-#define TRACE(role, ev, idx, bin)                                                              \
-    do {                                                                                       \
-        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (bin) >= B2_TRACE_BIN0 && (bin) < B2_TRACE_BIN0 + 2 && trace_n < 1024) { \
-            g_trace[((role) * 1024 + trace_n) * 2] = ((long long)(ev) << 16) | (long long)(idx);                \
-            g_trace[((role) * 1024 + trace_n) * 2 + 1] = clock64();                            \
-            ++trace_n;                                                                         \
-        }                                                                                      \
-    } while (0)
-#else
-#define TRACE(role, ev, idx, bin)
-#endif
-
-#ifdef B2_DEBUG_HANG
-__device__ unsigned int g_abort, g_nhang, g_hang[256], g_snapped, g_snap[16];
-__device__ unsigned int g_prog[16];      // progress counters of CTA 0: [0] synth chunks [1] epilogue accumulators
-                                         // [2] issue warp 0 steps [3] issue warp 1 steps [4] loader tiles, [8+] = 100*role + stage
-#define DBG_PROG(slot, v) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_prog[slot] = (v); } while (0)
-#else
-#define DBG_PROG(slot, v)
+#define PROF_CNT(slot, cond)
 #endif
 
 // ---------------------------------------------------------------- PTX wrappers
+// barriers and tiles are addressed by their 32-bit shared-space addresses (computed once per thread: a
+// generic -> shared conversion in front of every barrier operation was 9 % of the executed instructions)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
 // Wait for the phase with the given parity.  try_wait suspends the thread in hardware until the
-// phase completes or the time hint expires, so waiting warps do not burn issue slots spinning
-// (the first version of this kernel spent ~20 % of its executed instructions in wait loops).
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-#ifdef B2_DEBUG_HANG
-    uint32_t spins = 0;
-    unsigned long long t_begin;
+// phase completes or the time hint expires, so waiting warps do not burn issue slots spinning.
+// Watchdog: a wait that lasts longer than ~4 s can only be a protocol bug; the kernel then traps (the launch
+// fails with an error) instead of hanging the GPU until somebody kills the process.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    unsigned long long t_begin, t_now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
-#endif
+    uint32_t done = 0, spins = 0;
     do {
         asm volatile(
             "{\n\t"
@@ -181,48 +188,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t"
             "}"
             : "=r"(done)
-            : "r"(addr), "r"(parity), "r"(0x989680u)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
-#ifdef B2_DEBUG_HANG
-        // debug build: a barrier that stays closed for ~1 s is recorded and every waiter gives up, so the
-        // kernel ends (with garbage results) and the host can print who was stuck where
-        if (!done && ((++spins & 63) == 0)) {
-            unsigned long long t_now;
+        if (!done && ((++spins & 15) == 0)) {
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-            const bool aborting = *(volatile unsigned int *)&g_abort != 0;
-            if (aborting && t_now - t_begin < 100000000ull) break;
-            if (aborting || t_now - t_begin > 500000000ull) {   // this one wait has lasted 0.5 s (0.1 s when aborting)
-                if ((threadIdx.x & 31) == 0) {
-                    const unsigned int k = atomicAdd(&g_nhang, 1u);
-                    if (k < 64) { g_hang[4 * k] = blockIdx.x; g_hang[4 * k + 1] = threadIdx.x >> 5; g_hang[4 * k + 2] = addr; g_hang[4 * k + 3] = parity; }
-                }
-                if (!aborting && (threadIdx.x & 31) == 0 && atomicCAS(&g_snapped, 0u, 1u) == 0u)
-                    for (int q = 0; q < 16; ++q) g_snap[q] = *(volatile unsigned int *)&g_prog[q];
-                __threadfence();
-                *(volatile unsigned int *)&g_abort = 1;
-                break;
-            }
+            if (t_now - t_begin > 4000000000ull) __trap();
         }
-#endif
     } while (!done);
 }
-// non-blocking probe of a phase
-__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
-    return done != 0;
+    if (!done) mbar_wait_slow(bar, parity);
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -230,8 +219,8 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
@@ -247,8 +236,8 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
@@ -339,12 +328,17 @@ __device__ __forceinline__ uint32_t pack_f16(__half2 v) { return *reinterpret_ca
 __device__ __forceinline__ void sts128u(uint32_t saddr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // byte offset of the 16-byte chunk j (0..7) of row r inside a 128B-swizzled K-major tile
 __host__ __device__ __forceinline__ int sw128_offset(int r, int j) { return (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4); }
 
 // ---------------------------------------------------------------- per-tile geometry table
-// tab[((m >> 2) * 128 + row) * 4 + (m & 3)] = d = |grid_row - mic_m| - |grid_row - array centre| (fp32 of an
-// fp64 result): the bin-independent part of the steering phase.  The amplitude follows from r = r0 + d.
+// tab[((m >> 2) * 128 + row) * 4 + (m & 3)] = dn = |grid_row - array centre| - |grid_row - mic_m| = r0 - r_m (fp32 of
+// an fp64 result): the bin-independent part of the steering phase, NEGATED so that the synthesis needs no sign
+// flip: with p = q dn, (cos 2 pi p, sin 2 pi p) = (Re, Im) of exp(-i 2 pi q (r_m - r0)).  The amplitude follows
+// from r_m = r0 - dn.
 __device__ __forceinline__ int tab_index(int m, int row) { return (((m >> 2) * TILE_G) + row) * 4 + (m & 3); }
 
 // The four formulations of beamforming.py:1515-1703 all have |h_m| = c_g * u(r_m) with ONE per-grid-point
@@ -355,83 +349,38 @@ __host__ __device__ inline int amp_kind(int steering) {
     return steering == B2_STEER_CLASSIC ? AMP_ONE : (steering == B2_STEER_INVERSE ? AMP_R : AMP_RINV);
 }
 
-// Fill r for the microphones with ((m >> 2) % TPR) == part of one grid point (if `write`); returns c_g^2
-// (0 for rows past the end of the grid).  Padded microphones get r = 1 (their operand columns are zero).
-// *amp_scale = the power of two s_g that brings u(r) of this grid point near 1 (FP16 operands).
-__device__ __forceinline__ double row_table(float *__restrict__ tab, int row, int part, bool write, int64_t g,
-                                            int64_t G, const double *__restrict__ grid,
-                                            const double *__restrict__ mic, int M, int Mk, double cx0, double cy0,
-                                            double cz0, int steering, float *amp_scale, float *r0_out) {
-    const bool valid = g < G;
-    double x = 0, y = 0, z = 0, c = 0.0;
-    float r0f = 1.0f;                     // fp32 distance grid point -> array centre (the reference's rt0)
-    *amp_scale = 1.0f;
-    if (valid) {
-        x = grid[3 * g]; y = grid[3 * g + 1]; z = grid[3 * g + 2];
-        double s = 0.0;
-        for (int m = 0; m < M; ++m) {
-            const double dx = x - mic[3 * m], dy = y - mic[3 * m + 1], dz = z - mic[3 * m + 2];
-            s += 1.0 / (dx * dx + dy * dy + dz * dz);
-        }
-        const double r0 = das_distance(x, y, z, cx0, cy0, cz0);
-        r0f = float(r0);
-        if (steering != B2_STEER_CLASSIC && r0 > 0.0 && r0 < 1e30) {
-            int e = ilogb(r0);                                     // r0 = 2^e * [1, 2)
-            e = e < -60 ? -60 : (e > 60 ? 60 : e);
-            *amp_scale = float(scalbn(1.0, steering == B2_STEER_INVERSE ? -e : e));
-        }
-        switch (steering) {
-        case B2_STEER_CLASSIC: c = 1.0 / double(M); break;
-        case B2_STEER_INVERSE: c = 1.0 / (double(M) * r0); break;
-        case B2_STEER_TRUE_POWER: c = 1.0 / (r0 * s); break;
-        default: c = 1.0 / sqrt(double(M) * s); break;
-        }
-    }
-    if (write) {
-        for (int m4 = part * 4; m4 < Mk; m4 += 4 * TPR) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int m = m4 + i;
-                // d = r_m - r0 (beamforming.py:1557 etc. use exactly this difference in the phase): bounded by the array
-                // aperture however far the grid point is, so the fp32 phase product q*d stays accurate; r_m itself
-                // (amplitude) is recovered as r0 + d.  Padding: d with r0 + d = 1.
-                double d = 1.0 - double(r0f);
-                if (valid && m < M) d = das_distance(x, y, z, mic[3 * m], mic[3 * m + 1], mic[3 * m + 2]) - double(r0f);
-                tab[tab_index(m, row)] = float(d);
-            }
-        }
-    }
-    *r0_out = r0f;
-    return c * c;
-}
-
-// h'[g, m] = u(r) exp(-i 2 pi q d), d = r - r0, q = f / c in cycles per metre: returns (Re, Im).  (The common
-// phase exp(+i 2 pi q r0) of a grid point cancels in h^H C h.)  The phase is reduced to a fraction of a cycle
-// before the MUFU sincos.  |q d| is at most a few tens of cycles (d is bounded by the array aperture), so the
-// fp32 product carries an absolute phase error of ~1e-5 rad per element; being uncorrelated over microphones
-// it changes the map by < 1e-6 of its maximum (first-order phase perturbations cancel at a coherent peak).
+// h'[g, m] = us u(r_m) exp(-i 2 pi q (r_m - r0)) for TWO microphones at once, in packed fp32 arithmetic:
+// dn = (r0 - r_A, r0 - r_B), q = f / c in cycles per metre; returns hr = (Re h'_A, Re h'_B), hi = (Im ..).  (The
+// common phase exp(+i 2 pi q r0) of a grid point cancels in h^H C h.)  The phase is reduced to a fraction of a
+// cycle before the MUFU sincos: |q dn| is at most a few hundred cycles (dn is bounded by the array aperture), so
+// the fp32 product carries an absolute phase error of ~1e-5 rad per element; being uncorrelated over
+// microphones it changes the map by < 1e-6 of its maximum.  (Feeding the unreduced phase to the MUFU instead
+// was measured: 1.2e-5 abs error at 32 cycles, 1e-4 at 256 -- scripts/probe_mufu.cu.)
+// The amplitude is u = 1 / rr (AMP_RINV) or rr (AMP_R) with rr = ak * dn + ac, where (ak, ac) fold the distance
+// r_m = r0 - dn and the power-of-two scale `us` of the FP16 operands: (-1/us, r0/us) resp. (-us, r0 us).
 template <int AMP>
-__device__ __forceinline__ float2 steer(float d, float q, float r0, float us = 1.0f) {
-    const float p = q * d;
-    const float r = r0 + d;
-    const float rn = (p + 12582912.0f) - 12582912.0f;         // round to nearest integer (|p| < 2^22)
-    const float fr = p - rn;
-    float sn, cs;
-    __sincosf(6.28318530717958647692f * fr, &sn, &cs);
-    if (AMP == AMP_ONE) return make_float2(cs, -sn);
-    float u = r;
-    if (AMP == AMP_RINV) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(r));
-    u *= us;                                                   // us = 1 except for the FP16 operands
-    return make_float2(u * cs, -u * sn);
+__device__ __forceinline__ void steer2(float2 dn, float q, float ak, float ac, float2 &hr, float2 &hi) {
+    const float2 p = __fmul2_rn(make_float2(q, q), dn);
+    const float2 big = make_float2(12582912.0f, 12582912.0f);            // 1.5 * 2^23: rounds to the nearest integer
+    const float2 rn = __fadd2_rn(__fadd2_rn(p, big), make_float2(-12582912.0f, -12582912.0f));
+    const float2 fr = __ffma2_rn(rn, make_float2(-1.0f, -1.0f), p);     // exact
+    const float2 a = __fmul2_rn(fr, make_float2(6.28318530717958647692f, 6.28318530717958647692f));
+    float2 sn, cs;
+    __sincosf(a.x, &sn.x, &cs.x);
+    __sincosf(a.y, &sn.y, &cs.y);
+    if (AMP == AMP_ONE) { hr = cs; hi = sn; return; }
+    float2 u = __ffma2_rn(dn, make_float2(ak, ak), make_float2(ac, ac));
+    if (AMP == AMP_RINV) {
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(u.x) : "f"(u.x));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(u.y) : "f"(u.y));
+    }
+    hr = __fmul2_rn(u, cs);
+    hi = __fmul2_rn(u, sn);
 }
 
 // top 11 significant bits by truncation: the residual x - trunc(x) is exact and is carried by the
 // correction operand, so no rounding step is needed in the split modes
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-
-__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 
 // ---------------------------------------------------------------- the kernel
 // Order of the tensor-core work of one bin for a PAIR of neighbouring column blocks (b0, b1 = b0 + 1).
@@ -440,8 +389,8 @@ __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
 // accumulators are fed as two skewed streams: step i multiplies chunk NKC-1-i into b1 (first use of its A
 // tile) and chunk NKC-1-(i-LAG) into b0 (last use, frees the tile).  So every steering tile is
 // synthesised ONCE per bin although both blocks need it, the tensor pipe sees a steady mix of both
-// streams, and the accumulator of b0 is not touched during the first LAG steps -- which is what gives the
-// epilogue time to drain it from the previous bin.  A lone block is the case kcB = NKC.
+// streams, and the accumulator of b0 is not touched during the first LAG steps.  A lone block is the case
+// kcB = NKC.
 //   fn(kc, target /*1: b1, 0: b0*/, first_use_of_A_tile, last_use_of_A_tile)
 template <class F>
 __device__ __forceinline__ void walk_pair(int NKC, int kcA, int kcB, int LAG, F &&fn) {
@@ -463,8 +412,15 @@ __device__ __forceinline__ void walk_pair(int NKC, int kcA, int kcB, int LAG, F 
     const int f_begin = int(int64_t(nbins) * upart / nsplit);                \
     const int f_end = int(int64_t(nbins) * (upart + 1) / nsplit);
 
+// The chunk positions of ONE bin -- the same for every bin -- as a small program in shared memory, so that the
+// synthesis warps do not re-derive the pair / block structure for every chunk:
+//   bits 0-5 kc | bit 6: the chunk's own columns belong to a block of this pair (reduce them here) |
+//   bits 7-9: accumulator of that block within the bin | bits 10-12: (first column of the chunk in its block) / 16 |
+//   bit 13: lowest chunk of its block (the accumulator has been read completely) | bit 14: last chunk of the bin
+constexpr uint32_t PG_RED = 1u << 6, PG_LASTBLK = 1u << 13, PG_ENDBIN = 1u << 14;
+
 template <int NB, int PASSES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TcCfg<NB, PASSES>::THREADS, 1)
 das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scratch,
                   const float *__restrict__ bin_scale, int M, int nbins,
                   const double *__restrict__ freqs, const double *__restrict__ weights, double inv_c,
@@ -472,19 +428,21 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                   const double *__restrict__ grid, int64_t G, int steering, int clamp_negative,
                   double *__restrict__ map_out, double *__restrict__ per_bin, int ntiles, int nsplit) {
     using CF = TcCfg<NB, PASSES>;
-    constexpr int UMMA_N = CF::UMMA_N, NSA = CF::NSA, NSB = CF::NSB;
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float *part = reinterpret_cast<float *>(smem + NSA * CF::A_STAGE + NSB * CF::B_STAGE);   // [2][128] epilogue partials
-    uint64_t *bars = reinterpret_cast<uint64_t *>(part + 2 * TILE_G);
-    uint64_t *fullA = bars, *emptyA = fullA + NSA, *fullB = emptyA + NSA, *emptyB = fullB + NSB;
-    uint64_t *tfull = emptyB + NSB, *tempty = tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    constexpr int UMMA_N = CF::UMMA_N, NSA = CF::NSA, NSB = CF::NSB, NG = CF::NG, NGEN = CF::NGEN;
+    constexpr int NS_WARPS = CF::NS_WARPS, W_MMA = CF::W_MMA, PARTIAL_ROWS = CF::PARTIAL_ROWS;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float *partial = reinterpret_cast<float *>(smem + NSA * CF::A_STAGE + NSB * CF::B_STAGE);   // [PARTIAL_ROWS][128]
+    uint16_t *prog = reinterpret_cast<uint16_t *>(partial + PARTIAL_ROWS * TILE_G);              // [PROG_MAX]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(prog + PROG_MAX);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + CF::NBARS);
+    // shared-space addresses of the barrier arrays (8 bytes per barrier)
+    const uint32_t smem_base = smem_u32(smem);
+    // fullB: one set of NSB barriers PER ISSUE WARP (tile k of warp w signals fullB + 8 (w NSB + k % NSB))
+    const uint32_t fullA = smem_u32(bars), emptyA = fullA + 8 * NSA, fullB = emptyA + 8 * NSA, emptyB = fullB + 8 * 3 * NSB;
+    const uint32_t tdone = emptyB + 8 * NSB, tempty = tdone + 8 * NSA, tinit = tempty + 16;
+    const uint32_t b_ring = smem_base + NSA * CF::A_STAGE;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-#ifdef B2_MAP_TRACE
-    int trace_n = 0;
-#endif
     const int NKC = (M + KCH - 1) / KCH;          // K chunks
     const int Mk = NKC * KCH;
     const int NBLK = (M + NB - 1) / NB;           // column blocks
@@ -497,260 +455,361 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
     auto pair_b0 = [&](int p) { return SHARE ? 2 * p : p; };
     auto pair_b1 = [&](int p) { return (SHARE && 2 * p + 1 < NBLK) ? 2 * p + 1 : -1; };
     auto first_chunk = [&](int blk) { return (blk * NB) / KCH; };          // first K chunk that reaches block blk
-
-    // A ring stage: [A_hi][A_corr?]; B ring stage: [B_hi][B_corr?]
-    auto a_tile = [&](int s, int split) { return smem + s * CF::A_STAGE + split * A_TILE; };
-    auto b_tile = [&](int s, int split) { return smem + NSA * CF::A_STAGE + s * CF::B_STAGE + split * CF::B_TILE; };
+    int cpb = 0;                                  // chunk positions per bin
+    for (int p = 0; p < NPAIR; ++p) cpb += NKC - first_chunk(pair_b0(p));
 
     if (tid == 0) {
-        for (int s = 0; s < NSA; ++s) { mbar_init(&fullA[s], NGEN / 32); mbar_init(&emptyA[s], 2); }   // both issue warps release
-        for (int s = 0; s < NSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 2); }         // both issue warps release
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEPI / 32); }
+        if (smem_base & 1023u) __trap();          // SWIZZLE_128B operand tiles need a 1024-byte aligned base
+        for (int s = 0; s < NSA; ++s) {
+            mbar_init(fullA + 8 * s, 4);          // one arrival per warp of the group that owns the chunk
+            mbar_init(emptyA + 8 * s, 3);         // every issue warp releases every tile
+            mbar_init(tdone + 8 * s, 1);          // committed once per chunk by the warp that issues its last relevant step
+        }
+        for (int s = 0; s < 3 * NSB; ++s) mbar_init(fullB + 8 * s, 1);
+        for (int s = 0; s < NSB; ++s) mbar_init(emptyB + 8 * s, 1);      // released by the step's issue warp
+        for (int b = 0; b < 2; ++b) { mbar_init(tempty + 8 * b, NS_WARPS); mbar_init(tinit + 8 * b, 1); }
         fence_barrier_init();
+        // the per-bin chunk program
+        int n = 0, accbase = 0;
+        for (int p = 0; p < NPAIR; ++p) {
+            const int b0 = pair_b0(p), b1 = pair_b1(p);
+            for (int kc = NKC - 1; kc >= first_chunk(b0); --kc, ++n) {
+                const int blk = (kc * KCH) / NB;
+                uint32_t e = uint32_t(kc);
+                if (blk == b0 || blk == b1) {
+                    const int accoff = accbase + ((blk == b1 || b1 < 0) ? 0 : 1);   // completion order: b1 (if any), then b0
+                    e |= PG_RED | (uint32_t(accoff) << 7) | (uint32_t((kc * KCH - blk * NB) / KCH) << 10);
+                    if (kc == first_chunk(blk)) e |= PG_LASTBLK;
+                }
+                prog[n] = uint16_t(e);
+            }
+            accbase += b1 >= 0 ? 2 : 1;
+        }
+        prog[n - 1] = uint16_t(prog[n - 1] | PG_ENDBIN);
     }
-    if (warp == W_MMA) tmem_alloc(tmem_slot, CF::TMEM_COLS);
+    if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), CF::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-#ifdef B2_MAP_PROFILE
-    const long long t_kernel0 = clock64();
-#endif
 
-    if (warp < W_EPI0) {
-        // =========================== steering synthesis -> A operand tiles ===========================
-        // TPR threads per grid point; each handles MPT = 16 / TPR microphones of every chunk as G4 groups of 4
-        const int r = tid & 127, part = tid >> 7;
-        const uint32_t a_base = smem_u32(smem);
-        // this thread's distances of chunk kc: G4 runs of 16 bytes, tab_index(kc * 16 + (part * G4 + gi) * 4, r)
-        const float *tabp = tab + (part * G4 * TILE_G + r) * 4;
-        uint32_t sa = 0, pha = 0;                            // A ring stage and its phase bit
+    if (warp < NS_WARPS) {
+        // =========================== steering synthesis -> A operand tiles, and the reduction of T ===========================
+        const int r = tid & 127, grp = tid >> 7, quad = warp & 3;
+        const uint32_t lane_base = uint32_t(quad * 32) << 16;
+        const uint32_t row_off = uint32_t((r >> 3) * 1024 + (r & 7) * 128);     // this row inside a swizzled tile
+        const uint32_t rx = uint32_t(r & 7);
+        const float *tabr = tab + r * 4;
+        uint32_t seq_base = 0;                               // ring sequence number of the unit's first chunk
+        uint32_t accs = 0;                                   // accumulators handed out before the event cursor's bin
+        PROF_DECL;
+        const bool prof = blockIdx.x == 0 && tid == 0;
+        (void)prof;
+#ifdef B2_MAP_PROFILE
+        const long long t_role0 = clock64();
+#endif
+        if (NG > 1 && grp == 0) asm volatile("bar.arrive %0, %1;" ::"r"(2 + quad), "n"(32 * NG) : "memory");   // hand-off slots start free
         for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
             B2_UNIT_DECODE
-            // the epilogue warps are done with the previous tile's table before it is overwritten
-            asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");
-            float us;                                     // power-of-two amplitude scale of this grid point
-            float r0f;                                    // distance of this grid point to the array centre
-            row_table(tab, r, part, true, int64_t(tile) * TILE_G + r, G, grid, mic, M, Mk, cx0, cy0, cz0, steering, &us, &r0f);
-            if (PASSES != 4) us = 1.0f;
-            __threadfence_block();
-            asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");
-            // Distances are prefetched TWO chunks ahead and the load is issued right after the arrive: the
-            // proxy fence in front of the arrive is a MEMBAR that waits for every outstanding load of the
-            // thread, so a load issued one chunk ahead would expose its whole L2 latency there.
-            // Two register buffers alternate (the chunk loop is flat and unrolled by two); rotating one
-            // buffer into the other would make the compiler wait for the newest load at the top of the body.
-            float4 r_a[G4], r_b[G4];
-            // cursor of the next chunk to prefetch: every pair walks kc = NKC-1 ... first chunk of its block b0
-            int pf_p = 0, pf_kc = NKC - 1;
-            auto prefetch = [&](float4 *dst) {
-#pragma unroll
-                for (int gi = 0; gi < G4; ++gi)
-                    dst[gi] = __ldcg(reinterpret_cast<const float4 *>(tabp + (pf_kc * 4 + gi) * (TILE_G * 4)));
-                if (pf_kc == first_chunk(pair_b0(pf_p))) { pf_kc = NKC - 1; if (++pf_p == NPAIR) pf_p = 0; }
-                else --pf_kc;
-            };
-            prefetch(r_a);
-            prefetch(r_b);
-            int chunks_per_bin = 0;
-            for (int p = 0; p < NPAIR; ++p) chunks_per_bin += NKC - first_chunk(pair_b0(p));
-            const int total = (f_end - f_begin) * chunks_per_bin;
-            int fi = f_begin, cib = 0;                       // bin of the current chunk, its index inside the bin
-            float bf = float(freqs[fi] * inv_c);
-            // one chunk: synthesise MPT microphones of this row, wait for the ring slot, store, signal
-            auto chunk_body = [&](float4 (&r_cur)[G4]) {
-                // probe the ring slot now so that the barrier round trip overlaps the arithmetic
-                const bool slot_free = mbar_test(&emptyA[sa], pha ^ 1);
-                if (warp == 0) TRACE(0, 0, cib, fi - f_begin);
-                float rr[MPT];
-#pragma unroll
-                for (int gi = 0; gi < G4; ++gi) {
-                    rr[4 * gi] = r_cur[gi].x; rr[4 * gi + 1] = r_cur[gi].y;
-                    rr[4 * gi + 2] = r_cur[gi].z; rr[4 * gi + 3] = r_cur[gi].w;
+            const int64_t g = int64_t(tile) * TILE_G + r;
+            PROF_T0();
+            // ---- per-unit geometry: this thread's share of the row's distances, amplitude constants of the row ----
+            float ak = 0.0f, ac = 1.0f;                      // amplitude argument rr = ak * dn + ac
+            double c2 = 0.0;
+            {
+                double s_part = 0.0, r0 = 1.0;
+                const bool valid = g < G;
+                double x = 0, y = 0, z = 0;
+                if (valid) {
+                    x = grid[3 * g]; y = grid[3 * g + 1]; z = grid[3 * g + 2];
+                    r0 = das_distance(x, y, z, cx0, cy0, cz0);
                 }
-                float4 hi4[MPT / 2], lo4[MPT / 2];   // TF32 images: 2 microphones per 16 bytes
-                uint4 img1[G4], img2[G4];            // 16-bit images: 4 microphones per 16 bytes
+                const float r0f = float(r0);
+                // every thread is done with the previous unit: its table (read by all groups) and the A ring (used as
+                // scratch below; this thread has passed every chunk of that unit, hence all its MMAs have retired)
+                asm volatile("bar.sync 1, %0;" ::"n"(NGEN) : "memory");
+                for (int m4 = grp * 4; m4 < Mk; m4 += 4 * NG) {
+                    float4 dn4;
+                    float *dnp = reinterpret_cast<float *>(&dn4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int m = m4 + i;
+                        // dn = r0 - r_m (beamforming.py:1557 etc. use exactly this difference in the phase): bounded by
+                        // the array aperture however far the grid point is, so the fp32 phase product q*dn stays accurate;
+                        // r_m itself (amplitude) is recovered as r0 - dn.  Padding: dn with r0 - dn = 1.
+                        double dn = double(r0f) - 1.0;
+                        if (valid && m < M) {
+                            const double rm = das_distance(x, y, z, mic[3 * m], mic[3 * m + 1], mic[3 * m + 2]);
+                            dn = double(r0f) - rm;
+                            s_part += 1.0 / (rm * rm);
+                        }
+                        dnp[i] = float(dn);
+                    }
+                    *reinterpret_cast<float4 *>(tab + tab_index(m4, r)) = dn4;
+                }
+                // s = sum_m 1 / r_m^2 over ALL microphones: the NG threads of a row add their shares through shared
+                // memory (the free A ring).  The barrier also orders the table writes before the other groups' reads.
+                double s = s_part;
+                double *sp = reinterpret_cast<double *>(smem);
+                if (NG > 1) sp[grp * TILE_G + r] = s_part;
+                __threadfence_block();
+                asm volatile("bar.sync 1, %0;" ::"n"(NGEN) : "memory");
+                if (NG > 1) {
+                    s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NG; ++k) s += sp[k * TILE_G + r];
+                    asm volatile("bar.sync 1, %0;" ::"n"(NGEN) : "memory");      // read before the first tile overwrites it
+                }
+                if (valid) {
+                    double c = 0.0, us = 1.0;
+                    switch (steering) {
+                    case B2_STEER_CLASSIC: c = 1.0 / double(M); break;
+                    case B2_STEER_INVERSE: c = 1.0 / (double(M) * r0); break;
+                    case B2_STEER_TRUE_POWER: c = 1.0 / (r0 * s); break;
+                    default: c = 1.0 / sqrt(double(M) * s); break;
+                    }
+                    c2 = c * c;
+                    if (PASSES == 4 && steering != B2_STEER_CLASSIC && r0 > 0.0 && r0 < 1e30) {
+                        // power of two that brings u(r) of this grid point near 1 (FP16 operands); both the operand
+                        // and the kept h' carry it, so the finished power is divided by its square
+                        int e = ilogb(r0);                                     // r0 = 2^e * [1, 2)
+                        e = e < -60 ? -60 : (e > 60 ? 60 : e);
+                        us = scalbn(1.0, steering == B2_STEER_INVERSE ? -e : e);
+                        c2 /= us * us;
+                    }
+                    if (akind == AMP_RINV) { ak = float(-1.0 / us); ac = float(double(r0f) / us); }     // rr = r_m / us, u = 1 / rr
+                    else if (akind == AMP_R) { ak = float(-us); ac = float(double(r0f) * us); }         // rr = r_m us,   u = rr
+                }
+            }
+            const int total = (f_end - f_begin) * cpb;
+            PROF_ADD(24 + 7, prof);
+            // ---- cursors ----
+            // synthesis: own chunks i = grp, grp + NG, ... of the unit; (s_fi, s_cib) = bin and position inside the bin
+            int s_cib = grp, s_fi = f_begin;
+            while (s_cib >= cpb) { s_cib -= cpb; ++s_fi; }
+            uint32_t s_slot = (seq_base + uint32_t(grp)) % NSA, s_ph = ((seq_base + uint32_t(grp)) / NSA) & 1;
+            // events / reduction: every chunk of the unit in order
+            int e_idx = 0, e_cib = 0, e_fi = f_begin, e_mod = 0;
+            uint32_t e_slot = seq_base % NSA, e_ph = (seq_base / NSA) & 1;
+            float bf = s_fi < f_end ? float(freqs[s_fi] * inv_c) : 0.0f;
+            float2 hk[KCH];                                   // h' of the own chunk synthesised last: (Re, Im) per microphone
+            float2 pacc = make_float2(0.f, 0.f);              // sum of Re T Re h' / of (-Im T) Im h', current bin
+            double acc_map = 0.0;
+
+            // distances of the next own chunk (4 x 16 bytes), fetched one own-chunk ahead
+            float4 dnext[4];
+            auto prefetch = [&](int cib) {
+                const int kc = int(prog[cib] & 0x3Fu);
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi)
+                    dnext[gi] = __ldcg(reinterpret_cast<const float4 *>(tabr + (kc * 4 + gi) * (TILE_G * 4)));
+            };
+            if (grp < total) prefetch(s_cib);
+
+            // one chunk of the event stream: reduce it if it is ours, then the per-chunk events
+            auto pass_chunk = [&]() {
+                const uint32_t e = prog[e_cib];
+                const uint32_t buf = (accs + ((e >> 7) & 7u)) & 1u;
+                if (e_mod == grp && (e & PG_RED)) {
+                    PROF_T0();
+                    mbar_wait(tdone + 8 * e_slot, e_ph);
+                    PROF_ADD(24 + 1, prof);
+                    tc_fence_after();
+                    const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N + 32u * ((e >> 10) & 7u);
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        float t[16];                         // (Re T, -Im T) of 8 microphones
+                        tmem_ld16(tcol + 16 * hlf, t);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)          // padded microphones have all-zero operand rows: T = 0, no bounds test
+                            pacc = __ffma2_rn(make_float2(t[2 * j], t[2 * j + 1]), hk[8 * hlf + j], pacc);
+                    }
+                    PROF_ADD(24 + 2, prof);
+                }
+                if (e & PG_LASTBLK) {                        // this warp has read all its columns of the accumulator
+                    // A group that does not own this chunk still waits until the accumulator is COMPLETE before it
+                    // declares it read: otherwise, when a bin has fewer chunks than a few groups' strides, its arrival
+                    // for the NEXT use of the TMEM buffer could be counted for this one (scripts/sim_protocol.py).
+                    if (e_mod != grp) mbar_wait(tdone + 8 * e_slot, e_ph);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty + 8 * buf);
+                }
+                if (e & PG_ENDBIN) {
+                    // end of the bin: combine the NG threads of the row, finish P[g, f] in fp64
+                    const float ptot = pacc.x + pacc.y;
+                    pacc = make_float2(0.f, 0.f);
+                    double extra = 0.0;
+                    if (NG > 1) {
+                        // hand-off through shared memory inside the quadrant's NG warps, two named barriers per quadrant:
+                        // "slots free" (2 + quad: the reader arrives, the writers wait) and "slots full" (6 + quad)
+                        if (grp > 0) {
+                            asm volatile("bar.sync %0, %1;" ::"r"(2 + quad), "n"(32 * NG) : "memory");
+                            partial[(grp - 1) * TILE_G + r] = ptot;
+                            __threadfence_block();
+                            asm volatile("bar.arrive %0, %1;" ::"r"(6 + quad), "n"(32 * NG) : "memory");
+                        } else {
+                            asm volatile("bar.sync %0, %1;" ::"r"(6 + quad), "n"(32 * NG) : "memory");
+#pragma unroll
+                            for (int k = 0; k < NG - 1; ++k) extra += double(partial[k * TILE_G + r]);
+                            asm volatile("bar.arrive %0, %1;" ::"r"(2 + quad), "n"(32 * NG) : "memory");
+                        }
+                    }
+                    if (grp == 0) {
+                        double p = (double(ptot) + extra) * c2;                            // |h|^2 scale of this grid point
+                        if (PASSES == 4) p /= double(bin_scale[e_fi]);                     // power-of-two scale of L_f
+                        if (clamp_negative && p < 0.0) p = 0.0;                            // beamforming.py:871-872
+                        acc_map += weights[e_fi] * p;                                      // :875-876
+                        if (per_bin != nullptr && g < G) per_bin[g * nbins + e_fi] = p;
+                    }
+                    ++e_fi;
+                    e_cib = -1;
+                    accs += uint32_t(NBLK);
+                }
+                ++e_cib; ++e_idx;
+                if (++e_mod == NG) e_mod = 0;
+                if (++e_slot == NSA) { e_slot = 0; e_ph ^= 1; }
+            };
+
+            // synthesis of the own chunk at (s_fi, s_cib): 16 microphones of this row -> A tile + hk
+            auto synth_chunk = [&]() {
+                float2 dn[KCH / 2];
+#pragma unroll
+                for (int gi = 0; gi < 4; ++gi) {
+                    dn[2 * gi] = make_float2(dnext[gi].x, dnext[gi].y);
+                    dn[2 * gi + 1] = make_float2(dnext[gi].z, dnext[gi].w);
+                }
+                // the next own chunk: position, bin, distances (the loads have a whole chunk to land)
+                int n_cib = s_cib + NG, n_fi = s_fi;
+                while (n_cib >= cpb) { n_cib -= cpb; ++n_fi; }
+                if (n_fi < f_end) prefetch(n_cib);
+                PROF_T0();
+                mbar_wait(emptyA + 8 * s_slot, s_ph ^ 1);
+                PROF_ADD(24 + 3, prof);
+                const uint32_t ahi = smem_base + s_slot * CF::A_STAGE + row_off;
+                const uint32_t alo = ahi + (CF::NSPLIT - 1) * A_TILE;
                 auto synth = [&](auto amp_tag) {
                     constexpr int AMP = decltype(amp_tag)::value;
 #pragma unroll
-                    for (int j = 0; j < MPT / 2; ++j) {
-                        const float2 h0 = steer<AMP>(rr[2 * j], bf, r0f, us);
-                        const float2 h1 = steer<AMP>(rr[2 * j + 1], bf, r0f, us);
-                        uint32_t *p1 = reinterpret_cast<uint32_t *>(&img1[j >> 1]) + 2 * (j & 1);
-                        uint32_t *p2 = reinterpret_cast<uint32_t *>(&img2[j >> 1]) + 2 * (j & 1);
-                        if (PASSES == 4) {           // img1 = first FP16 halves, img2 = second halves
-                            const __half2 a1 = __floats2half2_rn(h0.x, h0.y), b1 = __floats2half2_rn(h1.x, h1.y);
-                            const float2 af = __half22float2(a1), bfl = __half22float2(b1);
-                            p1[0] = pack_f16(a1);
-                            p1[1] = pack_f16(b1);
-                            p2[0] = pack_f16(__floats2half2_rn(h0.x - af.x, h0.y - af.y));
-                            p2[1] = pack_f16(__floats2half2_rn(h1.x - bfl.x, h1.y - bfl.y));
-                            continue;
-                        }
-                        if (PASSES == 1) hi4[j] = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
-                        else hi4[j] = make_float4(trunc_tf32(h0.x), trunc_tf32(h0.y), trunc_tf32(h1.x), trunc_tf32(h1.y));
-                        if (PASSES == 3)   // residuals are exact in fp32; the tensor core keeps their top 11 bits
-                            lo4[j] = make_float4(h0.x - hi4[j].x, h0.y - hi4[j].y, h1.x - hi4[j].z, h1.y - hi4[j].w);
-                        if (PASSES == 2) {           // img1 = bf16 residuals, img2 = bf16 values
-                            p1[0] = pack_bf16(h0.x - hi4[j].x, h0.y - hi4[j].y);
-                            p1[1] = pack_bf16(h1.x - hi4[j].z, h1.y - hi4[j].w);
-                            p2[0] = pack_bf16(h0.x, h0.y);
-                            p2[1] = pack_bf16(h1.x, h1.y);
+                    for (int gi = 0; gi < 4; ++gi) {           // 4 microphones = 16 bytes of each 16-bit image
+                        float2 hr0, hi0, hr1, hi1;
+                        steer2<AMP>(dn[2 * gi], bf, ak, ac, hr0, hi0);
+                        steer2<AMP>(dn[2 * gi + 1], bf, ak, ac, hr1, hi1);
+                        const float2 h[4] = {make_float2(hr0.x, hi0.x), make_float2(hr0.y, hi0.y),
+                                             make_float2(hr1.x, hi1.x), make_float2(hr1.y, hi1.y)};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) hk[4 * gi + j] = h[j];
+                        if (PASSES == 4) {           // row = [first FP16 halves of the 16 mics | second halves]
+                            uint4 f1, f2;
+                            uint32_t *q1 = reinterpret_cast<uint32_t *>(&f1), *q2 = reinterpret_cast<uint32_t *>(&f2);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const __half2 a1 = __floats2half2_rn(h[j].x, h[j].y);
+                                const float2 af = __half22float2(a1);
+                                const float2 res = __ffma2_rn(af, make_float2(-1.0f, -1.0f), h[j]);      // exact residual
+                                q1[j] = pack_f16(a1);
+                                q2[j] = pack_f16(__floats2half2_rn(res.x, res.y));
+                            }
+                            sts128u(ahi + ((uint32_t(gi) ^ rx) << 4), f1);
+                            sts128u(ahi + ((uint32_t(4 + gi) ^ rx) << 4), f2);
+                        } else {
+                            // TF32 image: 2 microphones per 16 bytes
+                            float4 hi4[2], lo4[2];
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const float2 h0 = h[2 * j], h1 = h[2 * j + 1];
+                                if (PASSES == 1) hi4[j] = make_float4(to_tf32(h0.x), to_tf32(h0.y), to_tf32(h1.x), to_tf32(h1.y));
+                                else hi4[j] = make_float4(trunc_tf32(h0.x), trunc_tf32(h0.y), trunc_tf32(h1.x), trunc_tf32(h1.y));
+                                lo4[j] = make_float4(h0.x - hi4[j].x, h0.y - hi4[j].y, h1.x - hi4[j].z, h1.y - hi4[j].w);
+                                sts128(ahi + ((uint32_t(2 * gi + j) ^ rx) << 4), hi4[j]);
+                                // residuals are exact in fp32; the tensor core keeps their top 11 bits
+                                if (PASSES == 3) sts128(alo + ((uint32_t(2 * gi + j) ^ rx) << 4), lo4[j]);
+                            }
+                            if (PASSES == 2) {
+                                // 16-bit correction image row = [bf16 residuals of the 16 mics | bf16 values]
+                                uint4 i1, i2;
+                                i1.x = pack_bf16(lo4[0].x, lo4[0].y); i1.y = pack_bf16(lo4[0].z, lo4[0].w);
+                                i1.z = pack_bf16(lo4[1].x, lo4[1].y); i1.w = pack_bf16(lo4[1].z, lo4[1].w);
+                                i2.x = pack_bf16(h[0].x, h[0].y); i2.y = pack_bf16(h[1].x, h[1].y);
+                                i2.z = pack_bf16(h[2].x, h[2].y); i2.w = pack_bf16(h[3].x, h[3].y);
+                                sts128u(alo + ((uint32_t(gi) ^ rx) << 4), i1);
+                                sts128u(alo + ((uint32_t(4 + gi) ^ rx) << 4), i2);
+                            }
                         }
                     }
                 };
                 if (akind == AMP_RINV) synth(std::integral_constant<int, AMP_RINV>{});
                 else if (akind == AMP_R) synth(std::integral_constant<int, AMP_R>{});
                 else synth(std::integral_constant<int, AMP_ONE>{});
-                if (!slot_free) { PROF_T0(); mbar_wait(&emptyA[sa], pha ^ 1); PROF_ADD(0, blockIdx.x == 0 && tid == 0); }
-                if (warp == 0) TRACE(0, slot_free ? 1 : 2, cib, fi - f_begin);
-                const uint32_t ahi = a_base + sa * CF::A_STAGE;
-                const uint32_t alo = ahi + (CF::NSPLIT - 1) * A_TILE;
-                if (PASSES != 4) {
-#pragma unroll
-                    for (int j = 0; j < MPT / 2; ++j) {
-                        const int off = sw128_offset(r, part * (MPT / 2) + j);
-                        sts128(ahi + off, hi4[j]);
-                        if (PASSES == 3) sts128(alo + off, lo4[j]);
-                    }
-                }
-                if (PASSES == 2 || PASSES == 4) {
-                    // 16-bit image row = [img1 of the chunk's 16 mics | img2 of the 16 mics]: a group of 4 mics
-                    // is 16 bytes = 16-byte chunk (part * G4 + gi) of each 64-byte half.  In FP16x3 mode it is
-                    // the only image of the stage (alo == ahi).
-#pragma unroll
-                    for (int gi = 0; gi < G4; ++gi) {
-                        sts128u(alo + sw128_offset(r, part * G4 + gi), img1[gi]);
-                        sts128u(alo + sw128_offset(r, 4 + part * G4 + gi), img2[gi]);
-                    }
-                }
+                PROF_ADD(24 + 4, prof);
                 // generic-proxy writes -> visible to the MMA (async proxy); one arrival per warp
-                // (32 same-address arrivals serialise in the shared-memory atomic unit)
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&fullA[sa]);
-                if (warp == 0) TRACE(0, 3, cib, fi - f_begin);
-                if (++sa == NSA) { sa = 0; pha ^= 1; }
-#ifdef B2_DEBUG_HANG
-                if (warp == 0) { DBG_PROG(0, g_prog[0] + 1); }
-#endif
-                prefetch(r_cur);                     // the chunk after next uses this buffer again
-                if (++cib == chunks_per_bin) {
-                    cib = 0;
-                    if (++fi < f_end) bf = float(freqs[fi] * inv_c);
-                }
+                if (lane == 0) mbar_arrive(fullA + 8 * s_slot);
+                PROF_ADD(24 + 5, prof);
+                PROF_CNT(24 + 6, prof);
+                s_slot += NG;
+                if (s_slot >= uint32_t(NSA)) { s_slot -= NSA; s_ph ^= 1; }
+                s_cib = n_cib;
+                if (n_fi != s_fi) { s_fi = n_fi; if (s_fi < f_end) bf = float(freqs[s_fi] * inv_c); }
             };
-            int i = 0;
+
+            // own chunk i is synthesised after the chunks up to the previous own chunk i - NG have been passed (its
+            // h' is still in hk); the tail passes the chunks behind this group's last own chunk
 #pragma unroll 1
-            for (; i + 1 < total; i += 2) { chunk_body(r_a); chunk_body(r_b); }
-            if (i < total) chunk_body(r_a);
-        }
-    } else if (warp < W_MMA) {
-        // =========================== epilogue: TMEM -> P[g,f] -> map ===========================
-        const int ew = warp - W_EPI0;
-        const int quad = ew & 3, half = ew >> 2;             // TMEM lane quadrant, which half of the columns
-        const int r = quad * 32 + lane;
-        const uint32_t lane_base = uint32_t(quad * 32) << 16;
-        constexpr int CG_PER_HALF = (NB / 32 + 1) / 2;       // 32-column groups per epilogue half
-        uint32_t acc_it = 0;
-        for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
-            B2_UNIT_DECODE
-            const int64_t g = int64_t(tile) * TILE_G + r;
-            asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");
-            float us;
-            float r0f;
-            double c2 = row_table(tab, r, 0, false, g, G, grid, mic, M, Mk, cx0, cy0, cz0, steering, &us, &r0f);
-            if (PASSES == 4) c2 /= double(us);            // T carries the amplitude scale once (the epilogue's h does not)
-            asm volatile("bar.sync 1, %0;" ::"n"(NGEN + NEPI) : "memory");   // table of this tile is complete
-            double acc_map = 0.0;
-            for (int fi = f_begin; fi < f_end; ++fi) {
-                const float bf = float(freqs[fi] * inv_c);
-                float p0 = 0.f, p1 = 0.f;
-                for (int t = 0; t < NBLK; ++t, ++acc_it) {
-                    // accumulators complete in the order b1, b0 within a pair (see walk_pair)
-                    const int nbk = !SHARE ? t : ((t & 1) ? t - 1 : (t + 1 < NBLK ? t + 1 : t));
-                    const int buf = acc_it & 1;
-                    // this warp's groups of 8 columns (microphones) of the block: col0, col0 + 8, ...
-                    const int col0 = half * CG_PER_HALF * 32;
-                    const int cols_here = min(min(NB, Mk - nbk * NB) - col0, CG_PER_HALF * 32);
-                    const int ngrp = cols_here > 0 ? cols_here >> 3 : 0;
-                    // distances of the 8 microphones of a group for this row (two 16-byte runs of the table),
-                    // fetched one group ahead -- the first group before the accumulator is even complete
-                    const float *tabq = tab + tab_index(nbk * NB + col0, r);
-                    float4 ra = make_float4(1.f, 1.f, 1.f, 1.f), rb = ra;
-                    if (ngrp > 0) {
-                        ra = __ldcg(reinterpret_cast<const float4 *>(tabq));
-                        rb = __ldcg(reinterpret_cast<const float4 *>(tabq + TILE_G * 4));
-                    }
-                    if (ew == 0) TRACE(1, 0, nbk, fi - f_begin);
-                    { PROF_T0(); mbar_wait(&tfull[buf], (acc_it >> 1) & 1); PROF_ADD(5, blockIdx.x == 0 && ew == 0 && lane == 0); }
-                    if (ew == 0) TRACE(1, 1, nbk, fi - f_begin);
-                    tc_fence_after();
-                    const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N + 2 * col0;
-#pragma unroll 1
-                    for (int c = 0; c < ngrp; ++c) {
-                        float t[16];                                     // (Re T, Im T) of 8 columns n
-                        tmem_ld16(tcol + 16 * c, t);
-                        const float rq[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-                        if (c + 1 < ngrp) {
-                            ra = __ldcg(reinterpret_cast<const float4 *>(tabq + (2 * c + 2) * (TILE_G * 4)));
-                            rb = __ldcg(reinterpret_cast<const float4 *>(tabq + (2 * c + 3) * (TILE_G * 4)));
-                        }
-                        tmem_ld_wait();
-                        auto reduce = [&](auto amp_tag) {
-                            constexpr int AMP = decltype(amp_tag)::value;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                // padded microphones have all-zero operand rows, so T is 0 there: no bounds test
-                                const float2 h0 = steer<AMP>(rq[2 * j], bf, r0f), h1 = steer<AMP>(rq[2 * j + 1], bf, r0f);
-                                p0 = fmaf(t[4 * j], h0.x, p0);
-                                p0 = fmaf(-t[4 * j + 1], h0.y, p0);
-                                p1 = fmaf(t[4 * j + 2], h1.x, p1);
-                                p1 = fmaf(-t[4 * j + 3], h1.y, p1);
-                            }
-                        };
-                        if (akind == AMP_RINV) reduce(std::integral_constant<int, AMP_RINV>{});
-                        else if (akind == AMP_R) reduce(std::integral_constant<int, AMP_R>{});
-                        else reduce(std::integral_constant<int, AMP_ONE>{});
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[buf]);
-                    if (ew == 0) TRACE(1, 2, nbk, fi - f_begin);
-                    if (ew == 0) DBG_PROG(1, acc_it + 1);
-                }
-                // combine the two column halves of this row
-                float *pp = part + (fi & 1) * TILE_G;
-                if (half == 1) pp[r] = p0 + p1;
-                asm volatile("bar.sync 2, 256;" ::: "memory");
-                if (half == 0) {
-                    double p = (double(p0 + p1) + double(pp[r])) * c2;        // |h|^2 scale of this grid point
-                    if (PASSES == 4) p /= double(bin_scale[fi]);                    // power-of-two scale of L_f
-                    if (clamp_negative && p < 0.0) p = 0.0;                         // beamforming.py:871-872
-                    acc_map += weights[fi] * p;                                       // :875-876
-                    if (per_bin != nullptr && g < G) per_bin[g * nbins + fi] = p;
-                }
+            for (int i = grp; i < total + NG; i += NG) {
+                const int upto = i - NG < total - 1 ? i - NG : total - 1;
+                while (e_idx <= upto) pass_chunk();
+                if (i < total) synth_chunk();
             }
+            while (e_idx < total) pass_chunk();
+            seq_base += uint32_t(total);
             // the bins of a tile may be split over several work units: the map is zeroed by the
             // launcher and every unit adds its weighted partial sum
-            if (half == 0 && g < G) atomicAdd(map_out + g, acc_map);
+            if (grp == 0 && g < G) atomicAdd(map_out + g, acc_map);
         }
-    } else if (warp == W_MMA || warp == W_MMA + 1) {
+#ifdef B2_MAP_PROFILE
+        if (prof) atomicAdd(&g_map_prof[24], (unsigned long long)(clock64() - t_role0));
+#endif
+        // balance the reader's last "slots free" arrival so that no named barrier is left half-arrived
+        if (NG > 1 && grp > 0) asm volatile("bar.sync %0, %1;" ::"r"(2 + quad), "n"(32 * NG) : "memory");
+    } else if (warp >= W_MMA && warp < W_MMA + 3) {
         // =========================== MMA issue ===========================
-        // Two issue warps, one per accumulator stream of a pair (warp W_MMA: block b0, warp W_MMA+1: block
-        // b1): a single issue thread needs ~800 cycles of dependent instructions per step (three barrier
-        // waits, descriptors, elect, 6 MMAs, commits) and was the pacing resource of the kernel.  Both warps
-        // walk the same step sequence; each acts on the steps of its own stream.  Every A and B tile is released
-        // by BOTH warps (emptyA / emptyB count 2): the warp that does not multiply a tile arrives on it directly.
+        // tcgen05.mma issue is back-pressured by the tensor pipe (the issuing thread advances at the pipe's rate),
+        // and every step also costs its issuing thread ~650 cycles that the pipe cannot use: two or three mbarrier
+        // waits, the elect, the commits.  The pipe only stays busy while ANOTHER warp is issuing during those gaps,
+        // so the steps of a bin are dealt to THREE issue warps with 8 steps each (M = 256):
+        //   warp 1: stream of block b1 (chunks NKC-1 .. kcB into accumulator 1),
+        //   warp 2: upper half of the stream of block b0 (the same chunks, into accumulator 0, full width),
+        //   warp 0: lower half of the stream of b0 (chunks kcB-1 .. kcA: the triangle of b0).
+        // (With one warp per STREAM, warp 0 had 16 of the 24 steps and its gaps alone were 10 K of the 25 K cycles
+        // of a bin: role profile, profiles/r2_map_roles.txt.)  All warps walk the same step sequence (= the order of
+        // the B ring) and act on their own steps.
+        // mbarrier waits only see the PARITY of a phase, so a warp must observe EVERY use of a barrier it ever waits on:
+        //  * A ring: every issue warp releases every tile (emptyA counts 3) -- with tcgen05.commit if it multiplies
+        //    the tile, else by waiting for fullA and arriving directly (on the tile's first step of the walk);
+        //  * B ring: the slots are shared (walk order) and released by the step's warp alone, but each warp has its
+        //    OWN set of NSB full barriers, used in the order of its own steps: the loader cannot signal tile k + NSB
+        //    of a warp before the slot of tile k has been recycled, i.e. before that warp has consumed tile k.
+        // Warp 0 accumulates into the accumulator that warp 2 initialises: it waits for `tinit` (warp 2's overwriting
+        // MMA has retired).
         const int my = warp - W_MMA;
         // The whole warp walks the loop, so every address, descriptor and flag is warp-uniform and lives in
-        // uniform registers; one elected lane issues the tcgen05 instructions.  (Running the loop inside an
-        // `if (lane == 0)` made every tcgen05.mma cost ~13 instructions of register shuffling, and the issue
-        // thread -- not the tensor pipe -- set the pace of the kernel: time grew linearly with the number of
-        // MMA instructions, 110 cycles each.)
-        const uint32_t a0 = desc_lo(smem_u32(smem)), b0d = desc_lo(smem_u32(smem) + NSA * CF::A_STAGE);
+        // uniform registers; one elected lane issues the tcgen05 instructions.
+        const uint32_t a0 = desc_lo(smem_base), b0d = desc_lo(b_ring);
         uint32_t seqA = 0;                                   // A tiles consumed so far (ring sequence number)
-        uint32_t sb = 0, phb = 0, acc_it = 0;
+        uint32_t sb = 0;                                     // B ring slot of the current step (shared, walk order)
+        uint32_t mb = 0, phm = 0;                            // this warp's own full-barrier cursor and its phase
+        uint32_t acc_it = 0;
+        uint32_t tin[2] = {0, 0};                            // tinit phases completed so far on each TMEM buffer
+        const uint32_t fullBm = fullB + 8 * uint32_t(my) * NSB;
+        PROF_DECL;
+        const bool prof = blockIdx.x == 0 && lane == 0;
+        (void)prof;
+#ifdef B2_MAP_PROFILE
+        const long long t_role0 = clock64();
+#endif
         for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
             B2_UNIT_DECODE
             (void)tile;
@@ -763,49 +822,53 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                     acc_it = acc0 + 1;
                     const uint32_t seq0 = seqA;                  // ring sequence number of chunk NKC-1
                     seqA += uint32_t(NKC - kcA);
+                    // a pair of two blocks hands accumulator 0 from warp 2 to warp 0: one tinit phase on its buffer
+                    uint32_t tin_par = 0;
+                    if (B2_ISSUE3 && blk1 >= 0) { tin_par = tin[acc0 & 1] & 1; ++tin[acc0 & 1]; }
                     walk_pair(NKC, kcA, kcB, GS, [&](int kc, int tgt, bool first_use, bool last_use) {
                         (void)last_use;
-                        DBG_PROG(2 + my, g_prog[2 + my] + 1);
-                        if (tgt != my) {
-                            // the other warp's step: this warp only has to release a tile it never multiplies
-                            // (a b0-only chunk seen by the b1 warp) -- after the tile's phase is complete, so
-                            // that the arrival cannot land in an earlier phase
-                            if (my == 1 && first_use) {
-                                const uint32_t seq = seq0 + uint32_t(NKC - 1 - kc);
-                                const uint32_t sa = seq % NSA, pha = (seq / NSA) & 1;
-                                mbar_wait(&fullA[sa], pha);
-                                if (elect_one_sync()) mbar_arrive(&emptyA[sa]);
+                        PROF_T0();
+                        const int owner = step_owner(tgt, kc, kcB);
+                        const uint32_t seq = seq0 + uint32_t(NKC - 1 - kc);
+                        const uint32_t sa = seq % NSA, pha = (seq / NSA) & 1;
+                        if (owner != my) {
+                            // A tile this warp never multiplies (above kcB: warp 0; below: warps 1 and 2) is released on its
+                            // first step of the walk -- after its phase is complete, so that the arrival cannot land in an
+                            // earlier phase
+                            const bool uses_tile = kc >= kcB ? my == 1 || my == (B2_ISSUE3 ? 2 : 0) : my == 0;
+                            if (first_use && !uses_tile) {
+                                mbar_wait(fullA + 8 * sa, pha);
+                                if (elect_one_sync()) mbar_arrive(emptyA + 8 * sa);
                                 __syncwarp();
+                                PROF_ADD(8 * my + 5, prof);
                             }
-                            // The B tile of the step is not used by this warp, but the warp still waits for it
-                            // and releases it (emptyB counts 2): a stage is only recycled after BOTH warps have
-                            // passed it, so neither can get a whole ring round away from the other -- mbarrier
-                            // waits only know the parity of a phase, and a warp one round ahead (or two behind)
-                            // would mistake another phase for its own (scripts/sim_protocol.py reproduces the
-                            // deadlock that follows).
-                            mbar_wait(&fullB[sb], phb);
-                            if (elect_one_sync()) mbar_arrive(&emptyB[sb]);
-                            __syncwarp();
-                            if (++sb == NSB) { sb = 0; phb ^= 1; }
+                            if (++sb == NSB) sb = 0;
                             return;
                         }
                         const uint32_t acc = tgt ? acc1 : acc0;
                         const uint32_t buf = acc & 1;
-                        TRACE(2 + my, 0, kc, fi - f_begin);
-                        if (kc == NKC - 1) {                     // first MMA of this accumulator: buffer drained?
-                            PROF_T0(); mbar_wait(&tempty[buf], ((acc >> 1) & 1) ^ 1); PROF_ADD(3, blockIdx.x == 0 && lane == 0 && my == 0);
-                        }
+                        const uint32_t use_par = (acc >> 1) & 1;
+                        // first MMA of this accumulator: have the synthesis warps read its previous contents?
+                        if (kc == NKC - 1) mbar_wait(tempty + 8 * buf, use_par ^ 1);
+                        // first step of warp 0 into an accumulator that warp 2 has worked on: all of warp 2's MMAs must have
+                        // retired, because warp 0's commits are what declares the columns of its chunks final
+                        if (B2_ISSUE3 && my == 0 && kc == kcB - 1 && kcB < NKC) mbar_wait(tinit + 8 * buf, tin_par);
+                        PROF_ADD(8 * my + 1, prof);
                         const uint32_t d_tmem = tmem_base + buf * UMMA_N;
                         const int kbase = tgt ? kcB : kcA;
                         // columns of this block that chunk kc can reach (lower triangle): w, N = 2w
                         const int w = min(NB, KCH * (kc - kbase + 1));
-                        const uint32_t seq = seq0 + uint32_t(NKC - 1 - kc);
-                        const uint32_t sa = seq % NSA, pha = (seq / NSA) & 1;
-                        { PROF_T0(); mbar_wait(&fullB[sb], phb); PROF_ADD(7, blockIdx.x == 0 && lane == 0 && my == 0); }
-                        { PROF_T0(); mbar_wait(&fullA[sa], pha); PROF_ADD(2, blockIdx.x == 0 && lane == 0 && my == 0); }
+                        // Every chunk signals tdone exactly once per use of its ring slot: on the step that makes its
+                        // own columns final (the block that contains it), or -- for a chunk above both blocks of the
+                        // pair, whose columns belong to another pair -- on the b0 step.
+                        const int cblk = (kc * KCH) / NB;
+                        const bool own = cblk == (tgt ? blk1 : blk0);
+                        const bool signal_done = own || (tgt == 0 && cblk != blk0 && cblk != blk1);
+                        mbar_wait(fullBm + 8 * mb, phm);
+                        PROF_ADD(8 * my + 2, prof);
+                        mbar_wait(fullA + 8 * sa, pha);
+                        PROF_ADD(8 * my + 3, prof);
                         tc_fence_after();
-                        TRACE(2 + my, 1, kc, fi - f_begin);
-                        DBG_PROG(8 + my, 1000 * kc + 10 * tgt + 1);
                         // low words of the operand descriptors: first image, second (correction) image
                         const uint32_t a1 = a0 + sa * (CF::A_STAGE >> 4), b1 = b0d + sb * (CF::B_STAGE >> 4);
                         const uint32_t a2 = a1 + (CF::NSPLIT - 1) * (A_TILE >> 4), b2 = b1 + (CF::NSPLIT - 1) * (CF::B_TILE >> 4);
@@ -839,22 +902,29 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                                 }
                             }
                             // tcgen05.commit: the barriers are signalled when the MMAs issued so far retire
-                            umma_commit(&emptyA[sa]);                      // this warp is done with the A tile
-                            umma_commit(&emptyB[sb]);
-                            if (kc == kbase) umma_commit(&tfull[buf]);     // accumulator complete -> epilogue
+                            if (signal_done) umma_commit(tdone + 8 * sa);      // columns of chunk kc are final -> reduction
+                            umma_commit(emptyA + 8 * sa);                      // this warp is done with the A tile
+                            umma_commit(emptyB + 8 * sb);
+                            // warp 2's last step of this accumulator: warp 0 continues when it has retired
+                            if (B2_ISSUE3 && my == 2 && kc == kcB) umma_commit(tinit + 8 * buf);
                         }
                         __syncwarp();
-                        TRACE(2 + my, 2, kc, fi - f_begin);
-                        DBG_PROG(8 + my, 1000 * kc + 10 * tgt + 2);
-                        if (++sb == NSB) { sb = 0; phb ^= 1; }
+                        PROF_ADD(8 * my + 4, prof);
+                        PROF_CNT(8 * my + 6, prof);
+                        if (++sb == NSB) sb = 0;
+                        if (++mb == NSB) { mb = 0; phm ^= 1; }
                     });
                 }
             }
         }
+#ifdef B2_MAP_PROFILE
+        if (prof) atomicAdd(&g_map_prof[8 * my], (unsigned long long)(clock64() - t_role0));
+#endif
     } else {
         // =========================== B operand loader (one thread) ===========================
         if (lane == 0) {
             uint32_t sb = 0, phb = 0;
+            uint32_t mbw[3] = {0, 0, 0};                     // per issue warp: its next full barrier
             const size_t bin_bytes = size_t(NBLK) * NKC * CF::NSPLIT * CF::B_TILE;
             for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
                 B2_UNIT_DECODE
@@ -868,15 +938,15 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                             const int blk = tgt ? blk1 : blk0;
                             const int w = min(NB, KCH * (kc - (tgt ? kcB : kcA) + 1));
                             const uint32_t bytes = uint32_t(2 * w) * 128;          // first 2w rows of each image
-                            mbar_wait(&emptyB[sb], phb ^ 1);
+                            const int owner = step_owner(tgt, kc, kcB);
+                            const uint32_t fb = fullB + 8 * (uint32_t(owner) * NSB + mbw[owner]);
+                            if (++mbw[owner] == uint32_t(NSB)) mbw[owner] = 0;
+                            mbar_wait(emptyB + 8 * sb, phb ^ 1);
                             const unsigned char *src = op + size_t(fi) * bin_bytes + (size_t(blk) * NKC + kc) * (CF::NSPLIT * CF::B_TILE);
-                            mbar_arrive_expect_tx(&fullB[sb], CF::NSPLIT * bytes);
-                            bulk_g2s(b_tile(sb, 0), src, bytes, &fullB[sb]);
-                            if (CF::NSPLIT == 2) bulk_g2s(b_tile(sb, 1), src + CF::B_TILE, bytes, &fullB[sb]);
+                            mbar_arrive_expect_tx(fb, CF::NSPLIT * bytes);
+                            bulk_g2s(b_ring + sb * CF::B_STAGE, src, bytes, fb);
+                            if (CF::NSPLIT == 2) bulk_g2s(b_ring + sb * CF::B_STAGE + CF::B_TILE, src + CF::B_TILE, bytes, fb);
                             if (++sb == NSB) { sb = 0; phb ^= 1; }
-#ifdef B2_DEBUG_HANG
-                            if (blockIdx.x == 0) g_prog[4] += 1;
-#endif
                         });
                     }
                 }
@@ -884,14 +954,6 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         }
     }
 
-#ifdef B2_MAP_PROFILE
-    if (blockIdx.x == 0) {
-        const unsigned long long dt = (unsigned long long)(clock64() - t_kernel0);
-        if (tid == 0) atomicAdd(&g_map_prof[1], dt);
-        if (warp == W_MMA && lane == 0) atomicAdd(&g_map_prof[4], dt);
-        if (warp == W_EPI0 && lane == 0) atomicAdd(&g_map_prof[6], dt);
-    }
-#endif
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -952,9 +1014,9 @@ __global__ void das_prepare_tc_kernel(const double2 *__restrict__ csm, int M, in
                 if (n == m) { lr = remove_diag ? 0.0 : gain * c.x; }
                 else { lr = 2.0 * gain * c.x; li = 2.0 * gain * c.y; }
             }
-            // real rows: (Re L, Im L) ; imaginary rows: (Im L, -Re L)
-            v[2 * e] = float(imag_row ? li : lr);
-            v[2 * e + 1] = float(imag_row ? -lr : li);
+            // real rows: (Re L, Im L) -> Re T ; imaginary rows: (-Im L, Re L) -> -Im T
+            v[2 * e] = float(imag_row ? -li : lr);
+            v[2 * e + 1] = float(imag_row ? lr : li);
         }
         if (PASSES == 4) {
             // row = [g1 of the chunk's 16 mics | g2 of the 16 mics] (FP16): the 2 mics of this j are 8 bytes
@@ -1067,7 +1129,7 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
     const int nblocks = int(units < cap ? units : cap);
     B2_CUDA_OK(cudaMemsetAsync(map_out, 0, size_t(G) * sizeof(double), st));
     float *scratch = tables_ptr<PASSES>(op, M, nbins);
-    kern<<<nblocks, TC_THREADS, CF::SMEM, st>>>((const unsigned char *)op, scratch, scales_ptr<PASSES>(op, M, nbins), M, nbins,
+    kern<<<nblocks, CF::THREADS, CF::SMEM, st>>>((const unsigned char *)op, scratch, scales_ptr<PASSES>(op, M, nbins), M, nbins,
                                                 (const double *)freqs,
                                                 (const double *)weights, 1.0 / c, (const double *)mic, center[0],
                                                 center[1], center[2], (const double *)grid, G, steering,
@@ -1082,39 +1144,11 @@ template <int PASSES> int64_t operand_bytes(int M, int nbins) {
 
 }  // namespace
 
-#ifdef B2_DEBUG_HANG
-extern "C" int b2_debug_hang_report(unsigned int *out) {      // out[0] = count, then 4 words per record
-    unsigned int n = 0, z = 0;
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(&n, g_nhang, 4);
-    out[0] = n;
-    cudaMemcpyFromSymbol(out + 1, g_hang, sizeof(unsigned int) * 240);
-    cudaMemcpyFromSymbol(out + 241, g_snap, sizeof(unsigned int) * 16);
-    unsigned int zz[16] = {0};
-    cudaMemcpyToSymbol(g_prog, zz, sizeof(zz));
-    cudaMemcpyToSymbol(g_snap, zz, sizeof(zz));
-    cudaMemcpyToSymbol(g_snapped, &z, 4);
-    cudaMemcpyToSymbol(g_nhang, &z, 4);
-    cudaMemcpyToSymbol(g_abort, &z, 4);
-    return 0;
-}
-#endif
-
-#ifdef B2_MAP_TRACE
-extern "C" int b2_debug_trace(long long *out, int max_records) {      // copies [4 roles][1024]{tag, clock}
-    (void)max_records;
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 4 * 2 * 1024);
-    static long long zeros[4 * 2 * 1024];
-    cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros));
-    return 4096;
-}
-#endif
-
 #ifdef B2_MAP_PROFILE
 extern "C" int b2_debug_map_profile(unsigned long long *out) {
-    cudaMemcpyFromSymbol(out, g_map_prof, sizeof(unsigned long long) * 8);
-    unsigned long long z[8] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_map_prof, sizeof(unsigned long long) * 32);
+    unsigned long long z[32] = {0};
     cudaMemcpyToSymbol(g_map_prof, z, sizeof(z));
     return 0;
 }

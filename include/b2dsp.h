@@ -138,7 +138,16 @@ int b2_das_prepare(const void *csm_dev, int M, int nb, int bin0, int nbins, int 
  *   freqs_dev     nbins float64 bin frequencies in Hz
  *   weights_dev   nbins float64
  *   map_out_dev   G float64
- *   per_bin_out_dev  optional (G, nbins) float64 of the clamped per-bin powers, or NULL */
+ *   per_bin_out_dev  optional (G, nbins) float64 of the clamped per-bin powers, or NULL
+ * Two properties of the tensor-core modes a caller must know:
+ *   - op_dev also holds the kernel's per-CTA distance tables (written during the launch): one operand
+ *     buffer must not be shared by two b2_das_map launches that are in flight at the same time
+ *     (consecutive launches on one stream are fine).
+ *   - when there are more tiles of 128 grid points than SMs, the bins are split into ranges (sized to
+ *     keep the operand images of a range L2-resident) and the weighted partial sums of the ranges are
+ *     combined with fp64 atomicAdd: the map is reproducible only up to the order of at most
+ *     (number of ranges) fp64 additions per grid point (~1e-16 relative, tests/test_gpu_fullsize.py);
+ *     the per-bin output and the CUDA-core modes are bit-reproducible. */
 int b2_das_map(const void *op_dev, int M, int nbins, const void *freqs_dev,
                const void *weights_dev, double c, const void *mic_xyz_dev,
                const double *center_xyz, const void *grid_xyz_dev, int64_t G, int steering,
