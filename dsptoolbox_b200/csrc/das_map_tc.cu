@@ -74,16 +74,9 @@ constexpr int TILE_G = 128;
 constexpr int KCH = 16;                       // microphones per K chunk = 32 reals = one 128 B row
 constexpr int A_TILE = TILE_G * 128;          // bytes of one A operand image
 #ifndef B2_NG
-#define B2_NG 4
+#define B2_NG 2
 #endif
 static_assert(B2_NG >= 1 && B2_NG <= 4, "1..4 groups of 4 warps");
-
-#ifndef B2_ISSUE3
-#define B2_ISSUE3 0
-#endif
-// issue warp of a step: 1 = stream of block b1; the stream of block b0 is either all warp 0's, or (B2_ISSUE3) split
-// into warp 2 (the chunks shared with b1) and warp 0 (the triangle of b0)
-__device__ __forceinline__ int step_owner(int tgt, int kc, int kcB) { return tgt ? 1 : ((B2_ISSUE3 && kc >= kcB) ? 2 : 0); }
 
 constexpr int MAX_CTAS = 160;                 // scratch tables are sized for this many persistent CTAs
 constexpr int MAX_MICS = 1024;
@@ -93,7 +86,15 @@ __host__ __device__ constexpr int tc_nb(int M) { return M <= 32 ? 32 : (M <= 64 
 
 template <int NB, int PASSES> struct TcCfg {
     static constexpr int UMMA_N = 2 * NB;
-    static constexpr int B_TILE = UMMA_N * 128;
+    // PLANAR complex layout (FP16x3 mode): operand rows hold [Re of the chunk's 16 microphones | Im of them] per
+    // FP16 half instead of interleaved (Re, Im) pairs, and the B image has ONE row per matrix column n (not a Re-T and
+    // an Im-T row that carry the same numbers): Re T and Im T come from different K slices of the same rows,
+    //   Re T += Hr Lr^T + Hi Li^T,   Im T += Hr Li^T + (-Hi) Lr^T   (A negated by the instruction descriptor),
+    // as twice as many MMAs of half the width -- the same tensor work for HALF the B bytes.  The operand stream from
+    // L2 was what bound the kernel: 148 CTAs x 557 KB per (tile, bin) = 5.2 TB/s at 25 K cycles per bin.
+    static constexpr bool PLANAR = PASSES == 4;
+    static constexpr int B_ROWS = PLANAR ? NB : UMMA_N;
+    static constexpr int B_TILE = B_ROWS * 128;
     static constexpr int NSPLIT = (PASSES == 1 || PASSES == 4) ? 1 : 2; // operand images per stage (hi[, correction])
     // Two independent shared-memory rings: A (synthesised steering tiles, small stages) and B (streamed
     // operand images, large stages).  The A ring is made as deep as the 227 KB allow, because the
@@ -101,40 +102,46 @@ template <int NB, int PASSES> struct TcCfg {
     // chunk) and a deep ring is what lets them overlap instead of waiting for each other.
     static constexpr int A_STAGE = NSPLIT * A_TILE;
     static constexpr int B_STAGE = NSPLIT * B_TILE;
-    // B ring: the loader can only run NSB tiles ahead of the slowest issue warp, and a 32 KB tile needs ~1000
-    // cycles from L2 -- with 3 stages the issue warps waited ~360 cycles per step for B (role profile, r2).
-#ifdef B2_NSB
-    static constexpr int NSB = B2_NSB;
+    // A ring and two B rings.  Each of the two MMA issue warps (stream 0: block b0 of a pair, stream 1: block b1)
+    // has its OWN B ring and loader thread: with one shared ring in a fixed step order the loader could not fetch
+    // the first tile of the next bin for one warp before the other warp had consumed its last tiles of this bin,
+    // which chained the 24 steps of a bin into one serial sequence (~1000 cycles each: role profile, r2).
+    static constexpr bool SHARE = A_STAGE <= 16 * 1024 && B_STAGE <= 32 * 1024;   // pairs of column blocks share their A tiles
+#ifdef B2_NSB0
+    static constexpr int NSB0 = B2_NSB0, NSB1 = B2_NSB1;
 #else
-    static constexpr int NSB = B_STAGE >= 64 * 1024 ? 2 : 4;
+    static constexpr int NSB0 = !SHARE ? 2 : (B_STAGE <= 16 * 1024 ? 3 : 2);
+    static constexpr int NSB1 = !SHARE ? 0 : 2;
 #endif
+    static constexpr int NSB = NSB0 + NSB1;
     static constexpr int NSA_RAW = (224 * 1024 - NSB * B_STAGE) / A_STAGE;
 #ifdef B2_NSA
     static constexpr int NSA = B2_NSA;
 #else
     static constexpr int NSA = NSA_RAW > 10 ? 10 : NSA_RAW;
 #endif
-    // With a deep A ring, two neighbouring column blocks share the synthesised A tiles (see walk_pair);
-    // GS = how many chunks the second block's stream lags behind (their tiles are held in the ring).
-    static constexpr bool SHARE = NSA >= 6;
-#ifdef B2_LAG
-    static constexpr int GS = B2_LAG;
-#else
-    static constexpr int GS = NSA - 2;
+    // Synthesis/reduction warp groups (chunks are dealt round-robin: group j synthesises chunks j, j + NG, ...).  A
+    // group reduces a chunk DLAG of its OWN chunks after it synthesised it (it keeps the h' of DLAG chunks in
+    // registers): synthesis -> fullA -> MMA issue -> tensor pipe -> tdone -> TMEM load is a dependent chain of
+    // ~2000 cycles, and with DLAG = 1 each group had exactly one chunk in flight -- the whole kernel then ran at
+    // NG chunks per chain latency however deep the rings were (ablation: 9.0 of 13.6 ms WITHOUT any MMA).
+    // Before it synthesises chunk i a group passes the chunks (i - (DLAG + 1) NG, i - DLAG NG] of the event stream,
+    // waiting on `tdone` of its own chunk and of any block's lowest chunk in that range.  mbarrier waits only see
+    // the PARITY of a phase, so the ring slot of such a chunk must not be able to complete a further use meanwhile:
+    // chunk c + NSA is only synthesised after chunk i when c + NSA > i, i.e. NSA >= (DLAG + 1) NG.
+#ifndef B2_DLAG
+#define B2_DLAG 3
 #endif
-    // Synthesis/reduction warp groups (chunks are dealt round-robin).  Before a group synthesises chunk i it passes
-    // the chunks (i - 2 NG, i - NG] of the event stream, waiting on `tdone` of its own chunk i - NG and of any block's
-    // lowest chunk in that range.  mbarrier waits only see the PARITY of a phase, so the ring slot of a chunk it
-    // still has to wait for must not be able to complete a further use meanwhile: chunk c + NSA is only
-    // synthesised after chunk i when c + NSA > i, i.e. NSA >= 2 NG (scripts/sim_protocol.py checks the protocol).
-    static constexpr int NG = 2 * B2_NG <= NSA ? B2_NG : (NSA >= 4 ? NSA / 2 : 1);
+    static constexpr int NG = (B2_DLAG + 1) * B2_NG <= NSA ? B2_NG : (2 * B2_NG <= NSA ? B2_NG : (NSA >= 4 ? 2 : 1));
+    static constexpr int DLAG = (B2_DLAG + 1) * NG <= NSA ? B2_DLAG : ((NSA / NG - 1) >= 1 ? (NSA / NG - 1) : 1);
+    static_assert(NG == 1 || (DLAG + 1) * NG <= NSA, "a ring slot could complete a further use while a group still waits for it");
     static constexpr int NGEN = TILE_G * NG;                           // warp w owns TMEM lanes 32 (w % 4) ...
     static constexpr int NS_WARPS = NGEN / 32;
-    static constexpr int W_MMA = NS_WARPS;            // three MMA issue warps (see the issue role); the loader warp follows
+    static constexpr int W_MMA = NS_WARPS;            // two MMA issue warps, then their two B loader warps
     static constexpr int THREADS = NGEN + 128;
     static constexpr int PARTIAL_ROWS = NG > 1 ? NG - 1 : 1;           // per-bin partial sums handed to the first group
     static constexpr int TMEM_COLS = 2 * UMMA_N;                       // two accumulator buffers
-    static constexpr int NBARS = 3 * NSA + 4 * NSB + 4;
+    static constexpr int NBARS = 3 * NSA + 2 * NSB + 2;
     static constexpr int SMEM = NSA * A_STAGE + NSB * B_STAGE + PARTIAL_ROWS * TILE_G * 4 + PROG_MAX * 2 + NBARS * 8 + 16;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -284,10 +291,11 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
-// same, FP16 x FP16
+// same, FP16 x FP16; bit 13 negates the A operand
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
     return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
+constexpr uint32_t IDESC_NEGATE_A = 1u << 13;
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -360,6 +368,9 @@ __host__ __device__ inline int amp_kind(int steering) {
 // r_m = r0 - dn and the power-of-two scale `us` of the FP16 operands: (-1/us, r0/us) resp. (-us, r0 us).
 template <int AMP>
 __device__ __forceinline__ void steer2(float2 dn, float q, float ak, float ac, float2 &hr, float2 &hi) {
+#ifdef B2_ABL_NOSYNTH
+    hr = __fmul2_rn(dn, make_float2(q, q)); hi = __ffma2_rn(dn, make_float2(ak, ak), make_float2(ac, ac)); return;
+#endif
     const float2 p = __fmul2_rn(make_float2(q, q), dn);
     const float2 big = make_float2(12582912.0f, 12582912.0f);            // 1.5 * 2^23: rounds to the nearest integer
     const float2 rn = __fadd2_rn(__fadd2_rn(p, big), make_float2(-12582912.0f, -12582912.0f));
@@ -383,27 +394,11 @@ __device__ __forceinline__ void steer2(float2 dn, float q, float ak, float ac, f
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // ---------------------------------------------------------------- the kernel
-// Order of the tensor-core work of one bin for a PAIR of neighbouring column blocks (b0, b1 = b0 + 1).
-// Chunks are walked downwards from the last one (kc = NKC-1: the widest, its MMA overwrites the
-// accumulator).  Chunks kc >= kcB feed both blocks, chunks kcA <= kc < kcB feed b0 only.  The two
-// accumulators are fed as two skewed streams: step i multiplies chunk NKC-1-i into b1 (first use of its A
-// tile) and chunk NKC-1-(i-LAG) into b0 (last use, frees the tile).  So every steering tile is
-// synthesised ONCE per bin although both blocks need it, the tensor pipe sees a steady mix of both
-// streams, and the accumulator of b0 is not touched during the first LAG steps.  A lone block is the case
-// kcB = NKC.
-//   fn(kc, target /*1: b1, 0: b0*/, first_use_of_A_tile, last_use_of_A_tile)
-template <class F>
-__device__ __forceinline__ void walk_pair(int NKC, int kcA, int kcB, int LAG, F &&fn) {
-    const int n1 = NKC - kcB;                 // steps of the b1 stream (0 for a lone block)
-    const int n0 = NKC - kcA;                 // steps of the b0 stream
-    const int lag = n1 < LAG ? n1 : LAG;
-    for (int i = 0; i < n0 + lag; ++i) {
-        if (i < n1) fn(NKC - 1 - i, 1, true, false);
-        const int j = i - lag;
-        if (j >= 0) fn(NKC - 1 - j, 0, j >= n1, true);
-    }
-}
-
+// The tensor-core work of one bin for a PAIR of neighbouring column blocks (b0, b1 = b0 + 1): chunks are walked
+// downwards from the last one (kc = NKC-1: the widest, its MMA overwrites the accumulator).  Chunks kc >= kcB feed both
+// blocks, chunks kcA <= kc < kcB feed b0 only.  Stream 0 (issue warp 0) multiplies every chunk into the accumulator of
+// b0, stream 1 (issue warp 1) the chunks kc >= kcB into the accumulator of b1: every steering tile is synthesised ONCE
+// per bin although both blocks need it.  A lone block is the case kcB = NKC.
 // work unit -> (contiguous range of bins, tile of 128 grid points); units are dealt round-robin and ordered
 // bin-range-major: all CTAs work on the same range of bins at the same time, so the operand images of that
 // range (sized to fit the L2) are fetched from HBM once per launch instead of once per wave of tiles
@@ -428,7 +423,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                   const double *__restrict__ grid, int64_t G, int steering, int clamp_negative,
                   double *__restrict__ map_out, double *__restrict__ per_bin, int ntiles, int nsplit) {
     using CF = TcCfg<NB, PASSES>;
-    constexpr int UMMA_N = CF::UMMA_N, NSA = CF::NSA, NSB = CF::NSB, NG = CF::NG, NGEN = CF::NGEN;
+    constexpr int UMMA_N = CF::UMMA_N, NSA = CF::NSA, NSB = CF::NSB, NG = CF::NG, NGEN = CF::NGEN, DLAG = CF::DLAG;
     constexpr int NS_WARPS = CF::NS_WARPS, W_MMA = CF::W_MMA, PARTIAL_ROWS = CF::PARTIAL_ROWS;
     extern __shared__ __align__(1024) unsigned char smem[];
     float *partial = reinterpret_cast<float *>(smem + NSA * CF::A_STAGE + NSB * CF::B_STAGE);   // [PARTIAL_ROWS][128]
@@ -437,9 +432,9 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + CF::NBARS);
     // shared-space addresses of the barrier arrays (8 bytes per barrier)
     const uint32_t smem_base = smem_u32(smem);
-    // fullB: one set of NSB barriers PER ISSUE WARP (tile k of warp w signals fullB + 8 (w NSB + k % NSB))
-    const uint32_t fullA = smem_u32(bars), emptyA = fullA + 8 * NSA, fullB = emptyA + 8 * NSA, emptyB = fullB + 8 * 3 * NSB;
-    const uint32_t tdone = emptyB + 8 * NSB, tempty = tdone + 8 * NSA, tinit = tempty + 16;
+    // B barriers: ring 0 (NSB0 slots) then ring 1 (NSB1 slots)
+    const uint32_t fullA = smem_u32(bars), emptyA = fullA + 8 * NSA, fullB = emptyA + 8 * NSA, emptyB = fullB + 8 * NSB;
+    const uint32_t tdone = emptyB + 8 * NSB, tempty = tdone + 8 * NSA;
     const uint32_t b_ring = smem_base + NSA * CF::A_STAGE;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -450,7 +445,6 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
     float *tab = scratch + size_t(blockIdx.x) * TILE_G * Mk;
     // column blocks are processed in pairs that share their A tiles (CF::SHARE), else one by one
     constexpr bool SHARE = CF::SHARE;
-    constexpr int GS = CF::GS;
     const int NPAIR = SHARE ? (NBLK + 1) / 2 : NBLK;
     auto pair_b0 = [&](int p) { return SHARE ? 2 * p : p; };
     auto pair_b1 = [&](int p) { return (SHARE && 2 * p + 1 < NBLK) ? 2 * p + 1 : -1; };
@@ -462,12 +456,11 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         if (smem_base & 1023u) __trap();          // SWIZZLE_128B operand tiles need a 1024-byte aligned base
         for (int s = 0; s < NSA; ++s) {
             mbar_init(fullA + 8 * s, 4);          // one arrival per warp of the group that owns the chunk
-            mbar_init(emptyA + 8 * s, 3);         // every issue warp releases every tile
+            mbar_init(emptyA + 8 * s, 2);         // both issue warps release every tile
             mbar_init(tdone + 8 * s, 1);          // committed once per chunk by the warp that issues its last relevant step
         }
-        for (int s = 0; s < 3 * NSB; ++s) mbar_init(fullB + 8 * s, 1);
-        for (int s = 0; s < NSB; ++s) mbar_init(emptyB + 8 * s, 1);      // released by the step's issue warp
-        for (int b = 0; b < 2; ++b) { mbar_init(tempty + 8 * b, NS_WARPS); mbar_init(tinit + 8 * b, 1); }
+        for (int s = 0; s < NSB; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) mbar_init(tempty + 8 * b, NS_WARPS);
         fence_barrier_init();
         // the per-bin chunk program
         int n = 0, accbase = 0;
@@ -592,8 +585,9 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             int e_idx = 0, e_cib = 0, e_fi = f_begin, e_mod = 0;
             uint32_t e_slot = seq_base % NSA, e_ph = (seq_base / NSA) & 1;
             float bf = s_fi < f_end ? float(freqs[s_fi] * inv_c) : 0.0f;
-            float2 hk[KCH];                                   // h' of the own chunk synthesised last: (Re, Im) per microphone
+            float2 hkeep[DLAG][KCH];                          // h' of the last DLAG own chunks: (Re, Im) per microphone (pairs)
             float2 pacc = make_float2(0.f, 0.f);              // sum of Re T Re h' / of (-Im T) Im h', current bin
+            float2 pre = make_float2(0.f, 0.f);               // planar layout: (sum Re T Re h', sum Im T Im h')
             double acc_map = 0.0;
 
             // distances of the next own chunk (4 x 16 bytes), fetched one own-chunk ahead
@@ -607,7 +601,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             if (grp < total) prefetch(s_cib);
 
             // one chunk of the event stream: reduce it if it is ours, then the per-chunk events
-            auto pass_chunk = [&]() {
+            auto pass_chunk = [&](const float2 (&hk)[KCH]) {
                 const uint32_t e = prog[e_cib];
                 const uint32_t buf = (accs + ((e >> 7) & 7u)) & 1u;
                 if (e_mod == grp && (e & PG_RED)) {
@@ -615,15 +609,32 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                     mbar_wait(tdone + 8 * e_slot, e_ph);
                     PROF_ADD(24 + 1, prof);
                     tc_fence_after();
-                    const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N + 32u * ((e >> 10) & 7u);
+                    if (CF::PLANAR) {
+                        // accumulator of a block: Re T in columns [0, NB), Im T in [NB, 2 NB); hk = (Re h' of the 8
+                        // microphone pairs, Im h' of them): P = sum Re T Re h' - Im T Im h'
+                        const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N + 16u * ((e >> 10) & 7u);
 #pragma unroll
-                    for (int hlf = 0; hlf < 2; ++hlf) {
-                        float t[16];                         // (Re T, -Im T) of 8 microphones
-                        tmem_ld16(tcol + 16 * hlf, t);
-                        tmem_ld_wait();
+                        for (int hlf = 0; hlf < 2; ++hlf) {
+                            float t[16];
+                            tmem_ld16(tcol + hlf * NB, t);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)          // padded microphones have all-zero operand rows: T = 0, no bounds test
-                            pacc = __ffma2_rn(make_float2(t[2 * j], t[2 * j + 1]), hk[8 * hlf + j], pacc);
+                            for (int j = 0; j < 8; ++j)      // padded microphones have all-zero operand rows: T = 0, no bounds test
+                                pacc = __ffma2_rn(make_float2(t[2 * j], t[2 * j + 1]), hk[8 * hlf + j], pacc);
+                            if (hlf == 0) { pre.x += pacc.x + pacc.y; pacc = make_float2(0.f, 0.f); }
+                            else { pre.y += pacc.x + pacc.y; pacc = make_float2(0.f, 0.f); }
+                        }
+                    } else {
+                        const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N + 32u * ((e >> 10) & 7u);
+#pragma unroll
+                        for (int hlf = 0; hlf < 2; ++hlf) {
+                            float t[16];                     // (Re T, -Im T) of 8 microphones
+                            tmem_ld16(tcol + 16 * hlf, t);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)      // padded microphones have all-zero operand rows: T = 0, no bounds test
+                                pacc = __ffma2_rn(make_float2(t[2 * j], t[2 * j + 1]), hk[8 * hlf + j], pacc);
+                        }
                     }
                     PROF_ADD(24 + 2, prof);
                 }
@@ -638,8 +649,9 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 }
                 if (e & PG_ENDBIN) {
                     // end of the bin: combine the NG threads of the row, finish P[g, f] in fp64
-                    const float ptot = pacc.x + pacc.y;
+                    const float ptot = CF::PLANAR ? pre.x - pre.y : pacc.x + pacc.y;
                     pacc = make_float2(0.f, 0.f);
+                    pre = make_float2(0.f, 0.f);
                     double extra = 0.0;
                     if (NG > 1) {
                         // hand-off through shared memory inside the quadrant's NG warps, two named barriers per quadrant:
@@ -673,7 +685,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             };
 
             // synthesis of the own chunk at (s_fi, s_cib): 16 microphones of this row -> A tile + hk
-            auto synth_chunk = [&]() {
+            auto synth_chunk = [&](float2 (&hk)[KCH]) {
                 float2 dn[KCH / 2];
 #pragma unroll
                 for (int gi = 0; gi < 4; ++gi) {
@@ -691,6 +703,34 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 const uint32_t alo = ahi + (CF::NSPLIT - 1) * A_TILE;
                 auto synth = [&](auto amp_tag) {
                     constexpr int AMP = decltype(amp_tag)::value;
+                    if constexpr (CF::PLANAR) {
+                        // row = [f1 Re (16 mics) | f1 Im | f2 Re | f2 Im], 32 bytes each; 8 microphones = 16 bytes of every part
+#pragma unroll
+                        for (int g8 = 0; g8 < 2; ++g8) {
+                            uint4 f1r, f1i, f2r, f2i;
+                            uint32_t *q1r = reinterpret_cast<uint32_t *>(&f1r), *q1i = reinterpret_cast<uint32_t *>(&f1i);
+                            uint32_t *q2r = reinterpret_cast<uint32_t *>(&f2r), *q2i = reinterpret_cast<uint32_t *>(&f2i);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {      // microphone pairs
+                                float2 hr, hi;
+                                steer2<AMP>(dn[4 * g8 + j], bf, ak, ac, hr, hi);
+                                hk[4 * g8 + j] = hr;
+                                hk[8 + 4 * g8 + j] = hi;
+                                const __half2 ar = __floats2half2_rn(hr.x, hr.y), ai = __floats2half2_rn(hi.x, hi.y);
+                                const float2 rr = __ffma2_rn(__half22float2(ar), make_float2(-1.0f, -1.0f), hr);   // exact residuals
+                                const float2 ri = __ffma2_rn(__half22float2(ai), make_float2(-1.0f, -1.0f), hi);
+                                q1r[j] = pack_f16(ar);
+                                q1i[j] = pack_f16(ai);
+                                q2r[j] = pack_f16(__floats2half2_rn(rr.x, rr.y));
+                                q2i[j] = pack_f16(__floats2half2_rn(ri.x, ri.y));
+                            }
+                            sts128u(ahi + ((uint32_t(0 + g8) ^ rx) << 4), f1r);
+                            sts128u(ahi + ((uint32_t(2 + g8) ^ rx) << 4), f1i);
+                            sts128u(ahi + ((uint32_t(4 + g8) ^ rx) << 4), f2r);
+                            sts128u(ahi + ((uint32_t(6 + g8) ^ rx) << 4), f2i);
+                        }
+                        return;
+                    }
 #pragma unroll
                     for (int gi = 0; gi < 4; ++gi) {           // 4 microphones = 16 bytes of each 16-bit image
                         float2 hr0, hi0, hr1, hi1;
@@ -700,20 +740,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                                              make_float2(hr1.x, hi1.x), make_float2(hr1.y, hi1.y)};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) hk[4 * gi + j] = h[j];
-                        if (PASSES == 4) {           // row = [first FP16 halves of the 16 mics | second halves]
-                            uint4 f1, f2;
-                            uint32_t *q1 = reinterpret_cast<uint32_t *>(&f1), *q2 = reinterpret_cast<uint32_t *>(&f2);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const __half2 a1 = __floats2half2_rn(h[j].x, h[j].y);
-                                const float2 af = __half22float2(a1);
-                                const float2 res = __ffma2_rn(af, make_float2(-1.0f, -1.0f), h[j]);      // exact residual
-                                q1[j] = pack_f16(a1);
-                                q2[j] = pack_f16(__floats2half2_rn(res.x, res.y));
-                            }
-                            sts128u(ahi + ((uint32_t(gi) ^ rx) << 4), f1);
-                            sts128u(ahi + ((uint32_t(4 + gi) ^ rx) << 4), f2);
-                        } else {
+                        {
                             // TF32 image: 2 microphones per 16 bytes
                             float4 hi4[2], lo4[2];
 #pragma unroll
@@ -755,15 +782,22 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 if (n_fi != s_fi) { s_fi = n_fi; if (s_fi < f_end) bf = float(freqs[s_fi] * inv_c); }
             };
 
-            // own chunk i is synthesised after the chunks up to the previous own chunk i - NG have been passed (its
-            // h' is still in hk); the tail passes the chunks behind this group's last own chunk
+            // own chunk i is synthesised after the chunks up to the own chunk i - DLAG NG have been passed (the h' of
+            // that chunk sits in the register slot that chunk i then takes); the tail passes the chunks behind this
+            // group's last own chunk
 #pragma unroll 1
-            for (int i = grp; i < total + NG; i += NG) {
-                const int upto = i - NG < total - 1 ? i - NG : total - 1;
-                while (e_idx <= upto) pass_chunk();
-                if (i < total) synth_chunk();
+            for (int i0 = grp; i0 < total + DLAG * NG; i0 += DLAG * NG) {
+#pragma unroll
+                for (int d = 0; d < DLAG; ++d) {
+                    const int i = i0 + d * NG;
+                    if (i < total + DLAG * NG) {
+                        const int upto = i - DLAG * NG < total - 1 ? i - DLAG * NG : total - 1;
+                        while (e_idx <= upto) pass_chunk(hkeep[d]);
+                        if (i < total) synth_chunk(hkeep[d]);
+                    }
+                }
             }
-            while (e_idx < total) pass_chunk();
+            while (e_idx < total) pass_chunk(hkeep[0]);
             seq_base += uint32_t(total);
             // the bins of a tile may be split over several work units: the map is zeroed by the
             // launcher and every unit adds its weighted partial sum
@@ -774,36 +808,27 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
 #endif
         // balance the reader's last "slots free" arrival so that no named barrier is left half-arrived
         if (NG > 1 && grp > 0) asm volatile("bar.sync %0, %1;" ::"r"(2 + quad), "n"(32 * NG) : "memory");
-    } else if (warp >= W_MMA && warp < W_MMA + 3) {
+    } else if (warp == W_MMA || warp == W_MMA + 1) {
         // =========================== MMA issue ===========================
-        // tcgen05.mma issue is back-pressured by the tensor pipe (the issuing thread advances at the pipe's rate),
-        // and every step also costs its issuing thread ~650 cycles that the pipe cannot use: two or three mbarrier
-        // waits, the elect, the commits.  The pipe only stays busy while ANOTHER warp is issuing during those gaps,
-        // so the steps of a bin are dealt to THREE issue warps with 8 steps each (M = 256):
-        //   warp 1: stream of block b1 (chunks NKC-1 .. kcB into accumulator 1),
-        //   warp 2: upper half of the stream of block b0 (the same chunks, into accumulator 0, full width),
-        //   warp 0: lower half of the stream of b0 (chunks kcB-1 .. kcA: the triangle of b0).
-        // (With one warp per STREAM, warp 0 had 16 of the 24 steps and its gaps alone were 10 K of the 25 K cycles
-        // of a bin: role profile, profiles/r2_map_roles.txt.)  All warps walk the same step sequence (= the order of
-        // the B ring) and act on their own steps.
-        // mbarrier waits only see the PARITY of a phase, so a warp must observe EVERY use of a barrier it ever waits on:
-        //  * A ring: every issue warp releases every tile (emptyA counts 3) -- with tcgen05.commit if it multiplies
-        //    the tile, else by waiting for fullA and arriving directly (on the tile's first step of the walk);
-        //  * B ring: the slots are shared (walk order) and released by the step's warp alone, but each warp has its
-        //    OWN set of NSB full barriers, used in the order of its own steps: the loader cannot signal tile k + NSB
-        //    of a warp before the slot of tile k has been recycled, i.e. before that warp has consumed tile k.
-        // Warp 0 accumulates into the accumulator that warp 2 initialises: it waits for `tinit` (warp 2's overwriting
-        // MMA has retired).
+        // tcgen05.mma issue is back-pressured by the tensor pipe (the issuing thread advances at the pipe's rate), and
+        // every step also costs its issuing thread a few hundred cycles the pipe cannot use (mbarrier waits, elect,
+        // commits): the pipe only stays busy while the OTHER warp is issuing during those gaps.  Warp `my` issues
+        // stream `my`; the streams are independent of each other except through the A tiles they share.
+        // mbarrier waits only see the PARITY of a phase, so a warp must observe EVERY use of a barrier it ever waits
+        // on: both warps release every A tile (emptyA counts 2) -- with tcgen05.commit if they multiply it, else
+        // (stream 1, chunks below kcB) by waiting for fullA and arriving directly.
         const int my = warp - W_MMA;
         // The whole warp walks the loop, so every address, descriptor and flag is warp-uniform and lives in
         // uniform registers; one elected lane issues the tcgen05 instructions.
-        const uint32_t a0 = desc_lo(smem_base), b0d = desc_lo(b_ring);
+        constexpr int NSBm_max = CF::NSB0 > CF::NSB1 ? CF::NSB0 : CF::NSB1;
+        (void)NSBm_max;
+        const int nsb_my = my ? CF::NSB1 : CF::NSB0;                            // depth of this stream's B ring
+        const uint32_t slot0 = my ? uint32_t(CF::NSB0) : 0u;                     // its first slot / barrier
+        const uint32_t a0 = desc_lo(smem_base), b0d = desc_lo(b_ring + slot0 * CF::B_STAGE);
+        const uint32_t fullBm = fullB + 8 * slot0, emptyBm = emptyB + 8 * slot0;
         uint32_t seqA = 0;                                   // A tiles consumed so far (ring sequence number)
-        uint32_t sb = 0;                                     // B ring slot of the current step (shared, walk order)
-        uint32_t mb = 0, phm = 0;                            // this warp's own full-barrier cursor and its phase
+        uint32_t sb = 0, phb = 0;                            // this stream's B ring cursor
         uint32_t acc_it = 0;
-        uint32_t tin[2] = {0, 0};                            // tinit phases completed so far on each TMEM buffer
-        const uint32_t fullBm = fullB + 8 * uint32_t(my) * NSB;
         PROF_DECL;
         const bool prof = blockIdx.x == 0 && lane == 0;
         (void)prof;
@@ -817,54 +842,37 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 for (int p = 0; p < NPAIR; ++p) {
                     const int blk0 = pair_b0(p), blk1 = pair_b1(p);
                     const int kcA = first_chunk(blk0), kcB = blk1 >= 0 ? first_chunk(blk1) : NKC;
-                    // accumulators are handed out round-robin in completion order: b1 (if any), then b0
-                    const uint32_t acc1 = acc_it, acc0 = acc_it + (blk1 >= 0 ? 1u : 0u);
-                    acc_it = acc0 + 1;
-                    const uint32_t seq0 = seqA;                  // ring sequence number of chunk NKC-1
-                    seqA += uint32_t(NKC - kcA);
-                    // a pair of two blocks hands accumulator 0 from warp 2 to warp 0: one tinit phase on its buffer
-                    uint32_t tin_par = 0;
-                    if (B2_ISSUE3 && blk1 >= 0) { tin_par = tin[acc0 & 1] & 1; ++tin[acc0 & 1]; }
-                    walk_pair(NKC, kcA, kcB, GS, [&](int kc, int tgt, bool first_use, bool last_use) {
-                        (void)last_use;
+                    // accumulators are handed out in the order b1 (if any), then b0
+                    const uint32_t acc = my ? acc_it : acc_it + (blk1 >= 0 ? 1u : 0u);
+                    acc_it += blk1 >= 0 ? 2u : 1u;
+                    const uint32_t buf = acc & 1;
+                    const uint32_t d_tmem = tmem_base + buf * UMMA_N;
+                    const int kbase = my ? kcB : kcA;
+                    const int myblk = my ? blk1 : blk0;
+#pragma unroll 1
+                    for (int kc = NKC - 1; kc >= kcA; --kc, ++seqA) {
                         PROF_T0();
-                        const int owner = step_owner(tgt, kc, kcB);
-                        const uint32_t seq = seq0 + uint32_t(NKC - 1 - kc);
-                        const uint32_t sa = seq % NSA, pha = (seq / NSA) & 1;
-                        if (owner != my) {
-                            // A tile this warp never multiplies (above kcB: warp 0; below: warps 1 and 2) is released on its
-                            // first step of the walk -- after its phase is complete, so that the arrival cannot land in an
-                            // earlier phase
-                            const bool uses_tile = kc >= kcB ? my == 1 || my == (B2_ISSUE3 ? 2 : 0) : my == 0;
-                            if (first_use && !uses_tile) {
-                                mbar_wait(fullA + 8 * sa, pha);
-                                if (elect_one_sync()) mbar_arrive(emptyA + 8 * sa);
-                                __syncwarp();
-                                PROF_ADD(8 * my + 5, prof);
-                            }
-                            if (++sb == NSB) sb = 0;
-                            return;
+                        const uint32_t sa = seqA % NSA, pha = (seqA / NSA) & 1;
+                        if (my == 1 && kc < kcB) {
+                            // a tile only block b0 uses: released after its phase is complete, so that the arrival
+                            // cannot land in an earlier phase
+                            mbar_wait(fullA + 8 * sa, pha);
+                            if (elect_one_sync()) mbar_arrive(emptyA + 8 * sa);
+                            __syncwarp();
+                            PROF_ADD(8 * my + 5, prof);
+                            continue;
                         }
-                        const uint32_t acc = tgt ? acc1 : acc0;
-                        const uint32_t buf = acc & 1;
-                        const uint32_t use_par = (acc >> 1) & 1;
                         // first MMA of this accumulator: have the synthesis warps read its previous contents?
-                        if (kc == NKC - 1) mbar_wait(tempty + 8 * buf, use_par ^ 1);
-                        // first step of warp 0 into an accumulator that warp 2 has worked on: all of warp 2's MMAs must have
-                        // retired, because warp 0's commits are what declares the columns of its chunks final
-                        if (B2_ISSUE3 && my == 0 && kc == kcB - 1 && kcB < NKC) mbar_wait(tinit + 8 * buf, tin_par);
+                        if (kc == NKC - 1) mbar_wait(tempty + 8 * buf, ((acc >> 1) & 1) ^ 1);
                         PROF_ADD(8 * my + 1, prof);
-                        const uint32_t d_tmem = tmem_base + buf * UMMA_N;
-                        const int kbase = tgt ? kcB : kcA;
-                        // columns of this block that chunk kc can reach (lower triangle): w, N = 2w
+                        // columns of this block that chunk kc can reach (lower triangle): w
                         const int w = min(NB, KCH * (kc - kbase + 1));
                         // Every chunk signals tdone exactly once per use of its ring slot: on the step that makes its
                         // own columns final (the block that contains it), or -- for a chunk above both blocks of the
-                        // pair, whose columns belong to another pair -- on the b0 step.
+                        // pair, whose columns belong to another pair -- on the step of stream 0.
                         const int cblk = (kc * KCH) / NB;
-                        const bool own = cblk == (tgt ? blk1 : blk0);
-                        const bool signal_done = own || (tgt == 0 && cblk != blk0 && cblk != blk1);
-                        mbar_wait(fullBm + 8 * mb, phm);
+                        const bool signal_done = cblk == myblk || (my == 0 && cblk != blk0 && cblk != blk1);
+                        mbar_wait(fullBm + 8 * sb, phb);
                         PROF_ADD(8 * my + 2, prof);
                         mbar_wait(fullA + 8 * sa, pha);
                         PROF_ADD(8 * my + 3, prof);
@@ -874,19 +882,36 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                         const uint32_t a2 = a1 + (CF::NSPLIT - 1) * (A_TILE >> 4), b2 = b1 + (CF::NSPLIT - 1) * (CF::B_TILE >> 4);
                         const uint32_t first = kc != NKC - 1 ? 1u : 0u;    // 0: the first MMA overwrites the accumulator
                         if (elect_one_sync()) {
+#ifdef B2_ABL_NOMMA
+                            if (false) {
+#else
                             if (PASSES == 4) {
-                                // row = [f1 | f2] (A) resp. [g1 | g2] (B), 64 B each = 2 K-steps of 16 halfs:
-                                // f1*g1 + f1*g2 + f2*g1
-                                const uint32_t idh = idesc_f16(TILE_G, 2 * w);
-#pragma unroll
-                                for (uint32_t ks = 0; ks < 2; ++ks) {
-                                    const uint32_t adv = ks * 2;               // (32 B) >> 4
-                                    // the f1 slice of A is read from shared memory once for both products
-                                    umma_f16_afill(d_tmem, desc64(a1 + adv), desc64(b1 + adv), idh, ks > 0 ? 1u : first);
-                                    umma_f16_alastuse(d_tmem, desc64(a1 + adv), desc64(b1 + 4 + adv), idh, 1u);
-                                    umma_bf16(d_tmem, desc64(a1 + 4 + adv), desc64(b1 + adv), idh, 1u);
-                                }
+#endif
+                                // rows = [x1 Re | x1 Im | x2 Re | x2 Im] of the chunk's 16 microphones, 32 B (K = 16 halfs)
+                                // each; x = f (A: steering) resp. g (B: matrix); three products f1 g1 + f1 g2 + f2 g1:
+                                //   Re T += fr gr^T + fi gi^T,   Im T += fr gi^T + (-fi) gr^T
+                                // The A slice of a pair of MMAs is read from shared memory once (collector).
+                                const uint32_t idp = idesc_f16(TILE_G, w), idn = idp | IDESC_NEGATE_A;
+                                const uint32_t d_re = d_tmem, d_im = d_tmem + NB;
+                                const uint64_t f1r = desc64(a1), f1i = desc64(a1 + 2), f2r = desc64(a1 + 4), f2i = desc64(a1 + 6);
+                                const uint64_t g1r = desc64(b1), g1i = desc64(b1 + 2), g2r = desc64(b1 + 4), g2i = desc64(b1 + 6);
+                                umma_f16_afill(d_re, f1r, g1r, idp, first);
+                                umma_f16_alastuse(d_re, f1r, g2r, idp, 1u);
+                                umma_f16_afill(d_im, f1r, g1i, idp, first);
+                                umma_f16_alastuse(d_im, f1r, g2i, idp, 1u);
+                                umma_f16_afill(d_re, f1i, g1i, idp, 1u);
+                                umma_f16_alastuse(d_re, f1i, g2i, idp, 1u);
+                                umma_f16_afill(d_im, f1i, g1r, idn, 1u);
+                                umma_f16_alastuse(d_im, f1i, g2r, idn, 1u);
+                                umma_f16_afill(d_re, f2r, g1r, idp, 1u);
+                                umma_f16_alastuse(d_im, f2r, g1i, idp, 1u);
+                                umma_bf16(d_re, f2i, g1i, idp, 1u);
+                                umma_bf16(d_im, f2i, g1r, idn, 1u);
+#ifdef B2_ABL_NOMMA
+                            } else if (false) {
+#else
                             } else {
+#endif
                                 const uint32_t idesc = idesc_tf32(TILE_G, 2 * w);
 #pragma unroll
                                 for (uint32_t ks = 0; ks < 4; ++ks) {          // UMMA K = 8 tf32 = 32 bytes
@@ -904,16 +929,13 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                             // tcgen05.commit: the barriers are signalled when the MMAs issued so far retire
                             if (signal_done) umma_commit(tdone + 8 * sa);      // columns of chunk kc are final -> reduction
                             umma_commit(emptyA + 8 * sa);                      // this warp is done with the A tile
-                            umma_commit(emptyB + 8 * sb);
-                            // warp 2's last step of this accumulator: warp 0 continues when it has retired
-                            if (B2_ISSUE3 && my == 2 && kc == kcB) umma_commit(tinit + 8 * buf);
+                            umma_commit(emptyBm + 8 * sb);
                         }
                         __syncwarp();
                         PROF_ADD(8 * my + 4, prof);
                         PROF_CNT(8 * my + 6, prof);
-                        if (++sb == NSB) sb = 0;
-                        if (++mb == NSB) { mb = 0; phm ^= 1; }
-                    });
+                        if (++sb == uint32_t(nsb_my)) { sb = 0; phb ^= 1; }
+                    }
                 }
             }
         }
@@ -921,33 +943,38 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         if (prof) atomicAdd(&g_map_prof[8 * my], (unsigned long long)(clock64() - t_role0));
 #endif
     } else {
-        // =========================== B operand loader (one thread) ===========================
-        if (lane == 0) {
+        // =========================== B operand loaders (one thread per stream) ===========================
+        const int st = warp - (W_MMA + 2);                   // stream 0: blocks b0, stream 1: blocks b1
+        const int nsb_my = st ? CF::NSB1 : CF::NSB0;
+        if (lane == 0 && nsb_my > 0) {
+            const uint32_t slot0 = st ? uint32_t(CF::NSB0) : 0u;
+            const uint32_t ring = b_ring + slot0 * CF::B_STAGE, fullBm = fullB + 8 * slot0, emptyBm = emptyB + 8 * slot0;
             uint32_t sb = 0, phb = 0;
-            uint32_t mbw[3] = {0, 0, 0};                     // per issue warp: its next full barrier
             const size_t bin_bytes = size_t(NBLK) * NKC * CF::NSPLIT * CF::B_TILE;
             for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
                 B2_UNIT_DECODE
                 (void)tile;
                 for (int fi = f_begin; fi < f_end; ++fi) {
                     for (int p = 0; p < NPAIR; ++p) {
-                        const int blk0 = pair_b0(p), blk1 = pair_b1(p);
-                        const int kcA = first_chunk(blk0), kcB = blk1 >= 0 ? first_chunk(blk1) : NKC;
-                        // the tiles are consumed in exactly the order of the MMA warp's walk
-                        walk_pair(NKC, kcA, kcB, GS, [&](int kc, int tgt, bool, bool) {
-                            const int blk = tgt ? blk1 : blk0;
-                            const int w = min(NB, KCH * (kc - (tgt ? kcB : kcA) + 1));
-                            const uint32_t bytes = uint32_t(2 * w) * 128;          // first 2w rows of each image
-                            const int owner = step_owner(tgt, kc, kcB);
-                            const uint32_t fb = fullB + 8 * (uint32_t(owner) * NSB + mbw[owner]);
-                            if (++mbw[owner] == uint32_t(NSB)) mbw[owner] = 0;
-                            mbar_wait(emptyB + 8 * sb, phb ^ 1);
+                        const int blk = st ? pair_b1(p) : pair_b0(p);
+                        if (blk < 0) continue;
+                        const int kbase = first_chunk(blk);
+                        // the tiles are consumed in exactly the order of the issue warp's walk
+                        for (int kc = NKC - 1; kc >= kbase; --kc) {
+                            const int w = min(NB, KCH * (kc - kbase + 1));
+                            const uint32_t bytes = uint32_t(CF::PLANAR ? w : 2 * w) * 128;   // the rows of the first w columns of each image
+                            mbar_wait(emptyBm + 8 * sb, phb ^ 1);
                             const unsigned char *src = op + size_t(fi) * bin_bytes + (size_t(blk) * NKC + kc) * (CF::NSPLIT * CF::B_TILE);
-                            mbar_arrive_expect_tx(fb, CF::NSPLIT * bytes);
-                            bulk_g2s(b_ring + sb * CF::B_STAGE, src, bytes, fb);
-                            if (CF::NSPLIT == 2) bulk_g2s(b_ring + sb * CF::B_STAGE + CF::B_TILE, src + CF::B_TILE, bytes, fb);
-                            if (++sb == NSB) { sb = 0; phb ^= 1; }
-                        });
+#ifdef B2_ABL_NOLOAD
+                            (void)src; (void)bytes; (void)ring;
+                            mbar_arrive(fullBm + 8 * sb);
+#else
+                            mbar_arrive_expect_tx(fullBm + 8 * sb, CF::NSPLIT * bytes);
+                            bulk_g2s(ring + sb * CF::B_STAGE, src, bytes, fullBm + 8 * sb);
+                            if (CF::NSPLIT == 2) bulk_g2s(ring + sb * CF::B_STAGE + CF::B_TILE, src + CF::B_TILE, bytes, fullBm + 8 * sb);
+#endif
+                            if (++sb == uint32_t(nsb_my)) { sb = 0; phb ^= 1; }
+                        }
                     }
                 }
             }
@@ -988,47 +1015,67 @@ __global__ void das_bin_scale_kernel(const double2 *__restrict__ csm, int M, int
     }
 }
 
-// One thread per 16-byte chunk of an operand image: (bin, column block, K chunk, row, chunk j).
+// One thread per row of an operand image: (bin, column block, K chunk, row).
 template <int NB, int PASSES>
 __global__ void das_prepare_tc_kernel(const double2 *__restrict__ csm, int M, int bin0, double gain, int remove_diag,
                                       unsigned char *__restrict__ op, int NKC, int NBLK,
                                       const float *__restrict__ bin_scale) {
     using CF = TcCfg<NB, PASSES>;
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;       // 0 .. 2NB-1
-    if (row >= CF::UMMA_N) return;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;       // 0 .. B_ROWS-1
+    if (row >= CF::B_ROWS) return;
     const int kc = blockIdx.y % NKC, nbk = blockIdx.y / NKC;
     const int fi = blockIdx.z;
-    const bool imag_row = row & 1;                                // rows alternate Re T / Im T of column n
-    const int n = nbk * NB + (row >> 1);
     unsigned char *tile = op + ((size_t(fi) * NBLK + nbk) * NKC + kc) * size_t(CF::NSPLIT * CF::B_TILE);
     if (PASSES == 4) gain *= double(bin_scale[fi]);
+    // L[m, n] = 2 gain C[m, n] below the diagonal, gain C[n, n] (or 0) on it
+    auto lval = [&](int m, int n, double &lr, double &li) {
+        lr = 0.0; li = 0.0;
+        if (m < M && n < M && n <= m) {
+            const double2 c = csm[(int64_t(bin0 + fi) * M + m) * M + n];
+            if (n == m) { lr = remove_diag ? 0.0 : gain * c.x; }
+            else { lr = 2.0 * gain * c.x; li = 2.0 * gain * c.y; }
+        }
+    };
+    if constexpr (CF::PLANAR) {
+        // one row per matrix column n: [g1 Re (16 mics) | g1 Im | g2 Re | g2 Im], 32 bytes each (FP16 halves g1 + g2)
+        const int n = nbk * NB + row;
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {                          // 8 microphones = 16 bytes of every part
+            uint4 g1r, g1i, g2r, g2i;
+            uint32_t *q1r = reinterpret_cast<uint32_t *>(&g1r), *q1i = reinterpret_cast<uint32_t *>(&g1i);
+            uint32_t *q2r = reinterpret_cast<uint32_t *>(&g2r), *q2i = reinterpret_cast<uint32_t *>(&g2i);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double lr0, li0, lr1, li1;
+                lval(kc * KCH + 8 * h8 + 2 * j, n, lr0, li0);
+                lval(kc * KCH + 8 * h8 + 2 * j + 1, n, lr1, li1);
+                const float vr0 = float(lr0), vr1 = float(lr1), vi0 = float(li0), vi1 = float(li1);
+                const __half2 ar = __floats2half2_rn(vr0, vr1), ai = __floats2half2_rn(vi0, vi1);
+                const float2 fr = __half22float2(ar), fim = __half22float2(ai);
+                q1r[j] = pack_f16(ar);
+                q1i[j] = pack_f16(ai);
+                q2r[j] = pack_f16(__floats2half2_rn(vr0 - fr.x, vr1 - fr.y));
+                q2i[j] = pack_f16(__floats2half2_rn(vi0 - fim.x, vi1 - fim.y));
+            }
+            *reinterpret_cast<uint4 *>(tile + sw128_offset(row, 0 + h8)) = g1r;
+            *reinterpret_cast<uint4 *>(tile + sw128_offset(row, 2 + h8)) = g1i;
+            *reinterpret_cast<uint4 *>(tile + sw128_offset(row, 4 + h8)) = g2r;
+            *reinterpret_cast<uint4 *>(tile + sw128_offset(row, 6 + h8)) = g2i;
+        }
+        return;
+    }
+    const bool imag_row = row & 1;                                // rows alternate Re T / -Im T of column n
+    const int n = nbk * NB + (row >> 1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float v[4];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int m = kc * KCH + 2 * j + e;
-            double lr = 0.0, li = 0.0;
-            if (m < M && n < M && n <= m) {
-                const double2 c = csm[(int64_t(bin0 + fi) * M + m) * M + n];
-                if (n == m) { lr = remove_diag ? 0.0 : gain * c.x; }
-                else { lr = 2.0 * gain * c.x; li = 2.0 * gain * c.y; }
-            }
+            double lr, li;
+            lval(kc * KCH + 2 * j + e, n, lr, li);
             // real rows: (Re L, Im L) -> Re T ; imaginary rows: (-Im L, Re L) -> -Im T
             v[2 * e] = float(imag_row ? -li : lr);
             v[2 * e + 1] = float(imag_row ? lr : li);
-        }
-        if (PASSES == 4) {
-            // row = [g1 of the chunk's 16 mics | g2 of the 16 mics] (FP16): the 2 mics of this j are 8 bytes
-            // at byte offset 8*j of each 64-byte part
-            const __half2 a1 = __floats2half2_rn(v[0], v[1]), b1 = __floats2half2_rn(v[2], v[3]);
-            const float2 af = __half22float2(a1), bfl = __half22float2(b1);
-            const uint2 g1 = make_uint2(pack_f16(a1), pack_f16(b1));
-            const uint2 g2 = make_uint2(pack_f16(__floats2half2_rn(v[0] - af.x, v[1] - af.y)),
-                                        pack_f16(__floats2half2_rn(v[2] - bfl.x, v[3] - bfl.y)));
-            *reinterpret_cast<uint2 *>(tile + sw128_offset(row, j >> 1) + 8 * (j & 1)) = g1;
-            *reinterpret_cast<uint2 *>(tile + sw128_offset(row, 4 + (j >> 1)) + 8 * (j & 1)) = g2;
-            continue;
         }
         const int off = sw128_offset(row, j);
         const float4 hi = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
@@ -1052,7 +1099,7 @@ __global__ void das_prepare_tc_kernel(const double2 *__restrict__ csm, int M, in
 template <int PASSES> int64_t images_bytes(int M, int nbins) {
     const int NKC = (M + KCH - 1) / KCH;
     const int nb = tc_nb(M), NBLK = (M + nb - 1) / nb;
-    const int64_t btile = 2 * nb * 128;
+    const int64_t btile = (PASSES == 4 ? 1 : 2) * nb * 128;       // planar FP16x3 image: one row per column
     return int64_t(nbins) * NBLK * NKC * ((PASSES == 1 || PASSES == 4) ? 1 : 2) * btile;
 }
 // operand buffer = [images][one distance table of 128 x Mk floats per persistent CTA][per-bin scales]
@@ -1069,7 +1116,7 @@ int launch_prepare(const void *csm, int M, int bin0, int nbins, int remove_diag,
     using CF = TcCfg<NB, PASSES>;
     const int NKC = (M + KCH - 1) / KCH, NBLK = (M + NB - 1) / NB;
     const double gain = remove_diag ? double(M) / double(M - 1) : 1.0;
-    dim3 grid((CF::UMMA_N + 127) / 128, NKC * NBLK, nbins);
+    dim3 grid((CF::B_ROWS + 127) / 128, NKC * NBLK, nbins);
     float *scales = scales_ptr<PASSES>(op, M, nbins);
     if (PASSES == 4) {
         das_bin_scale_kernel<<<nbins, 256, 0, st>>>((const double2 *)csm, M, bin0, gain, remove_diag, scales);

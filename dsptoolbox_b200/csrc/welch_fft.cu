@@ -233,8 +233,11 @@ __device__ __forceinline__ void stockham_all(cx<T> *s, const cx<T> *__restrict__
     }
 }
 
+#ifndef B2_FFT_MINB
+#define B2_FFT_MINB 1
+#endif
 template <typename T, int LOG2NC>
-__global__ void __launch_bounds__(Geo<T, LOG2NC>::NT)
+__global__ void __launch_bounds__(Geo<T, LOG2NC>::NT, B2_FFT_MINB)
 welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframes,
                   const T *__restrict__ window, const cx<T> *__restrict__ tw, int detrend,
                   T scale, cx<T> *__restrict__ X, int M, int64_t Kp, int vec_ok) {

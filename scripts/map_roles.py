@@ -21,13 +21,15 @@ for rep in range(2):
     torch.cuda.synchronize()
     lib.b2_debug_map_profile(buf)
 v = list(buf)
-for w in (0, 1):
+for w in (0, 1, 2):
     b = v[8 * w: 8 * w + 8]
     steps = max(1, b[6])
     print(f"issue warp {w}: total {b[0]} cyc, steps {b[6]}; per step: tempty {b[1]/steps:.0f} fullB {b[2]/steps:.0f} fullA {b[3]/steps:.0f} "
-          f"issue+commit {b[4]/steps:.0f}; release steps of the other stream {b[5]} cyc total ({b[5]/max(1,b[0])*100:.1f} %)")
+          f"issue+commit {b[4]/steps:.0f}; releases of A tiles it does not multiply {b[5]} cyc total ({b[5]/max(1,b[0])*100:.1f} %)")
+    if b[0] == 0:
+        continue
     print(f"   shares: tempty {b[1]/b[0]*100:.1f}% fullB {b[2]/b[0]*100:.1f}% fullA {b[3]/b[0]*100:.1f}% issue {b[4]/b[0]*100:.1f}% release {b[5]/b[0]*100:.1f}%")
-b = v[16:24]
+b = v[24:32]
 ch = max(1, b[6])
 print(f"synthesis warp 0 (group 0): total {b[0]} cyc, own chunks {b[6]}; per own chunk: wait tdone {b[1]/ch:.0f} ld+fma {b[2]/ch:.0f} wait emptyA {b[3]/ch:.0f} "
       f"synth+stores {b[4]/ch:.0f} fence+arrive {b[5]/ch:.0f}; table {b[7]} cyc total")

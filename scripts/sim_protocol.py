@@ -2,18 +2,17 @@
 deadlocks and phase-aliasing bugs before they cost GPU time.
 
 Roles of das_map_tc_kernel: NG synthesis/reduction warp groups that take the chunks round-robin (group j
-synthesises chunks j, j + NG, ...; before it synthesises its next chunk it passes all chunks up to its previous
-one -- reducing that one after waiting for its `tdone`, signalling `tempty` when a block's lowest chunk goes
-by), the B loader, and the three MMA issue warps (W1: stream of block b1; W2: the steps of block b0 on the chunks it
-shares with b1; W0: the rest of b0's stream, accumulating behind W2's first step -- `tinit`).  A B tile is waited
-for and released by its step's warp only.
+synthesises chunks j, j + NG, ...; before it synthesises chunk i it passes all chunks up to its own chunk
+i - DLAG NG -- reducing that one after waiting for its `tdone`, signalling `tempty` when a block's lowest chunk
+goes by), two MMA issue warps (W0: stream of block b0 = every chunk of the pair; W1: stream of block b1 = the chunks
+from kcB up, plus the release of the tiles only b0 uses) and one B loader per stream with its own ring.
 Barriers only know the PARITY of a phase, exactly like mbarrier.try_wait.parity, so a role that gets a whole
 ring round away from its partner is modelled faithfully (it passes or blocks on the wrong phase).  Besides
 deadlock the model checks that every consumer sees the tile it expects, that the columns of a chunk are final
 when a synthesis warp reads them (every step that writes them has been issued) and that an accumulator is not
 overwritten before every synthesis warp has read all of its columns.
 
-usage: python scripts/sim_protocol.py M NB NSA NSB LAG NG nbins [share=1] [runs=300]
+usage: python scripts/sim_protocol.py M NB NSA NSB0 NSB1 NG nbins [share=1] [runs=300] [DLAG=1]
 """
 import random
 import sys
@@ -36,26 +35,7 @@ class Bar:
         return (self.phase & 1) != parity
 
 
-def walk_pair(NKC, kcA, kcB, LAG):
-    """(kc, target, first_use_of_A, last_use_of_A) -- mirrors walk_pair in das_map_tc.cu"""
-    n1, n0 = NKC - kcB, NKC - kcA
-    lag = min(n1, LAG)
-    for i in range(n0 + lag):
-        if i < n1:
-            yield (NKC - 1 - i, 1, True, False)
-        j = i - lag
-        if j >= 0:
-            yield (NKC - 1 - j, 0, j >= n1, True)
-
-
-ISSUE3 = False     # False: warp 0 issues the whole stream of block b0; True: warp 2 takes the chunks it shares with b1
-
-
-def step_owner(tgt, kc, kcB):
-    return 1 if tgt else (2 if (ISSUE3 and kc >= kcB) else 0)
-
-
-def main(M, NB, NSA, NSB, LAG, NG, nbins, share=True, seed=0, stall=0.9, quiet=True, units=2):
+def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet=True, units=2, DLAG=1):
     KCH = 16
     NKC = (M + KCH - 1) // KCH
     NBLK = (M + NB - 1) // NB
@@ -63,12 +43,12 @@ def main(M, NB, NSA, NSB, LAG, NG, nbins, share=True, seed=0, stall=0.9, quiet=T
     b0 = lambda p: 2 * p if share else p
     b1 = lambda p: (2 * p + 1) if (share and 2 * p + 1 < NBLK) else -1
     fc = lambda b: b * NB // KCH
-    assert NG == 1 or 2 * NG <= NSA, "a ring slot could complete a further use while a group still waits for it"
-    fullA = [Bar(1) for _ in range(NSA)]; emptyA = [Bar(3) for _ in range(NSA)]      # one arrival per owning group / every issue warp releases
-    fullB = [[Bar(1) for _ in range(NSB)] for _ in range(3)]                          # one set of full barriers per issue warp
-    emptyB = [Bar(1) for _ in range(NSB)]                                              # released by the step's issue warp
-    tdone = [Bar(1) for _ in range(NSA)]; tempty = [Bar(NG), Bar(NG)]; tinit = [Bar(1), Bar(1)]
-    inA = [None] * NSA; inB = [None] * NSB              # what the producers last put into a stage
+    assert NG == 1 or (DLAG + 1) * NG <= NSA, "a ring slot could complete a further use while a group still waits for it"
+    NSBs = (NSB0, NSB1)
+    fullA = [Bar(1) for _ in range(NSA)]; emptyA = [Bar(2) for _ in range(NSA)]      # one arrival per owning group / both issue warps release
+    fullB = [[Bar(1) for _ in range(n)] for n in NSBs]; emptyB = [[Bar(1) for _ in range(n)] for n in NSBs]   # one ring per stream
+    tdone = [Bar(1) for _ in range(NSA)]; tempty = [Bar(NG), Bar(NG)]
+    inA = [None] * NSA; inB = [[None] * n for n in NSBs]   # what the producers last put into a stage
     issued = {}                   # accumulator sequence number -> set of chunks multiplied into it
     readers = {}                  # accumulator sequence number -> groups that have finished reading it
     buf_owner = [None, None]      # accumulator currently held by a TMEM buffer
@@ -108,8 +88,8 @@ def main(M, NB, NSA, NSB, LAG, NG, nbins, share=True, seed=0, stall=0.9, quiet=T
                 e += 1
 
             i = j
-            while i < total + NG:
-                upto = min(i - NG, total - 1)
+            while i < total + DLAG * NG:
+                upto = min(i - DLAG * NG, total - 1)
                 while e <= upto:
                     yield from pass_chunk()
                 if i < total:
@@ -123,74 +103,61 @@ def main(M, NB, NSA, NSB, LAG, NG, nbins, share=True, seed=0, stall=0.9, quiet=T
                 yield from pass_chunk()
             seq_base += total
 
-    def loader():
+    def loader(st):
         sb = phb = 0; q = 0
-        mbw = [0, 0, 0]
         for _u in range(units):
             for fi in range(nbins):
                 for p in range(NPAIR):
-                    kcA = fc(b0(p)); kcB = fc(b1(p)) if b1(p) >= 0 else NKC
-                    for (kc, tgt, fu, lu) in walk_pair(NKC, kcA, kcB, LAG):
-                        owner = step_owner(tgt, kc, kcB)
-                        while not emptyB[sb].done(phb ^ 1): yield ("loader wait emptyB", sb)
-                        inB[sb] = q; q += 1
-                        fullB[owner][mbw[owner]].arrive()
-                        mbw[owner] = (mbw[owner] + 1) % NSB
+                    blk = b1(p) if st else b0(p)
+                    if blk < 0: continue
+                    for kc in range(NKC - 1, fc(blk) - 1, -1):
+                        while not emptyB[st][sb].done(phb ^ 1): yield (f"loader{st} wait emptyB", sb)
+                        inB[st][sb] = q; q += 1
+                        fullB[st][sb].arrive()
                         sb += 1
-                        if sb == NSB: sb = 0; phb ^= 1
+                        if sb == NSBs[st]: sb = 0; phb ^= 1
                         yield None
 
     def issuer(my):
-        sb = 0; mb = phm = 0; seqA = 0; acc_it = 0; q = 0
-        tin = [0, 0]
+        sb = phb = 0; seqA = 0; acc_it = 0; q = 0
         for _u in range(units):
             for fi in range(nbins):
                 for p in range(NPAIR):
                     blk0, blk1 = b0(p), b1(p)
                     kcA = fc(blk0); kcB = fc(blk1) if blk1 >= 0 else NKC
-                    acc1 = acc_it; acc0 = acc_it + (1 if blk1 >= 0 else 0); acc_it = acc0 + 1
-                    seq0 = seqA; seqA += NKC - kcA
-                    tin_par = 0
-                    if ISSUE3 and blk1 >= 0:
-                        tin_par = tin[acc0 & 1] & 1; tin[acc0 & 1] += 1
-                    for (kc, tgt, fu, lu) in walk_pair(NKC, kcA, kcB, LAG):
-                        i = NKC - 1 - kc
-                        seq = seq0 + i; sa = seq % NSA; pha = (seq // NSA) & 1
-                        acc = acc1 if tgt else acc0; buf = acc & 1; use_par = (acc >> 1) & 1
-                        owner = step_owner(tgt, kc, kcB)
-                        if owner != my:
-                            uses_tile = (my == 1 or my == (2 if ISSUE3 else 0)) if kc >= kcB else (my == 0)
-                            if fu and not uses_tile:                        # release of a tile this warp never multiplies
-                                while not fullA[sa].done(pha): yield (f"W{my} wait fullA (release)", sa, pha, kc)
-                                assert inA[sa] == seq, f"W{my} releases A tile {inA[sa]} instead of {seq}"
-                                emptyA[sa].arrive()
+                    acc = acc_it if my else acc_it + (1 if blk1 >= 0 else 0)
+                    acc_it += 2 if blk1 >= 0 else 1
+                    buf = acc & 1; use_par = (acc >> 1) & 1
+                    myblk = blk1 if my else blk0
+                    for kc in range(NKC - 1, kcA - 1, -1):
+                        sa = seqA % NSA; pha = (seqA // NSA) & 1
+                        if my == 1 and kc < kcB:                            # release of a tile only b0 uses
+                            while not fullA[sa].done(pha): yield (f"W{my} wait fullA (release)", sa, pha, kc)
+                            assert inA[sa] == seqA, f"W{my} releases A tile {inA[sa]} instead of {seqA}"
+                            emptyA[sa].arrive()
                         else:
-                            if i == 0:                                      # previous contents read by everybody?
+                            if kc == NKC - 1:                               # previous contents read by everybody?
                                 while not tempty[buf].done(use_par ^ 1): yield (f"W{my} wait tempty", buf)
                                 prev = buf_owner[buf]
                                 assert prev is None or len(readers.get(prev, ())) == NG, f"accumulator {prev} overwritten before it was read"
                                 buf_owner[buf] = acc
-                            if ISSUE3 and my == 0 and kc == kcB - 1 and kcB < NKC:     # continue behind W2's last step
-                                while not tinit[buf].done(tin_par): yield (f"W{my} wait tinit", buf)
-                                assert buf_owner[buf] == acc and set(range(kcB, NKC)) <= issued.get(acc, set()), "W0 continues an unfinished accumulator"
-                            while not fullB[my][mb].done(phm): yield (f"W{my} wait fullB", mb, phm, kc)
-                            assert inB[sb] == q, f"W{my} sees B tile {inB[sb]} instead of {q}"
+                            while not fullB[my][sb].done(phb): yield (f"W{my} wait fullB", sb, phb, kc)
+                            assert inB[my][sb] == q, f"W{my} sees B tile {inB[my][sb]} instead of {q}"
                             while not fullA[sa].done(pha): yield (f"W{my} wait fullA", sa, pha, kc)
-                            assert inA[sa] == seq, f"W{my} sees A tile {inA[sa]} instead of {seq}"
+                            assert inA[sa] == seqA, f"W{my} sees A tile {inA[sa]} instead of {seqA}"
                             issued.setdefault(acc, set()).add(kc)
                             cblk = kc * KCH // NB
-                            own = cblk == (blk1 if tgt else blk0)
-                            if own or (tgt == 0 and cblk != blk0 and cblk != blk1):
+                            if cblk == myblk or (my == 0 and cblk != blk0 and cblk != blk1):
                                 tdone[sa].arrive()
-                            emptyA[sa].arrive(); emptyB[sb].arrive()
-                            if ISSUE3 and my == 2 and kc == kcB: tinit[buf].arrive()
-                            mb += 1
-                            if mb == NSB: mb = 0; phm ^= 1
-                        q += 1; sb += 1
-                        if sb == NSB: sb = 0
+                            emptyA[sa].arrive(); emptyB[my][sb].arrive()
+                            q += 1; sb += 1
+                            if sb == NSBs[my]: sb = 0; phb ^= 1
+                        seqA += 1
                         yield None
 
-    roles = {"loader": loader(), "W0": issuer(0), "W1": issuer(1), "W2": issuer(2)}
+    roles = {"loader0": loader(0), "W0": issuer(0), "W1": issuer(1)}
+    if NSB1 > 0:
+        roles["loader1"] = loader(1)
     for j in range(NG):
         roles[f"G{j}"] = group(j)
     rng = random.Random(seed)
@@ -218,15 +185,16 @@ def main(M, NB, NSA, NSB, LAG, NG, nbins, share=True, seed=0, stall=0.9, quiet=T
 
 if __name__ == "__main__":
     a = sys.argv
-    M, NB, NSA, NSB, LAG, NG, nbins = (int(x) for x in a[1:8])
+    M, NB, NSA, NSB0, NSB1, NG, nbins = (int(x) for x in a[1:8])
     share = len(a) < 9 or a[8] != "0"
+    dlag = int(a[10]) if len(a) > 10 else 1
     bad = 0
     for seed in range(int(a[9]) if len(a) > 9 else 300):
         try:
-            ok = main(M, NB, NSA, NSB, LAG, NG, nbins, share, seed)
+            ok = main(M, NB, NSA, NSB0, NSB1, NG, nbins, share, seed, DLAG=dlag)
         except AssertionError as e:
             print("BUG (seed %d):" % seed, e); ok = False
         if not ok:
             bad += 1
             if bad >= 3: break
-    print(f"M={M} NB={NB} NSA={NSA} NSB={NSB} LAG={LAG} NG={NG} share={share}: failures {bad}")
+    print(f"M={M} NB={NB} NSA={NSA} NSB={NSB0}+{NSB1} NG={NG} share={share}: failures {bad}")
