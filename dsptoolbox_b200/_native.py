@@ -36,6 +36,12 @@ PROTOTYPES = {
     "b2_csm_finalize": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_void_p]),
     "b2_welch_autopower": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_void_p]),
     "b2_auto_finalize": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_void_p]),
+    "b2_fft_plan_bytes": (c_int64, [c_int64]),
+    "b2_fft_work_bytes": (c_int64, [c_int64, c_int]),
+    "b2_fft_plan": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
+    "b2_rfft_any": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int64, c_int64, c_int, c_void_p, c_int,
+                            c_void_p, c_void_p, c_double, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "b2_csm_rank1": (c_int, [c_void_p, c_int, c_int64, c_double, c_int, c_int, c_void_p, c_void_p]),
     "b2_das_operand_bytes": (c_int64, [c_int, c_int, c_int]),
     "b2_das_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "b2_das_map": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_double, c_void_p, POINTER(c_double),

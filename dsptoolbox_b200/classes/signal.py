@@ -166,7 +166,12 @@ class Signal(MultichannelData):
     def _compute_csm_device(self, frame_range=None, reduce_fn=None):
         p = self._spectrum_parameters
         if self.spectrum_method != SpectrumMethod.WelchPeriodogram:
-            raise NotImplementedError("SpectrumMethod.FFT cross-spectral matrices are outside the accelerated path")
+            # reference signal.py:989-1002: the spectrum is taken with FFTBackward scaling, `_csm_fft` applies the
+            # requested one
+            assert frame_range is None and reduce_fn is None, "the single-FFT cross-spectral matrix is not sharded"
+            f, sp = _sm.spectrum_fft_device(self.time_data, self.sampling_rate_hz, SpectrumScaling.FFTBackward,
+                                            p["pad_to_fast_length"], p["smoothing"], None)
+            return f, _sm.csm_fft_device(sp, p["scaling"], None, self.sampling_rate_hz)
         return _sm.csm_welch_device(self.time_data, self.sampling_rate_hz, p["window_length_samples"],
                                     p["window_type"], p["overlap_percent"], p["detrend"], p["average"],
                                     p["scaling"], frame_range=frame_range, reduce_fn=reduce_fn)
@@ -195,12 +200,14 @@ class Signal(MultichannelData):
 
     # ---- explicitly out of scope -------------------------------------------------------------------
     def get_spectrum(self, force_computation: bool = False):
-        """(f, spectrum) with the Welch auto-spectrum of every channel, float64 (nb, channels) --
-        the WelchPeriodogram branch of reference signal.py:861-946.  The
-        single-FFT branch (arbitrary-length FFT, smoothing) is outside the accelerated path."""
-        if self.spectrum_method != SpectrumMethod.WelchPeriodogram:
-            raise NotImplementedError("SpectrumMethod.FFT spectra are outside the accelerated path")
+        """(f, spectrum): the Welch auto-spectrum of every channel, float64 (nb, channels), or -- SpectrumMethod.FFT --
+        the spectrum of the whole recording (complex128 for the amplitude scalings), reference signal.py:861-946
+        (SURVEY.md section 8f.3).  Fractional-octave smoothing is outside the accelerated path."""
         p = self._spectrum_parameters
+        if self.spectrum_method != SpectrumMethod.WelchPeriodogram:
+            f, sp = _sm.spectrum_fft_device(self.time_data, self.sampling_rate_hz, p["scaling"], p["pad_to_fast_length"],
+                                            p["smoothing"], None)
+            return f, sp.cpu().numpy()
         spec = _sm.welch_autospectra_device(self.time_data, self.sampling_rate_hz, p["window_length_samples"],
                                             p["window_type"], p["overlap_percent"], p["detrend"], p["average"],
                                             p["scaling"])

@@ -12,6 +12,19 @@ class Spectrum:
         self.frequency_vector_hz = frequency_vector_hz
         self.spectral_data = spectral_data
 
+    @staticmethod
+    def from_signal(sig, complex: bool = False) -> "Spectrum":
+        """From `sig.get_spectrum()` with the signal's own parameters (reference spectrum.py:56-88): the complex
+        spectrum, or its magnitude (square root of the power for the power scalings)."""
+        if complex:
+            assert sig.spectrum_scaling.outputs_complex_spectrum(sig.spectrum_method), (
+                "Method or scaling do not deliver a complex spectrum")
+        f, sp = sig.get_spectrum()
+        if complex:
+            assert np.iscomplexobj(sp), "Spectrum of signal is not complex"
+            return Spectrum(f, sp)
+        return Spectrum(f, np.abs(sp) if sig.spectrum_scaling.is_amplitude_scaling() else np.abs(sp) ** 0.5)
+
     @property
     def frequency_vector_hz(self):
         return self.__frequency_vector_hz

@@ -273,6 +273,26 @@ __global__ void auto_finalize_kernel(const double *__restrict__ P, int M, int nb
     out[i] = amplitude_sqrt ? sqrt(v) : v;
 }
 
+// CSM of ONE spectrum per channel (no averaging): csm[f][j][i] = X[f][j] conj(X[f][i]), the whole Hermitian matrix
+// written directly -- `_csm_fft` (_spectral_methods.py:374-443).  Scalings other than FFTBackward: DC and last bin
+// halved, times the conversion factor, element-wise principal sqrt for the amplitude scalings (:430-443).
+__global__ void csm_rank1_kernel(const double2 *__restrict__ X, int M, int64_t nb, double factor, int halve_edges,
+                                 int amplitude_sqrt, double2 *__restrict__ out) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t mm = int64_t(M) * M;
+    if (idx >= nb * mm) return;
+    const int64_t f = idx / mm;
+    const int r = int(idx - f * mm);
+    const int j = r / M, i = r - j * M;
+    const double2 a = X[f * M + j], b = X[f * M + i];
+    double2 v = make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);      // a conj(b)
+    if (i == j) v.y = 0.0;
+    if (halve_edges && (f == 0 || f == nb - 1)) { v.x *= 0.5; v.y *= 0.5; }
+    v.x *= factor; v.y *= factor;
+    if (amplitude_sqrt) v = (i == j) ? make_double2(sqrt(v.x), 0.0) : csqrt_principal(v);
+    out[idx] = v;
+}
+
 template <typename TIN>
 int launch_herk(const void *X, int M, int64_t Kp, int nb, int bin0, int nbins, void *S, int accumulate, cudaStream_t st) {
     using SM = HerkSmem<TIN>;
@@ -338,5 +358,17 @@ extern "C" int b2_auto_finalize(const void *P_dev, int M, int nb, double inv_fra
     auto_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const double *)P_dev, M, nb, inv_frames, factor, halve_edges, amplitude_sqrt, (double *)out_dev);
     B2_LAUNCH_OK("b2_auto_finalize");
+    return B2_OK;
+}
+
+extern "C" int b2_csm_rank1(const void *spectrum_dev, int M, int64_t nb, double factor, int halve_edges,
+                            int amplitude_sqrt, void *csm_out_dev, void *stream) {
+    B2_REQUIRE(spectrum_dev && csm_out_dev, B2_EINVAL, "b2_csm_rank1: null pointer");
+    B2_REQUIRE(M > 0 && nb > 0, B2_EINVAL, "b2_csm_rank1: bad M=%d / nb=%lld", M, (long long)nb);
+    const int64_t n = nb * int64_t(M) * M;
+    B2_REQUIRE((n + 255) / 256 <= 0x7fffffff, B2_EINVAL, "b2_csm_rank1: matrix too large for one launch");
+    csm_rank1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const double2 *)spectrum_dev, M, nb, factor, halve_edges, amplitude_sqrt, (double2 *)csm_out_dev);
+    B2_LAUNCH_OK("b2_csm_rank1");
     return B2_OK;
 }

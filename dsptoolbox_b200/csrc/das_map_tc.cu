@@ -74,7 +74,7 @@ constexpr int TILE_G = 128;
 constexpr int KCH = 16;                       // microphones per K chunk = 32 reals = one 128 B row
 constexpr int A_TILE = TILE_G * 128;          // bytes of one A operand image
 #ifndef B2_NG
-#define B2_NG 2
+#define B2_NG 3
 #endif
 static_assert(B2_NG >= 1 && B2_NG <= 4, "1..4 groups of 4 warps");
 
@@ -110,8 +110,8 @@ template <int NB, int PASSES> struct TcCfg {
 #ifdef B2_NSB0
     static constexpr int NSB0 = B2_NSB0, NSB1 = B2_NSB1;
 #else
-    static constexpr int NSB0 = !SHARE ? 2 : (B_STAGE <= 16 * 1024 ? 3 : 2);
-    static constexpr int NSB1 = !SHARE ? 0 : 2;
+    static constexpr int NSB0 = !SHARE ? 2 : (B_STAGE <= 16 * 1024 ? 4 : 2);
+    static constexpr int NSB1 = !SHARE ? 0 : (B_STAGE <= 16 * 1024 ? 3 : 2);
 #endif
     static constexpr int NSB = NSB0 + NSB1;
     static constexpr int NSA_RAW = (224 * 1024 - NSB * B_STAGE) / A_STAGE;
@@ -130,7 +130,7 @@ template <int NB, int PASSES> struct TcCfg {
     // the PARITY of a phase, so the ring slot of such a chunk must not be able to complete a further use meanwhile:
     // chunk c + NSA is only synthesised after chunk i when c + NSA > i, i.e. NSA >= (DLAG + 1) NG.
 #ifndef B2_DLAG
-#define B2_DLAG 3
+#define B2_DLAG 1
 #endif
     static constexpr int NG = (B2_DLAG + 1) * B2_NG <= NSA ? B2_NG : (2 * B2_NG <= NSA ? B2_NG : (NSA >= 4 ? 2 : 1));
     static constexpr int DLAG = (B2_DLAG + 1) * NG <= NSA ? B2_DLAG : ((NSA / NG - 1) >= 1 ? (NSA / NG - 1) : 1);
@@ -613,17 +613,19 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                         // accumulator of a block: Re T in columns [0, NB), Im T in [NB, 2 NB); hk = (Re h' of the 8
                         // microphone pairs, Im h' of them): P = sum Re T Re h' - Im T Im h'
                         const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N + 16u * ((e >> 10) & 7u);
+                        float tr[16], ti[16];                // Re T, Im T of the chunk's 16 microphones: both loads, one wait
+                        tmem_ld16(tcol, tr);
+                        tmem_ld16(tcol + NB, ti);
+                        tmem_ld_wait();
+                        float2 pi2 = make_float2(0.f, 0.f);
 #pragma unroll
-                        for (int hlf = 0; hlf < 2; ++hlf) {
-                            float t[16];
-                            tmem_ld16(tcol + hlf * NB, t);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)      // padded microphones have all-zero operand rows: T = 0, no bounds test
-                                pacc = __ffma2_rn(make_float2(t[2 * j], t[2 * j + 1]), hk[8 * hlf + j], pacc);
-                            if (hlf == 0) { pre.x += pacc.x + pacc.y; pacc = make_float2(0.f, 0.f); }
-                            else { pre.y += pacc.x + pacc.y; pacc = make_float2(0.f, 0.f); }
+                        for (int j = 0; j < 8; ++j) {        // padded microphones have all-zero operand rows: T = 0, no bounds test
+                            pacc = __ffma2_rn(make_float2(tr[2 * j], tr[2 * j + 1]), hk[j], pacc);
+                            pi2 = __ffma2_rn(make_float2(ti[2 * j], ti[2 * j + 1]), hk[8 + j], pi2);
                         }
+                        pre.x += pacc.x + pacc.y;
+                        pre.y += pi2.x + pi2.y;
+                        pacc = make_float2(0.f, 0.f);
                     } else {
                         const uint32_t tcol = tmem_base + lane_base + buf * UMMA_N + 32u * ((e >> 10) & 7u);
 #pragma unroll

@@ -94,6 +94,34 @@ def welch_frames(length: int, wl: int, step: int) -> tuple[int, int]:
 
 _twiddle_cache: dict = {}
 
+# Stage-1 temporaries (channel-major copy, spectra) and the map operand are multi-GB buffers that never leave the
+# engine: they are kept per (role, device) and reused while the size fits, instead of going back to torch's caching
+# allocator, whose block splitting turned the differently-sized requests of consecutive steps into cudaMalloc /
+# cudaFree cycles (+40 ms per step at 256 mics x 60 s).  `release_workspaces()` drops them.
+_workspaces: dict = {}
+
+
+def _workspace(role: str, nbytes: int, device):
+    torch = _torch()
+    key = (role, str(device))
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes or buf.numel() > 2 * nbytes + (64 << 20):
+        _workspaces.pop(key, None)
+        buf = None
+        buf = _workspaces[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return buf
+
+
+def _workspace_tensor(role: str, shape, dtype, device):
+    torch = _torch()
+    n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+    return _workspace(role, max(n, 16), device)[:n].view(dtype).reshape(shape)
+
+
+def release_workspaces():
+    """Free the engine's cached multi-GB temporaries (they are re-created on the next call)."""
+    _workspaces.clear()
+
 
 def _twiddles(wl: int, prec: int, device):
     torch = _torch()
@@ -281,12 +309,12 @@ def _csm_partial_sums(torch, lib, prec, device, x, length, wl, step, window, det
         Lp = (Kp - 1) * step + wl
         Lp += (-Lp) % 4
         timer.mark("h2d")
-        xc = torch.empty((M, Lp), dtype=rdt, device=device)
+        xc = _workspace_tensor("xc", (M, Lp), rdt, device)
         N.check(lib.b2_prepare_channels(N.ptr(xs), code, s_t, s_m, 0, t1 - t0, M, N.ptr(xc), Lp, prec, st),
                 "b2_prepare_channels")
         _count()
         timer.mark("k0_prepare")
-        X = torch.empty((nb, M, Kp), dtype=cdt, device=device)
+        X = _workspace_tensor("spectra", (nb, M, Kp), cdt, device)
         N.check(lib.b2_welch_rfft(N.ptr(xc), Lp, M, wl, step, nfr, N.ptr(win), N.ptr(tw), int(bool(detrend)),
                                   float(fft_scale), N.ptr(X), Kp, prec, st), "b2_welch_rfft")
         _count()
@@ -368,6 +396,116 @@ def frame_spectra(x, length: int, wl: int, step: int, window: np.ndarray, detren
     return out
 
 
+# --------------------------------------------------------------------------- large / arbitrary-length FFT
+_fft_plans: dict = {}
+
+
+def _fft_plan(n: int, device):
+    torch = _torch()
+    lib = N.lib()
+    key = (int(n), str(device))
+    plan = _fft_plans.get(key)
+    if plan is None:
+        nbytes = N.check(lib.b2_fft_plan_bytes(n), "b2_fft_plan_bytes")
+        plan = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        work = _workspace("fft_work", N.check(lib.b2_fft_work_bytes(n, 1), "b2_fft_work_bytes"), device)
+        N.check(lib.b2_fft_plan(n, N.ptr(plan), N.ptr(work), N.stream_handle()), "b2_fft_plan")
+        _count(3)
+        if len(_fft_plans) >= 8:
+            _fft_plans.pop(next(iter(_fft_plans)))
+        _fft_plans[key] = plan
+    return plan
+
+
+def rfft_rows(x_dev, n: int, scale: float = 1.0, batch_bytes: int = 6 << 30):
+    """np.fft.rfft(x, n=n, axis=0) * scale for a (L, M) float32/float64 CUDA tensor -> complex128 CUDA (n//2+1, M).
+    Any length n (cropping or zero-padding the L samples like numpy); channels are processed in groups that keep the
+    two work buffers under `batch_bytes`."""
+    torch = _torch()
+    lib = N.lib()
+    assert x_dev.is_cuda and x_dev.ndim == 2 and x_dev.dtype in (torch.float32, torch.float64)
+    device = x_dev.device
+    L, M = int(x_dev.shape[0]), int(x_dev.shape[1])
+    nb = n // 2 + 1
+    out = torch.empty((nb, M), dtype=torch.complex128, device=device)
+    with torch.cuda.device(device):
+        plan = _fft_plan(n, device)
+        per_row = N.check(lib.b2_fft_work_bytes(n, 1), "b2_fft_work_bytes")
+        group = max(1, min(M, batch_bytes // per_row))
+        code = N.F64 if x_dev.dtype == torch.float64 else N.F32
+        st, sb = x_dev.stride(0), x_dev.stride(1)
+        for m0 in range(0, M, group):
+            b = min(group, M - m0)
+            work = _workspace("fft_work", N.check(lib.b2_fft_work_bytes(n, b), "b2_fft_work_bytes"), device)
+            xs = x_dev[:, m0:m0 + b]
+            N.check(lib.b2_rfft_any(N.ptr(xs), code, st, sb, 0, b, L, n, b, None, 0, N.ptr(plan), N.ptr(work), float(scale),
+                                    N.ptr(out[:, m0:m0 + b]), M, 1, 0, N.stream_handle()), "b2_rfft_any")
+            _count()
+    return out
+
+
+def rfft_frames(xc, Lp: int, M: int, wl: int, step: int, n_frames: int, n: int, window, detrend: bool, scale: float,
+                batch_bytes: int = 6 << 30):
+    """Spectra of all frames for an FFT length n != wl (or beyond the shared-memory kernel): complex128 CUDA tensor
+    (n//2+1, n_frames, M) = np.fft.rfft(windowed [, de-meaned] frames, n=n, axis=0) of reference `_stft`
+    (_spectral_methods.py:257-263).  `xc` is the channel-major zero-padded copy (M, Lp) from b2_prepare_channels."""
+    torch = _torch()
+    lib = N.lib()
+    device = xc.device
+    nb = n // 2 + 1
+    out = torch.empty((nb, n_frames, M), dtype=torch.complex128, device=device)
+    win = torch.from_numpy(np.ascontiguousarray(window, dtype=np.float64)).to(device)
+    code = N.F64 if xc.dtype == torch.float64 else N.F32
+    with torch.cuda.device(device):
+        plan = _fft_plan(n, device)
+        per_row = N.check(lib.b2_fft_work_bytes(n, 1), "b2_fft_work_bytes")
+        ch_group = max(1, min(M, batch_bytes // (per_row * n_frames)))
+        for m0 in range(0, M, ch_group):
+            mc = min(ch_group, M - m0)
+            b = mc * n_frames
+            work = _workspace("fft_work", N.check(lib.b2_fft_work_bytes(n, b), "b2_fft_work_bytes"), device)
+            # row (m, k): input at m * Lp + k * step, output out[f][k][m0 + m]
+            N.check(lib.b2_rfft_any(N.ptr(xc[m0:m0 + mc]), code, 1, step, Lp, n_frames, wl, n, b, N.ptr(win), int(bool(detrend)),
+                                    N.ptr(plan), N.ptr(work), float(scale), N.ptr(out[:, :, m0:m0 + mc]), n_frames * M, M, 1,
+                                    N.stream_handle()), "b2_rfft_any")
+            _count()
+    return out
+
+
+def frame_spectra_any(x, length: int, wl: int, step: int, window: np.ndarray, detrend: bool, n_fft: int, fft_scale: float,
+                      device=None):
+    """Like `frame_spectra` for an FFT length different from the window length (frames cropped or zero-padded to
+    n_fft, reference _spectral_methods.py:263) or a window beyond the shared-memory kernel: K0 builds the
+    channel-major zero-padded copy, the large / arbitrary-length FFT transforms every frame in float64.
+    Returns complex128 (n_fft//2+1, frames, channels)."""
+    torch = _torch()
+    lib = N.lib()
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    M = int(x.shape[1])
+    K_total, _ = welch_frames(length, wl, step)
+    with torch.cuda.device(device):
+        Lp = (K_total - 1) * step + wl
+        Lp += (-Lp) % 4
+        xs, code, s_t, s_m = _as_device_block(x, 0, length, device)
+        xc = torch.empty((M, Lp), dtype=torch.float64, device=device)
+        N.check(lib.b2_prepare_channels(N.ptr(xs), code, s_t, s_m, 0, length, M, N.ptr(xc), Lp, N.F64, N.stream_handle()),
+                "b2_prepare_channels")
+        _count()
+        return rfft_frames(xc, Lp, M, wl, step, K_total, n_fft, window, detrend, fft_scale)
+
+
+def csm_rank1(spectrum_dev, factor: float, halve_edges: bool, amplitude_sqrt: bool):
+    """(nb, M, M) complex128 CSM of one spectrum per channel -- `_csm_fft` (_spectral_methods.py:374-443)."""
+    torch = _torch()
+    nb, M = spectrum_dev.shape
+    out = torch.empty((nb, M, M), dtype=torch.complex128, device=spectrum_dev.device)
+    with torch.cuda.device(spectrum_dev.device):
+        N.check(N.lib().b2_csm_rank1(N.ptr(spectrum_dev.contiguous()), M, nb, float(factor), int(bool(halve_edges)),
+                                     int(bool(amplitude_sqrt)), N.ptr(out), N.stream_handle()), "b2_csm_rank1")
+    _count()
+    return out
+
+
 def csm_finalize(S, M: int, n_frames: int, factor: float, halve_edges: bool, amplitude_sqrt: bool):
     """Average / scale / sqrt / mirror the packed summed spectra (nb, M(M+1)/2) -> complex128 (nb, M, M)
     CUDA tensor."""
@@ -399,7 +537,8 @@ def das_prepare(csm_dev, bin0: int, nbins: int, remove_diag: bool, mode: int):
     lib = N.lib()
     nb, M, _ = csm_dev.shape
     nbytes = N.check(lib.b2_das_operand_bytes(M, nbins, mode), "b2_das_operand_bytes")
-    op = torch.empty(nbytes, dtype=torch.uint8, device=csm_dev.device)
+    # one operand buffer per device: a map call consumes it before the next one is prepared (same stream)
+    op = _workspace("map_operand", nbytes, csm_dev.device)[:nbytes]
     N.check(lib.b2_das_prepare(N.ptr(csm_dev), M, nb, bin0, nbins, int(bool(remove_diag)), N.ptr(op), mode,
                                N.stream_handle()), "b2_das_prepare")
     _count()

@@ -6,8 +6,11 @@ libb2dsp (K0/K1/K2/K2e, see engine.py).  Instead of one Welch call per channel p
 channel is transformed once and each bin's cross-spectral matrix is one Hermitian rank-K
 update on the tensor cores.
 
+`_csm_fft` (:374-443), the single-FFT spectrum behind `Signal.get_spectrum` (classes/signal.py:903-946) and `_stft`
+(:176-282, any FFT length) run on the large / arbitrary-length FFT of csrc/big_fft.cu.
+
 Not supported on the GPU path (raises NotImplementedError, there is no CPU fallback):
-average="median" (reference :153-162) and window lengths above 16384.
+average="median" (reference :153-162), Welch window lengths above 16384, fractional-octave smoothing.
 """
 
 from __future__ import annotations
@@ -148,8 +151,8 @@ def stft_device(time_data, fs_hz: int, window_length_samples: int, window_type, 
     assert window_length_samples in valid_window_sizes, (
         "Window length should be a power of 2 between [16, 65536] or [2**4, 2**16]")
     assert overlap_percent >= 0 and overlap_percent < 100, "overlap_percent should be between 0 and 100"
-    if fft_length_samples is not None and fft_length_samples != window_length_samples:
-        raise NotImplementedError("an FFT length different from the window length is not part of the B200 path")
+    n_fft = window_length_samples if fft_length_samples is None else int(fft_length_samples)
+    assert n_fft >= 2, "the FFT length must be at least 2"
     spec = window_type.to_scipy_format() if isinstance(window_type, Window) else window_type
     from scipy.signal.windows import get_window
 
@@ -170,12 +173,19 @@ def stft_device(time_data, fs_hz: int, window_length_samples: int, window_type, 
         else:
             time_data = np.pad(np.asarray(time_data), ((overlap_samples, overlap_samples), (0, 0)))
     length = int(time_data.shape[0])
-    stft = engine.frame_spectra(time_data, length, window_length_samples, step, window, detrend,
-                                scaling.fft_scale(window_length_samples))
+    norm_scale = {"backward": 1.0, "forward": 1.0 / n_fft, "ortho": n_fft ** -0.5}[scaling.fft_norm()]
+    if n_fft == window_length_samples and window_length_samples <= 16384:
+        # the shared-memory kernels of the Welch stage
+        stft = engine.frame_spectra(time_data, length, window_length_samples, step, window, detrend, norm_scale)
+    else:
+        # another FFT length (numpy crops or zero-pads the frames, :263) or a window beyond the shared-memory kernel:
+        # framing from the channel-major copy, large / arbitrary-length FFT (Bluestein unless a power of two)
+        stft = engine.frame_spectra_any(time_data, length, window_length_samples, step, window, detrend, n_fft, norm_scale)
     if scaling.has_physical_units():
         stft[0] /= 2 ** 0.5
-        stft[-1] /= 2 ** 0.5                       # the length is a power of two, i.e. even (:268)
-        factor = float(np.squeeze(scaling.get_scaling_factor(window_length_samples, fs_hz, window)))
+        if n_fft % 2 == 0:
+            stft[-1] /= 2 ** 0.5                   # (:268)
+        factor = float(np.squeeze(scaling.get_scaling_factor(n_fft, fs_hz, window)))
         if not scaling.is_amplitude_scaling():
             stft = stft.real ** 2 + stft.imag ** 2
         stft = stft * factor
@@ -189,3 +199,62 @@ def _stft(x, fs_hz: int, window_length_samples: int, window_type, overlap_percen
     t, f, st = stft_device(x, fs_hz, window_length_samples, window_type, overlap_percent, fft_length_samples,
                            detrend, padding, scaling)
     return t, f, st.cpu().numpy()
+
+
+# --------------------------------------------------------------------------- next row f3: single-FFT spectrum and CSM
+def spectrum_fft_device(time_data, sampling_rate_hz: int, scaling: SpectrumScaling, pad_to_fast_length: bool = True,
+                        smoothing: float = 0.0, window=None):
+    """The FFT branch of `Signal.get_spectrum` (reference classes/signal.py:903-946) left on the device:
+    (freqs [numpy], spectrum CUDA tensor (nb, channels)) -- complex128 for the amplitude scalings, float64 power for
+    PowerSpectrum / PowerSpectralDensity.  One FFT over the whole recording of length next_fast_len(L) (or L)."""
+    import torch
+    from scipy.fft import next_fast_len
+
+    if smoothing != 0:
+        raise NotImplementedError("fractional-octave smoothing of the spectrum is outside the accelerated path")
+    if not hasattr(time_data, "shape"):
+        time_data = np.asarray(time_data)
+    if len(time_data.shape) == 1:
+        time_data = time_data[:, None]
+    L = int(time_data.shape[0])
+    n = int(next_fast_len(L, True)) if pad_to_fast_length else L
+    x = time_data if isinstance(time_data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(time_data))
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.to(torch.float64)
+    x = x.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
+    norm_scale = {"backward": 1.0, "forward": 1.0 / n, "ortho": n ** -0.5}[scaling.fft_norm()]
+    sp = engine.rfft_rows(x, n, norm_scale)
+    if scaling.has_physical_units():
+        # `_scale_spectrum` (helpers/spectrum_utilities.py:268-330): DC (and Nyquist for an even length) / sqrt(2),
+        # |.|^2 for the power scalings, times the scaling factor
+        sp[0] /= 2 ** 0.5
+        if n % 2 == 0:
+            sp[-1] /= 2 ** 0.5
+        factor = torch.from_numpy(np.atleast_1d(scaling.get_scaling_factor(n, sampling_rate_hz, window)).astype(np.float64)).to(sp.device)
+        if not scaling.is_amplitude_scaling():
+            sp = sp.real ** 2 + sp.imag ** 2
+        sp = sp * factor
+    return np.fft.rfftfreq(n, 1 / sampling_rate_hz), sp
+
+
+def csm_fft_device(spectrum_dev, scaling: SpectrumScaling, window, sampling_rate_hz: int):
+    """`_csm_fft` (reference _spectral_methods.py:374-443) on a device spectrum (nb, channels) with FFTBackward
+    normalisation -> complex128 CUDA tensor (nb, channels, channels)."""
+    nb = int(spectrum_dev.shape[0])
+    if scaling == SpectrumScaling.FFTBackward:
+        return engine.csm_rank1(spectrum_dev, 1.0, False, False)
+    # the reference passes `spectrum.shape[0] // 2 + 1` as the time length of the conversion (:437-439)
+    factor = np.atleast_1d(SpectrumScaling.FFTBackward.conversion_factor(scaling, nb // 2 + 1, sampling_rate_hz, window))
+    if factor.size != 1:
+        raise NotImplementedError("per-channel time windows are outside the accelerated path")
+    return engine.csm_rank1(spectrum_dev, float(factor.ravel()[0]), True, scaling.is_amplitude_scaling())
+
+
+def _csm_fft(spectrum, scaling: SpectrumScaling, window, sampling_rate_hz: int):
+    """Drop-in for reference _spectral_methods.py:374-443: complex128 host array (frequency, channels, channels)."""
+    import torch
+
+    if window is not None:
+        assert np.asarray(window).shape[1] == np.asarray(spectrum).shape[1], "Number of channels does not match"
+    sp = torch.from_numpy(np.ascontiguousarray(spectrum, dtype=np.complex128)).to(torch.device("cuda", torch.cuda.current_device()))
+    return csm_fft_device(sp, scaling, window, sampling_rate_hz).cpu().numpy()

@@ -53,6 +53,19 @@ class SpectrumScaling(Enum):
             return 1.0 / np.sqrt(window_length_samples)
         return 1.0
 
+    def conversion_factor(self, output: "SpectrumScaling", length_time_data_samples: int, sampling_rate_hz: int, window):
+        """Factor from this scaling to `output` (reference enums.py:131-181): linear / linear or squared / squared
+        when both are of the same kind, else the one to multiply SQUARED data with."""
+        fin = self.get_scaling_factor(length_time_data_samples, sampling_rate_hz, window)
+        fout = output.get_scaling_factor(length_time_data_samples, sampling_rate_hz, window)
+        if self.is_amplitude_scaling() == output.is_amplitude_scaling():
+            return fout / fin
+        if self.is_amplitude_scaling():
+            fin = fin ** 2.0
+        else:
+            fout = fout ** 2.0
+        return fout / fin
+
     def get_scaling_factor(self, length_time_data_samples: int, sampling_rate_hz: int, window):
         """One-sided forward-transform factor; linear for amplitude scalings, squared for power."""
         n = length_time_data_samples

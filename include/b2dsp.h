@@ -120,6 +120,34 @@ int b2_welch_autopower(const void *X_dev, int M, int64_t Kp, int nb, void *P_dev
 int b2_auto_finalize(const void *P_dev, int M, int nb, double inv_frames, double factor, int halve_edges,
                      int amplitude_sqrt, void *out_dev, void *stream);
 
+/* Large / arbitrary-length real FFT along the time axis, batched over rows (float64 arithmetic).  Replaces
+ * `np.fft.rfft(time_data, axis=0, n=fft_length)` of the single-FFT spectrum (classes/signal.py:903-911;
+ * fft_length = scipy.fft.next_fast_len(L, True) or L itself -- not a power of two) and
+ * `np.fft.rfft(frames, axis=0, n=fft_length_samples)` of `_stft` (_spectral_methods.py:263) when the FFT length differs
+ * from the window length or exceeds the shared-memory kernel.  Power-of-two lengths run as global-memory Stockham
+ * passes, every other length as Bluestein's chirp-z transform on top of them.
+ *   plan      b2_fft_plan_bytes(n) bytes, filled once per length by b2_fft_plan (needs b2_fft_work_bytes(n, 1) of work)
+ *   work      b2_fft_work_bytes(n, batch) bytes of scratch
+ *   input     row b starts at element (b / rows_per_group) * stride_group + (b % rows_per_group) * stride_b and
+ *             advances by stride_t per sample; n_in samples are read (cropped to n or zero-padded to n: numpy's
+ *             rfft(x, n)); optional window (n_in float64) and mean removal of the windowed row (detrend)
+ *   output    complex128, bin k of row b at k * out_stride_k + (b / rows_per_group) * out_stride_group
+ *             + (b % rows_per_group) * out_stride_b, k = 0 .. n/2, multiplied by `scale` (the rfft norm). */
+int64_t b2_fft_plan_bytes(int64_t n);
+int64_t b2_fft_work_bytes(int64_t n, int batch);
+int b2_fft_plan(int64_t n, void *plan_dev, void *work_dev, void *stream);
+int b2_rfft_any(const void *x_dev, int in_dtype, int64_t stride_t, int64_t stride_b, int64_t stride_group,
+                int rows_per_group, int64_t n_in, int64_t n, int batch, const void *window_dev, int detrend,
+                const void *plan_dev, void *work_dev, double scale, void *out_dev, int64_t out_stride_k,
+                int64_t out_stride_b, int64_t out_stride_group, void *stream);
+
+/* Cross-spectral matrix of ONE spectrum per channel (no averaging): csm[f][j][i] = X[f][j] conj(X[f][i]), fully
+ * populated [nb][M][M] complex128.  Replaces `_csm_fft` (_spectral_methods.py:374-443): for scalings other than
+ * FFTBackward the first and last bin are halved, everything is multiplied by `factor` and the amplitude scalings
+ * take the element-wise principal square root (:430-443).  spectrum_dev: [nb][M] complex128. */
+int b2_csm_rank1(const void *spectrum_dev, int M, int64_t nb, double factor, int halve_edges, int amplitude_sqrt,
+                 void *csm_out_dev, void *stream);
+
 /* K3a: operand preparation for the map: diagonal removal + M/(M-1) gain
  * (beamforming/beamforming.py:841-845), bin selection (:853-855) and the split of the
  * Hermitian matrix into L = strict lower triangle + diag/2 so that h^H C h = 2 Re(h^H L h).

@@ -140,7 +140,46 @@ def tf_golden(dsp):
     np.savez_compressed(os.path.join(GOLDEN, "transfer_functions.npz"), **out)
 
 
+FFT_CASES = [  # (samples, channels, pad_to_fast_length, scaling)
+    (2001, 3, True, "FFTBackward"),
+    (2001, 3, False, "FFTBackward"),              # odd, prime-ish length: Bluestein
+    (1536, 2, True, "FFTForward"),
+    (4096, 2, True, "FFTOrthogonal"),             # power of two
+    (1999, 3, False, "AmplitudeSpectrum"),        # prime length
+    (3000, 2, True, "AmplitudeSpectralDensity"),
+    (2500, 3, True, "PowerSpectrum"),
+    (2187, 2, False, "PowerSpectralDensity"),
+]
+
+
+def fft_golden(dsp):
+    """Next row f3: SpectrumMethod.FFT -- `Signal.get_spectrum` (classes/signal.py:903-946), `Signal.get_csm` ->
+    `_csm_fft` (:989-1002, _spectral_methods.py:374-443)."""
+    rng = np.random.default_rng(31)
+    fs = 12000
+    out = dict(fs=fs, n_cases=len(FFT_CASES))
+    for i, (L, ch, fast, sc) in enumerate(FFT_CASES):
+        x = rng.standard_normal((L, ch)) * np.linspace(1.0, 2.0, ch) + 0.3
+        s = dsp.Signal(None, x.copy(), fs)
+        s.set_spectrum_parameters(method=dsp.SpectrumMethod.FFT, pad_to_fast_length=fast, scaling=getattr(dsp.SpectrumScaling, sc))
+        f, sp = s.get_spectrum()
+        fc, csm = s.get_csm()
+        fo, spo = R.spectrum_fft(x, fs, sc, fast)
+        _, sp_b = R.spectrum_fft(x, fs, "fftbackward", fast)
+        csmo = R.csm_fft(sp_b, sc, fs)
+        e1, e2 = rel_to_max(spo, sp), rel_to_max(csmo, csm)
+        print(f"H{i} FFT method L={L} ch={ch} fast={fast} {sc}: n={2 * (len(f) - 1)}.. spectrum oracle-vs-ref {e1:.2e} ({sp.dtype}), csm {e2:.2e}")
+        assert spo.shape == sp.shape and spo.dtype == sp.dtype and e1 < 1e-12 and np.allclose(fo, f, rtol=0, atol=1e-9)
+        assert csmo.shape == csm.shape and e2 < 1e-12 and np.allclose(fc, f)
+        out[f"x_{i}"], out[f"names_{i}"], out[f"fast_{i}"] = x, np.array([sc]), np.array([int(fast)])
+        out[f"f_{i}"], out[f"sp_{i}"], out[f"csm_{i}"] = f, sp, csm
+    np.savez_compressed(os.path.join(GOLDEN, "fft_method.npz"), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "fft":         # regenerate only the FFT-method fixture
+        fft_golden(ref_loader.load())
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "stft":        # regenerate only the STFT fixture
         stft_golden(ref_loader.load())
         return
@@ -306,6 +345,7 @@ def main():
         csm_diag_bin85=np.diagonal(c1[85]).copy(), map=m1, f_range=fr1)
     stft_golden(dsp)
     tf_golden(dsp)
+    fft_golden(dsp)
     print("golden vectors written to", GOLDEN)
 
 

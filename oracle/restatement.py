@@ -236,6 +236,66 @@ def transfer_function(x_out, x_in, fs, wl, window="hann", overlap_percent=50, de
     return np.fft.rfftfreq(wl, 1 / fs), tf, coherence
 
 
+# --------------------------------------------------------------------------- next row f3: single-FFT spectrum and CSM
+def spectrum_fft(x, fs, scaling="fftbackward", pad_to_fast_length=True):
+    """FFT branch of `Signal.get_spectrum` (classes/signal.py:903-946, smoothing = 0, no time window): one rfft over
+    the whole recording of length next_fast_len(L, real) or L, with the scaling's norm; physical scalings go through
+    `_scale_spectrum` (helpers/spectrum_utilities.py:268-330).  -> (freqs, spectrum (nb, channels))."""
+    from scipy.fft import next_fast_len
+
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    L = x.shape[0]
+    n = next_fast_len(L, True) if pad_to_fast_length else L
+    sp = np.fft.rfft(x, axis=0, n=n, norm=fft_norm(scaling))
+    sc = scaling.lower()
+    if sc in PHYSICAL_SCALINGS:
+        if sc in ("amplitudespectraldensity", "powerspectraldensity"):
+            factor = (2 / n / fs) ** 0.5
+        else:
+            factor = 2 ** 0.5 / n
+        if sc not in AMPLITUDE_SCALINGS:
+            factor = factor ** 2.0
+        sp[0] /= 2 ** 0.5
+        if n % 2 == 0:
+            sp[-1] /= 2 ** 0.5
+        if sc not in AMPLITUDE_SCALINGS:
+            sp = np.abs(sp) ** 2
+        sp = sp * factor
+    return np.fft.rfftfreq(n, 1 / fs), sp
+
+
+def csm_fft(spectrum, scaling, fs):
+    """`_csm_fft` (_spectral_methods.py:374-443) without a time window: csm[f, j, i] = X[f, j] conj(X[f, i]); for
+    scalings other than FFTBackward the first and last bin are halved, the matrix is multiplied by the output
+    scaling's factor evaluated -- as the reference does -- for a time length of `nb // 2 + 1`, and the amplitude
+    scalings take the element-wise square root."""
+    sp = np.asarray(spectrum, dtype=np.complex128)
+    csm = sp[:, :, None] * sp[:, None, :].conj()
+    idx = np.arange(sp.shape[1])
+    csm[:, idx, idx] = (np.abs(sp) ** 2).astype(np.complex128)
+    sc = scaling.lower()
+    if sc == "fftbackward":
+        return csm
+    csm[np.array([0, -1])] /= 2.0
+    n = sp.shape[0] // 2 + 1
+    if sc == "fftforward":
+        lin = 1.0 / n
+    elif sc == "fftorthogonal":
+        lin = (1.0 / n) ** 0.5
+    elif sc in ("amplitudespectraldensity", "powerspectraldensity"):
+        lin = (2 / n / fs) ** 0.5
+    else:
+        lin = 2 ** 0.5 / n
+    # conversion from FFTBackward (amplitude, factor 1): linear factor for amplitude outputs, squared for power outputs
+    factor = lin if sc in AMPLITUDE_SCALINGS else lin ** 2.0
+    csm = csm * factor
+    if sc in AMPLITUDE_SCALINGS:
+        csm = np.sqrt(csm)
+    return csm
+
+
 # --------------------------------------------------------------------------- next row f4: STFT
 def stft_step(wl: int, overlap_percent: float) -> tuple[int, int]:
     """_spectral_methods.py:248-249: NOTE the overlap is rounded here (+0.5), unlike `_welch`."""

@@ -36,7 +36,7 @@ def _cases(golden_dir):
 
 
 def test_golden_spectrograms(golden_dir):
-    seen = unsupported = 0
+    seen = 0
     for g, i, wl, win, ov, nfft, det, pad, sc in _cases(golden_dir):
         s = dsp.Signal(None, g["x"].copy(), int(g["fs"]))
         s.set_spectrogram_parameters(window_length_samples=wl, window_type=getattr(dsp.Window, win), overlap_percent=ov,
@@ -44,18 +44,13 @@ def test_golden_spectrograms(golden_dir):
                                      scaling=getattr(dsp.SpectrumScaling, sc))
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            if nfft is not None:                       # zero-padded / cropped FFT lengths: not on this path
-                with pytest.raises(NotImplementedError):
-                    s.get_spectrogram()
-                unsupported += 1
-                continue
-            t, f, st = s.get_spectrogram()
+            t, f, st = s.get_spectrogram()           # nfft != window length runs on the any-length FFT (big_fft.cu)
         ref = g[f"stft_{i}"]
         assert st.shape == ref.shape and st.dtype == ref.dtype, (i, st.shape, ref.shape, st.dtype)
         assert np.max(np.abs(st - ref)) <= REL_TO_MAX * np.max(np.abs(ref)), i
         assert np.array_equal(f, g[f"f_{i}"]) and np.allclose(t, g[f"t_{i}"], rtol=0, atol=1e-15)
         seen += 1
-    assert seen == 7 and unsupported == 2
+    assert seen == 9
 
 
 @pytest.mark.parametrize("L,M,wl,ov", [(5000, 1, 1024, 50.0), (12345, 5, 4096, 75.0), (40000, 3, 16384, 50.0),
@@ -102,5 +97,22 @@ def test_device_tensor_input_cache_and_errors():
         _stft(x, 8000, 100, dsp.Window.Hann, 50.0, None, False, True, dsp.SpectrumScaling.FFTBackward)
     with pytest.raises(AssertionError):
         _stft(x, 8000, 256, dsp.Window.Hann, 100.0, None, False, True, dsp.SpectrumScaling.FFTBackward)
-    with pytest.raises(NotImplementedError):
-        _stft(x, 8000, 32768, dsp.Window.Hann, 50.0, None, False, True, dsp.SpectrumScaling.FFTBackward)
+
+
+@pytest.mark.parametrize("L,M,wl,nfft,ov", [(200000, 2, 32768, None, 50.0), (150000, 3, 65536, None, 75.0),
+                                            (9000, 2, 512, 2048, 50.0), (9000, 3, 1024, 512, 25.0),
+                                            (70000, 2, 16384, 32768, 50.0)])
+def test_long_windows_and_fft_lengths(L, M, wl, nfft, ov):
+    """Window lengths above the shared-memory kernel's 16384 (up to the reference's 2^16 exploration sizes) and FFT
+    lengths that differ from the window (zero-padded or cropped frames, _spectral_methods.py:1180-1215) run on the
+    global-memory Stockham path -- against the oracle."""
+    rng = np.random.default_rng(wl + (nfft or 0))
+    x = rng.standard_normal((L, M)) + 0.1
+    for sc, det in [("FFTBackward", False), ("AmplitudeSpectrum", True)]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t, f, st = _stft(x, 48000, wl, dsp.Window.Hann, ov, nfft, det, True, getattr(dsp.SpectrumScaling, sc))
+            to, fo, so = R.stft(x, 48000, wl, "hann", ov, nfft, det, True, sc)
+        assert st.shape == so.shape and st.dtype == so.dtype
+        assert np.max(np.abs(st - so)) <= REL_TO_MAX * np.max(np.abs(so))
+        assert np.array_equal(f, fo) and np.allclose(t, to, rtol=0, atol=1e-15)

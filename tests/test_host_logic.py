@@ -172,8 +172,19 @@ def test_spectrogram_parameters_and_stft_argument_checks():
         _stft(x, 8000, 8, dsp.Window.Hann, 50.0, None, False, True, dsp.SpectrumScaling.FFTBackward)       # < 2**4
     with pytest.raises(AssertionError):
         _stft(x, 8000, 256, dsp.Window.Hann, 100.0, None, False, True, dsp.SpectrumScaling.FFTBackward)
-    with pytest.raises(NotImplementedError):
-        _stft(x, 8000, 256, dsp.Window.Hann, 50.0, 512, False, True, dsp.SpectrumScaling.FFTBackward)
+    with pytest.raises(AssertionError):
+        _stft(x, 8000, 1 << 17, dsp.Window.Hann, 50.0, None, False, True, dsp.SpectrumScaling.FFTBackward)  # > 2**16
+    with pytest.raises(AssertionError):
+        _stft(x, 8000, 256, dsp.Window.Hann, 50.0, 1, False, True, dsp.SpectrumScaling.FFTBackward)         # FFT length < 2
+    from dsptoolbox_b200.standard._spectral_methods import spectrum_fft_device
+    with pytest.raises(NotImplementedError):                  # smoothing is checked before any device work
+        spectrum_fft_device(x, 8000, dsp.SpectrumScaling.FFTBackward, True, 3)
+    # FFTBackward -> output scaling conversion of `_csm_fft` (reference enums.py:131-181): amplitude/amplitude is a
+    # ratio of linear factors, amplitude -> power multiplies SQUARED data
+    b = dsp.SpectrumScaling.FFTBackward
+    assert np.allclose(b.conversion_factor(dsp.SpectrumScaling.FFTForward, 100, 8000, None), 1 / 100)
+    assert np.allclose(b.conversion_factor(dsp.SpectrumScaling.PowerSpectrum, 100, 8000, None), 2 / 100 ** 2)
+    assert np.allclose(b.conversion_factor(dsp.SpectrumScaling.AmplitudeSpectralDensity, 100, 8000, None), (2 / 100 / 8000) ** 0.5)
 
 
 def test_spectrum_holder_and_transfer_function_argument_checks():

@@ -174,3 +174,17 @@ def test_transfer_functions_next_row(golden_dir):
         assert np.array_equal(f, g[f"f_{i}"])
         assert np.max(np.abs(tf - g[f"tf_{i}"])) <= 1e-12 * np.max(np.abs(g[f"tf_{i}"]))
         assert np.max(np.abs(coh - g[f"coh_{i}"])) <= 1e-12 * np.max(np.abs(g[f"coh_{i}"]))
+
+
+def test_fft_method_next_row(golden_dir):
+    """Next row f3: the oracle's single-FFT spectrum and `_csm_fft` restatements against the reference's
+    Signal.get_spectrum / get_csm with SpectrumMethod.FFT, every scaling, padded-to-fast and exact lengths."""
+    g = np.load(os.path.join(golden_dir, "fft_method.npz"))
+    for i in range(int(g["n_cases"])):
+        sc, fast = str(g[f"names_{i}"][0]), bool(g[f"fast_{i}"][0])
+        f, sp = R.spectrum_fft(g[f"x_{i}"], int(g["fs"]), sc, fast)
+        assert sp.dtype == g[f"sp_{i}"].dtype and np.allclose(f, g[f"f_{i}"], rtol=0, atol=1e-9)
+        assert np.max(np.abs(sp - g[f"sp_{i}"])) <= 1e-13 * np.max(np.abs(g[f"sp_{i}"]))
+        _, spb = R.spectrum_fft(g[f"x_{i}"], int(g["fs"]), "fftbackward", fast)
+        csm = R.csm_fft(spb, sc, int(g["fs"]))
+        assert np.max(np.abs(csm - g[f"csm_{i}"])) <= 1e-13 * np.max(np.abs(g[f"csm_{i}"]))
