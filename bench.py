@@ -532,6 +532,8 @@ def run_b200(args):
     for _ in range(max(3, args.warmup)):
         step_resident()
     barrier()
+    if os.environ.get("B2_BENCH_TRACE") == "1":
+        engine.config.profile = True
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = engine.launches
@@ -540,10 +542,21 @@ def run_b200(args):
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
     evs = []
+    prof = None
+    if os.environ.get("B2_BENCH_TRACE") == "2":  # debug: where the HOST spends its time inside the timed loop
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     for _ in range(args.steps):
         ev, out, fq_last, csm_last = step_resident()
         evs.append(ev)
+        if os.environ.get("B2_BENCH_TRACE") == "1":     # debug: per-kernel times of stage 1 inside the timed loop (adds syncs)
+            print("trace", engine.config.stats["csm"].get("times_ms"), file=sys.stderr)
     e_stop.record()
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(18)
     barrier()
     wall = time.perf_counter() - wall0
     launches = engine.launches - launches0

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "b2_fft_plan": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
     "b2_rfft_any": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int64, c_int64, c_int, c_void_p, c_int,
                             c_void_p, c_void_p, c_double, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "b2_delay_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p]),
     "b2_csm_rank1": (c_int, [c_void_p, c_int, c_int64, c_double, c_int, c_int, c_void_p, c_void_p]),
     "b2_das_operand_bytes": (c_int64, [c_int, c_int, c_int]),
     "b2_das_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

@@ -17,8 +17,11 @@ from .beamforming import (  # noqa: F401
     true_power_steering,
     true_location_steering,
     simpson_weights,
+    MonopoleSource,
+    mix_sources_on_array,
 )
 from .enums import SteeringVectorType  # noqa: F401
 
 __all__ = ["Grid", "Regular2DGrid", "Regular3DGrid", "LineGrid", "MicArray", "SteeringVector",
-           "BeamformerDASFrequency", "BeamformerMVDR", "BeamformerFunctional", "BeamformerOrthogonal", "BeamformerCleanSC", "SteeringVectorType"]
+           "BeamformerDASFrequency", "BeamformerMVDR", "BeamformerFunctional", "BeamformerOrthogonal", "BeamformerCleanSC", "SteeringVectorType",
+           "MonopoleSource", "mix_sources_on_array"]

@@ -8,7 +8,9 @@ Call-compatible with reference beamforming/beamforming.py for Grid (:35-75), Reg
 vectors are synthesised inside the map kernel, and the grid may be sharded over ranks (dist.py).
 BeamformerMVDR (:1223-1314), BeamformerFunctional (:1127-1220) and BeamformerOrthogonal (:1010-1124)
 and BeamformerCleanSC (:883-1007) reuse the same map kernel on per-bin transformed matrices
-(SURVEY.md section 8f.1).  DASTime and the source simulator are outside this round's scope.
+(SURVEY.md section 8f.1).  MonopoleSource (:1397-1458) and mix_sources_on_array (:1461-1511) -- the data path in
+front of stage 1 -- run as one fractional-delay kernel (csrc/delay_fir.cu) and leave the
+array recording on the device.  BeamformerDASTime is outside the scope.
 """
 
 from __future__ import annotations
@@ -502,3 +504,70 @@ class BeamformerCleanSC(_QuadraticFormBeamformer):
             D0 = torch.where(active[:, None, None], D1, D0)
             D1 = D1 - safety_factor * Gm
         return self._finish(second, fsel)
+
+
+# =========================================================================== source simulation (next row f2)
+def _source_filters(source, mics: "MicArray", c: float, length: int):
+    """Taps (M, 31) with the 1 / (1 + r) gain folded in and integer shifts (M,) of one source -- the filter
+    `fractional_delay(emitted, r / c, keep_length=True)` applies per microphone (reference :1443-1451)."""
+    from ..standard._standard_backend import fractional_delay_filters
+
+    distances = np.atleast_1d(mics.get_distances_to_point(source.coordinates)).astype(np.float64)
+    delays = distances / c
+    assert np.all(delays >= 0), "Delay must be positive"
+    delay_samples = delays * source.emitted_signal.sampling_rate_hz
+    assert np.all(delay_samples < length), "Delay too large for the given signal"
+    shifts, taps = fractional_delay_filters(delay_samples, 30, 60.0)
+    on_mic = delays == 0                                  # zero delay: the reference returns an unfiltered copy
+    taps[on_mic] = 0.0
+    taps[on_mic, 0] = 1.0
+    shifts[on_mic] = 0
+    return taps / (1.0 + distances)[:, None], shifts
+
+
+class MonopoleSource:
+    """Omnidirectional source: one emitted one-channel `Signal` at a position (reference :1397-1425)."""
+
+    def __init__(self, signal: Signal, coordinates):
+        assert signal.number_of_channels == 1, "Only signals with a single channel are supported"
+        coordinates = np.squeeze(coordinates)
+        assert len(coordinates) == 3 and coordinates.ndim == 1, "Coordinates should have exactly three values"
+        self.emitted_signal = signal
+        self.coordinates = coordinates
+
+    def get_signals_on_array(self, mics: MicArray, c: float = 343) -> Signal:
+        """The emitted signal as every microphone receives it: delayed by distance / c with a 31-tap windowed-sinc
+        fractional-delay filter, divided by 1 + distance, same length as the emitted signal (reference :1427-1458).
+        The returned `Signal` holds a CUDA tensor (time samples, microphones) -- ready for `get_csm`."""
+        x = self.emitted_signal.time_data
+        length = int(x.shape[0])
+        taps, shifts = _source_filters(self, mics, c, length)
+        out = engine.delay_mix([x[:, 0]], taps[None], shifts[None], length)
+        return Signal(None, out, self.emitted_signal.sampling_rate_hz)
+
+
+def mix_sources_on_array(sources, mics: MicArray, c: float = 343) -> Signal:
+    """Sum of the sources' signals on the array (reference :1461-1511), one kernel launch for all sources.  When the
+    emitted signals differ in length the reference trims the running sum and the next emitted signal to the
+    shorter of the two, with a warning; the same lengths apply here (the emitted `Signal`s are not modified, and
+    the caller's list is left as it is -- the reference pops its first element)."""
+    from warnings import warn
+
+    if type(sources) is MonopoleSource:
+        sources = [sources]
+    assert len(sources) > 0, "There must be at least one source to project on array"
+    assert all(type(i) is MonopoleSource for i in sources), "All sources in list should be of type Source"
+    fs = sources[0].emitted_signal.sampling_rate_hz
+    total = int(sources[0].emitted_signal.time_data.shape[0])
+    signals, taps, shifts = [], [], []
+    for n, s in enumerate(sources):
+        x = s.emitted_signal.time_data
+        if total != int(x.shape[0]):
+            warn("Emitted signals from sources differ in length. Trimming to shortest will be done")
+            total = min(total, int(x.shape[0]))
+        t, d = _source_filters(s, mics, c, total)          # this source is delayed at the running length
+        signals.append(x[:total, 0])
+        taps.append(t)
+        shifts.append(d)
+    out = engine.delay_mix(signals, np.stack(taps), np.stack(shifts), total)
+    return Signal(None, out, fs)

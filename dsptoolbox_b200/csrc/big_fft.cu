@@ -199,7 +199,10 @@ __global__ void pointwise_conj_kernel(const double2 *__restrict__ fa, const doub
 }
 
 // out[k][b] = scale * (bluestein ? w[k] conj(y[b][k]) / P : y[b][k]) for k < nbins; threads over (k, b), b fastest
-__global__ void store_bins_kernel(const double2 *__restrict__ y, const double2 *__restrict__ w, int64_t P, int64_t nbins,
+// The DC bin and, for an even length, the Nyquist bin of a real signal are real: their imaginary part is written as an
+// exact +0 like a real-input FFT does (the complex transform leaves a rounding residue there, and the element-wise
+// square root of `_csm_fft` sits on its branch cut for exactly these bins).
+__global__ void store_bins_kernel(const double2 *__restrict__ y, const double2 *__restrict__ w, int64_t P, int64_t n, int64_t nbins,
                                   int batch, double scale, double2 *__restrict__ out, int64_t stride_k, int64_t stride_b,
                                   int64_t stride_group, int rpg) {
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -208,6 +211,7 @@ __global__ void store_bins_kernel(const double2 *__restrict__ y, const double2 *
     const int b = int(idx - k * batch);
     double2 v = y[int64_t(b) * P + k];
     if (w) v = cmul(w[k], make_double2(v.x / double(P), -v.y / double(P)));
+    if (k == 0 || 2 * k == n) v.y = 0.0;
     out[k * stride_k + int64_t(b / rpg) * stride_group + int64_t(b % rpg) * stride_b] = make_double2(v.x * scale, v.y * scale);
 }
 
@@ -287,7 +291,7 @@ extern "C" int b2_rfft_any(const void *x_dev, int in_dtype, int64_t stride_t, in
     }
     const int64_t nbins = n / 2 + 1;
     const int64_t tb = nbins * int64_t(batch);
-    store_bins_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, st>>>(res, w, L.P, nbins, batch, scale, (double2 *)out_dev,
+    store_bins_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, st>>>(res, w, L.P, n, nbins, batch, scale, (double2 *)out_dev,
                                                                     out_stride_k, out_stride_b, out_stride_group, rows_per_group);
     B2_LAUNCH_OK("b2_rfft_any(store)");
     return B2_OK;

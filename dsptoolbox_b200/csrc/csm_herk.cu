@@ -284,8 +284,14 @@ __global__ void csm_rank1_kernel(const double2 *__restrict__ X, int M, int64_t n
     const int64_t f = idx / mm;
     const int r = int(idx - f * mm);
     const int j = r / M, i = r - j * M;
-    const double2 a = X[f * M + j], b = X[f * M + i];
-    double2 v = make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);      // a conj(b)
+    // The reference fills the lower triangle with conj(X_i) X_j and adds the conjugate transpose of that
+    // (upper triangle still zero) -- which decides the SIGN OF A ZERO imaginary part (real DC / Nyquist bins), and
+    // with it the branch the element-wise square root of the amplitude scalings takes for a negative real product:
+    // lower: the product's own zero; upper: 0 + (-imag) = +0.  Evaluated the same way here.
+    const int lo = j > i ? i : j, hi = j > i ? j : i;
+    const double2 a = X[f * M + hi], b = X[f * M + lo];
+    double2 v = make_double2(b.x * a.x + b.y * a.y, __dadd_rn(__dmul_rn(b.x, a.y), __dmul_rn(-b.y, a.x)));   // conj(b) a
+    if (j < i) v.y = __dadd_rn(0.0, -v.y);
     if (i == j) v.y = 0.0;
     if (halve_edges && (f == 0 || f == nb - 1)) { v.x *= 0.5; v.y *= 0.5; }
     v.x *= factor; v.y *= factor;

@@ -20,11 +20,7 @@ namespace {
 template <typename T, int LOG2NC> struct Geo {
     static constexpr int NC = 1 << LOG2NC;              // complex points = wl / 2
     static constexpr int N = 2 * NC;                    // wl
-    static constexpr int NCP = NC + (NC >> 3);          // 1 pad slot per 8 points
-    static constexpr int PITCH = NCP + 1;               // per-frame pitch (staggers frames)
     static constexpr int CXB = int(sizeof(cx<T>));
-    static constexpr int frames_fit(int fr) { return fr * PITCH * CXB <= 74 * 1024; }   // 3 CTAs per SM
-    static constexpr int FR = frames_fit(16) ? 16 : frames_fit(8) ? 8 : frames_fit(4) ? 4 : frames_fit(2) ? 2 : 1;
 #ifndef B2_FFT_VPT64
 #define B2_FFT_VPT64 16
 #endif
@@ -33,12 +29,36 @@ template <typename T, int LOG2NC> struct Geo {
 #endif
     static constexpr int VPT = sizeof(T) == 8 ? B2_FFT_VPT64 : B2_FFT_VPT32;  // complex values held per thread
     static constexpr int RMAX = VPT >= 16 ? 16 : 8;                          // largest butterfly held in registers
+    static constexpr int R1 = NC >= RMAX ? RMAX : NC;                        // radix of the first pass
+    // One pad slot per R1 points: the first pass writes with a stride of R1 points between lanes, which the pad turns
+    // into R1 + 1 -- odd, so the 8 (fp64) or 16 (fp32) lanes of one shared-memory wavefront fall into distinct
+    // 16-byte / 8-byte bank groups.  (One slot per 8 points under a radix-16 pass gave a stride of 18 and two-way
+    // conflicts: 29 % of all shared wavefronts of the fp64 nfft-4096 kernel, profiles/r2_k1_ncu.txt.)
+    static constexpr int PADSH = R1 >= 16 ? 4 : 3;
+    static constexpr int NCP = NC + (NC >> PADSH);
+    static constexpr int PITCH = NCP + 1;               // per-frame pitch (staggers frames)
+    static constexpr int frames_fit(int fr) { return fr * PITCH * CXB <= 74 * 1024; }   // 3 CTAs per SM
+    static constexpr int FR = frames_fit(16) ? 16 : frames_fit(8) ? 8 : frames_fit(4) ? 4 : frames_fit(2) ? 2 : 1;
     static constexpr int NT_RAW = FR * NC / VPT;
     static constexpr int NT = NT_RAW < 64 ? 64 : (NT_RAW > 1024 ? 1024 : NT_RAW);
     static constexpr int SMEM = FR * PITCH * CXB;
+    // two resident CTAs (128 registers per thread) where the CTA is small enough: 6.20 instead of 7.85 ms for
+    // 256 channels x 60 s x nfft 4096 in fp64 (profiles/r2_stage1_variants.txt); three (80 registers) spills and loses
+#ifndef B2_FFT_MINB
+#define B2_FFT_MINB 2
+#endif
+    static constexpr int MINB = NT * B2_FFT_MINB <= 512 ? B2_FFT_MINB : 1;
 };
 
-__device__ __forceinline__ int padidx(int i) { return i + (i >> 3); }
+template <int SH> __device__ __forceinline__ int padidx(int i) { return i + (i >> SH); }
+
+// Two neighbouring complex values with one store: 256-bit for fp64 (sm_100 has 32-byte global accesses), 128-bit for fp32.
+__device__ __forceinline__ void store_pair(double2 *p, double2 a, double2 b) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+__device__ __forceinline__ void store_pair(float2 *p, float2 a, float2 b) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a.x, a.y, b.x, b.y);
+}
 
 // One Stockham pass over all FR frames in the CTA: radix R, NS = product of earlier radices.
 template <typename T, int LOG2NC, int R, int NS>
@@ -56,7 +76,7 @@ __device__ __forceinline__ void stockham_pass(cx<T> *s, const cx<T> *__restrict_
             int k = j & (NS - 1);
             cx<T> *base = s + fr * G::PITCH;
 #pragma unroll
-            for (int r = 0; r < R; ++r) v[it][r] = base[padidx(j + r * J)];
+            for (int r = 0; r < R; ++r) v[it][r] = base[padidx<G::PADSH>(j + r * J)];
             if constexpr (NS > 1) {
                 // twiddles w^r, w = exp(-2 pi i k / (NS R)): one table read, powers by products
                 // (depth <= 3 multiplications, so the error stays at a few ulp)
@@ -103,7 +123,7 @@ __device__ __forceinline__ void stockham_pass(cx<T> *s, const cx<T> *__restrict_
             int j0 = (j - k) * R + k;
             cx<T> *base = s + fr * G::PITCH;
 #pragma unroll
-            for (int r = 0; r < R; ++r) base[padidx(j0 + r * NS)] = v[it][r];
+            for (int r = 0; r < R; ++r) base[padidx<G::PADSH>(j0 + r * NS)] = v[it][r];
         }
     }
     __syncthreads();
@@ -154,7 +174,7 @@ __device__ __forceinline__ void first_pass_from_global(cx<T> *s, const T *__rest
             dftR<T, R>(v[it]);
             C *base = s + fr * G::PITCH;
 #pragma unroll
-            for (int r = 0; r < R; ++r) base[padidx(j * R + r)] = v[it][r];
+            for (int r = 0; r < R; ++r) base[padidx<G::PADSH>(j * R + r)] = v[it][r];
         }
     }
     __syncthreads();
@@ -180,11 +200,8 @@ __device__ __forceinline__ void stockham_all(cx<T> *s, const cx<T> *__restrict__
     }
 }
 
-#ifndef B2_FFT_MINB
-#define B2_FFT_MINB 1
-#endif
 template <typename T, int LOG2NC>
-__global__ void __launch_bounds__(Geo<T, LOG2NC>::NT, B2_FFT_MINB)
+__global__ void __launch_bounds__(Geo<T, LOG2NC>::NT, Geo<T, LOG2NC>::MINB)
 welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframes,
                   const T *__restrict__ window, const cx<T> *__restrict__ tw, int detrend,
                   T scale, cx<T> *__restrict__ X, int M, int64_t Kp, int vec_ok) {
@@ -218,23 +235,37 @@ welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframe
     // Spectra layout [frame chunk of 16][bin][channel][16 frames]: all CTAs of one frame chunk write
     // inside one (nb * M * 16)-element window and the rank-K kernel reads whole tiles contiguously.
     const T half = T(0.5) * scale;
-    auto store = [&](int kf, int fr, C out) {
-        // Removing the frame mean (_spectral_methods.py:136-137) changes the DC bin only: the DFT of a
-        // constant vanishes at every other bin.  The reference's own DC value is rounding noise.
-        if (detrend && kf == 0) out = mk<T>(T(0), T(0));
-        const int64_t k = k0 + fr;
-        X[(((k >> 4) * nb + kf) * M + m) * 16 + (k & 15)] = out;
-    };
-    for (int idx = tid; idx < (NC / 2 + 1) * FR; idx += NT) {
-        const int fr = idx % FR, kp = idx / FR;
-        const C *base = s + fr * G::PITCH;
-        const C a = base[padidx(kp)];
-        const C b = cconj(base[padidx((NC - kp) & (NC - 1))]);
+    // Removing the frame mean (_spectral_methods.py:136-137) changes the DC bin only: the DFT of a constant
+    // vanishes at every other bin.  The reference's own DC value is rounding noise.
+    auto untangle = [&](const C *base, int kp, C &lo, C &hi) {
+        const C a = base[padidx<G::PADSH>(kp)];
+        const C b = cconj(base[padidx<G::PADSH>((NC - kp) & (NC - 1))]);
         const C w = __ldg(tw + kp);
         const C sum = cadd(a, b), dif = cmul(w, csub(a, b));      // dif = w (a - conj b)
-        store(kp, fr, mk<T>((sum.x + dif.y) * half, (sum.y - dif.x) * half));
-        // partner bin NC - kp (kp = 0 gives the Nyquist bin; kp = NC/2 is its own partner)
-        if (2 * kp != NC) store(NC - kp, fr, mk<T>((sum.x - dif.y) * half, -(sum.y + dif.x) * half));
+        lo = mk<T>((sum.x + dif.y) * half, (sum.y - dif.x) * half);
+        hi = mk<T>((sum.x - dif.y) * half, -(sum.y + dif.x) * half);   // bin NC - kp (kp = 0: the Nyquist bin)
+        if (detrend && kp == 0) lo = mk<T>(T(0), T(0));
+    };
+    if constexpr (FR >= 2) {
+        // two neighbouring frames of one bin per thread: one 32-byte (fp64) / 16-byte (fp32) store instead of two --
+        // the scattered 16-byte stores were 40 % of the LSU wavefronts of this kernel
+        constexpr int NP = FR / 2;
+        for (int idx = tid; idx < (NC / 2 + 1) * NP; idx += NT) {
+            const int pr = idx % NP, kp = idx / NP;
+            C lo0, hi0, lo1, hi1;
+            untangle(s + (2 * pr) * G::PITCH, kp, lo0, hi0);
+            untangle(s + (2 * pr + 1) * G::PITCH, kp, lo1, hi1);
+            const int64_t k = k0 + 2 * pr;
+            store_pair(X + (((k >> 4) * nb + kp) * M + m) * 16 + (k & 15), lo0, lo1);
+            if (2 * kp != NC) store_pair(X + (((k >> 4) * nb + (NC - kp)) * M + m) * 16 + (k & 15), hi0, hi1);
+        }
+    } else {
+        for (int kp = tid; kp < NC / 2 + 1; kp += NT) {
+            C lo, hi;
+            untangle(s, kp, lo, hi);
+            X[(((k0 >> 4) * nb + kp) * M + m) * 16 + (k0 & 15)] = lo;
+            if (2 * kp != NC) X[(((k0 >> 4) * nb + (NC - kp)) * M + m) * 16 + (k0 & 15)] = hi;
+        }
     }
 }
 

@@ -494,6 +494,36 @@ def frame_spectra_any(x, length: int, wl: int, step: int, window: np.ndarray, de
         return rfft_frames(xc, Lp, M, wl, step, K_total, n_fft, window, detrend, fft_scale)
 
 
+def delay_mix(signals, taps: np.ndarray, shifts: np.ndarray, out_length: int, device=None):
+    """Mixed array signals of several sources: float64 CUDA tensor (out_length, M),
+    out[n, m] = sum_s sum_t taps[s, m, t] x_s[n - shifts[s, m] - t] (x_s zero outside its samples).
+
+    signals: one 1-D array / tensor per source (host or device, any float type); taps (S, M, T) float64 with the
+    gains folded in; shifts (S, M) integers.  The per-microphone loop of `MonopoleSource.get_signals_on_array` and
+    the per-source sum of `mix_sources_on_array` (reference beamforming/beamforming.py:1427-1511) as one kernel."""
+    torch = _torch()
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    S, M, T = taps.shape
+    assert len(signals) == S and shifts.shape == (S, M)
+    with torch.cuda.device(device):
+        parts, lens = [], []
+        for x in signals:
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            t = t.reshape(-1).to(device=device, dtype=torch.float64, non_blocking=True)
+            parts.append(t)
+            lens.append(int(t.numel()))
+        xcat = parts[0] if S == 1 else torch.cat(parts)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        meta = torch.from_numpy(np.concatenate([offs, np.asarray(lens, dtype=np.int64)])).to(device)
+        taps_d = torch.from_numpy(np.ascontiguousarray(np.transpose(taps, (0, 2, 1)), dtype=np.float64)).to(device)   # [S][T][M]
+        shifts_d = torch.from_numpy(np.ascontiguousarray(shifts, dtype=np.int32)).to(device)
+        out = torch.empty((int(out_length), M), dtype=torch.float64, device=device)
+        N.check(N.lib().b2_delay_mix(N.ptr(xcat), N.ptr(meta), N.ptr(meta[S:]), S, N.ptr(taps_d), N.ptr(shifts_d), T, M,
+                                     int(out_length), N.ptr(out), N.stream_handle()), "b2_delay_mix")
+    _count()
+    return out
+
+
 def csm_rank1(spectrum_dev, factor: float, halve_edges: bool, amplitude_sqrt: bool):
     """(nb, M, M) complex128 CSM of one spectrum per channel -- `_csm_fft` (_spectral_methods.py:374-443)."""
     torch = _torch()

@@ -148,6 +148,19 @@ int b2_rfft_any(const void *x_dev, int in_dtype, int64_t stride_t, int64_t strid
 int b2_csm_rank1(const void *spectrum_dev, int M, int64_t nb, double factor, int halve_edges, int amplitude_sqrt,
                  void *csm_out_dev, void *stream);
 
+/* Source simulation in front of stage 1: the mixed signals n_src monopole sources leave
+ * on M microphones,
+ *     out[n][m] = sum_s sum_t taps[s][t][m] * x_s[n - shift[s][m] - t],   n < L,  x_s = 0 outside its x_len[s] samples.
+ * Replaces the per-microphone loop of `MonopoleSource.get_signals_on_array` (beamforming/beamforming.py:1427-1458:
+ * `fractional_delay(..., keep_length=True)` of standard/latency_delay.py:159-257, gain 1 / (1 + r), append) and the
+ * per-source sum of `mix_sources_on_array` (:1461-1511).  The host passes the windowed-sinc taps of
+ * `_fractional_delay_filter` (standard/_standard_backend.py:430-493) with the gain folded in, and its integer delay.
+ *   x_dev [sum of lengths] float64, source s at x_offset[s] (int64, device) with x_len[s] samples (int64, device);
+ *   taps_dev [n_src][n_taps][M] float64;  shift_dev [n_src][M] int32 (may be negative);  out_dev [L][M] float64.
+ * n_taps must be 31 (filter order 30, the only one the simulator uses); other orders -> B2_EUNSUPPORTED. */
+int b2_delay_mix(const void *x_dev, const void *x_offset_dev, const void *x_len_dev, int n_src, const void *taps_dev,
+                 const void *shift_dev, int n_taps, int M, int64_t L, void *out_dev, void *stream);
+
 /* K3a: operand preparation for the map: diagonal removal + M/(M-1) gain
  * (beamforming/beamforming.py:841-845), bin selection (:853-855) and the split of the
  * Hermitian matrix into L = strict lower triangle + diag/2 so that h^H C h = 2 Re(h^H L h).

@@ -176,7 +176,49 @@ def fft_golden(dsp):
     np.savez_compressed(os.path.join(GOLDEN, "fft_method.npz"), **out)
 
 
+def sources_golden(dsp):
+    """Next row f2: `MonopoleSource.get_signals_on_array` / `mix_sources_on_array`
+    (beamforming/beamforming.py:1397-1511) with `fractional_delay` (standard/latency_delay.py:159-257)."""
+    import warnings
+
+    rng = np.random.default_rng(41)
+    fs = 16000
+    mic = np.concatenate([rng.uniform(-0.4, 0.4, (9, 2)), np.zeros((9, 1))], axis=1)
+    mic[3] = [0.02, 0.0, 0.0]                                  # 2 cm from source 2: negative integer shift
+    mics = dsp.beamforming.MicArray(dict(x=mic[:, 0], y=mic[:, 1], z=mic[:, 2]))
+    src = np.array([[0.3, -0.2, 1.5], [-1.0, 0.7, 2.5], [0.0, 0.0, 0.0], [0.1, 0.1, 0.8]])
+    src[2] = mic[5]                                            # a source ON a microphone: zero delay for that channel
+    src[3] = mic[3] + [0.02, 0.0, 0.0]
+    lens = [3000, 3000, 2500, 2800]
+    sig = [rng.standard_normal(n) * (1 + 0.5 * i) for i, n in enumerate(lens)]
+    out = dict(fs=fs, mic=mic, src=src, c=343.0, n_src=len(src))
+    for i, x in enumerate(sig):
+        out[f"x_{i}"] = x
+        got = dsp.beamforming.MonopoleSource(dsp.Signal(None, x.copy(), fs), src[i]).get_signals_on_array(mics, 343.0).time_data
+        mine = R.monopole_on_array(x, fs, src[i], mic, 343.0)
+        print(f"I{i} monopole source {i}: {got.shape}, oracle-vs-ref {rel_to_max(mine, got):.2e}")
+        assert mine.shape == got.shape and rel_to_max(mine, got) < 1e-13
+        out[f"on_array_{i}"] = got
+    for tag, ids in [("equal", [0, 1]), ("ragged", [0, 1, 2, 3]), ("ragged2", [2, 0, 3])]:
+        srcs = [dsp.beamforming.MonopoleSource(dsp.Signal(None, sig[i].copy(), fs), src[i]) for i in ids]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            got = dsp.beamforming.mix_sources_on_array(srcs, mics, 343.0).time_data
+        mine = R.mix_sources_on_array([sig[i] for i in ids], [src[i] for i in ids], fs, mic, 343.0)
+        print(f"I mix {tag} {ids}: {got.shape}, oracle-vs-ref {rel_to_max(mine, got):.2e}")
+        assert mine.shape == got.shape and rel_to_max(mine, got) < 1e-13
+        out[f"mix_{tag}"], out[f"mix_{tag}_ids"] = got, np.array(ids)
+    for d in (0.3, 7.5, 123.456, 15.0, 0.5):                  # the filter itself at a few delays
+        di, h = dsp.standard._standard_backend._fractional_delay_filter(d, 30, 60)
+        dm, hm = R.fractional_delay_filter(d)
+        assert di == dm and np.array_equal(h, hm), d
+    np.savez_compressed(os.path.join(GOLDEN, "sources_on_array.npz"), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "sources":     # regenerate only the source-simulation fixture
+        sources_golden(ref_loader.load())
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "fft":         # regenerate only the FFT-method fixture
         fft_golden(ref_loader.load())
         return
@@ -346,6 +388,7 @@ def main():
     stft_golden(dsp)
     tf_golden(dsp)
     fft_golden(dsp)
+    sources_golden(dsp)
     print("golden vectors written to", GOLDEN)
 
 

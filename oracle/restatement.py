@@ -236,6 +236,70 @@ def transfer_function(x_out, x_in, fs, wl, window="hann", overlap_percent=50, de
     return np.fft.rfftfreq(wl, 1 / fs), tf, coherence
 
 
+# --------------------------------------------------------------------------- next row f2: source simulation in front of stage 1
+def fractional_delay_filter(delay_samples, filter_order=30, side_lobe_suppression_db=60.0):
+    """`_fractional_delay_filter` (standard/_standard_backend.py:430-493) with its Kaiser window
+    (`_kaiser_window_fractional` :290-321, beta :257-287): windowed-sinc FIR of `filter_order + 1` taps for the
+    fractional part and the integer shift that completes the delay (it may be negative for short delays)."""
+    from scipy.special import iv
+
+    delay_int = int(delay_samples)
+    frac = delay_samples - delay_int
+    if filter_order % 2:
+        m_opt = int(frac) - (filter_order - 1) / 2
+    else:
+        m_opt = np.round(frac) - filter_order / 2
+    sinc = np.sinc(np.arange(filter_order + 1) + m_opt - frac)
+    a = abs(side_lobe_suppression_db)
+    beta = 0.1102 * (a - 8.7) if a > 50 else (0.5842 * (a - 21) ** 0.4 + 0.07886 * (a - 21) if a >= 21 else 0.0)
+    alpha = filter_order / 2
+    pos = np.arange(filter_order + 1).astype(float) - frac
+    if filter_order % 2:
+        pos += 0.5
+    elif frac > 0.5:
+        pos += 1
+    z = beta * np.sqrt(np.array(1 - ((pos - alpha) / alpha) ** 2, dtype="complex"))
+    kaiser = np.real(iv(0, z)) / iv(0, beta)
+    return int(delay_int + m_opt), sinc * kaiser
+
+
+def fractional_delay_keep_length(x, fs, delay_seconds, order=30, side_lobe_suppression_db=60.0):
+    """`fractional_delay(sig, delay, keep_length=True)` on one channel (standard/latency_delay.py:159-257):
+    full convolution with the filter, shifted by the integer delay (leading zeros, or leading samples dropped
+    when it is negative), cut to the input length.  Direct convolution here, overlap-add FFT there."""
+    x = np.asarray(x, dtype=np.float64)
+    assert delay_seconds >= 0, "Delay must be positive"
+    if delay_seconds == 0:
+        return x.copy()
+    delay_samples = delay_seconds * fs
+    assert delay_samples < x.shape[0], "Delay too large for the given signal"
+    d, h = fractional_delay_filter(delay_samples, order, side_lobe_suppression_db)
+    full = np.convolve(x, h)
+    y = np.concatenate([np.zeros(d), full]) if d >= 0 else full[-d:]
+    return y[: x.shape[0]]
+
+
+def monopole_on_array(x, fs, source_xyz, mic_xyz, c=343.0):
+    """`MonopoleSource.get_signals_on_array` (beamforming/beamforming.py:1427-1458): channel m is the emitted
+    signal delayed by r_m / c and divided by 1 + r_m, r_m from the expansion-formula distance matrix."""
+    r = distance_matrix(np.asarray(mic_xyz, dtype=np.float64), np.asarray(source_xyz, dtype=np.float64)[None, :])[:, 0]
+    return np.stack([fractional_delay_keep_length(x, fs, r[m] / c) / (1.0 + r[m]) for m in range(len(r))], axis=1)
+
+
+def mix_sources_on_array(signals, sources_xyz, fs, mic_xyz, c=343.0):
+    """`mix_sources_on_array` (beamforming/beamforming.py:1461-1511): sum of the sources' array signals; when the
+    emitted signals differ in length the running sum and the next emitted signal are trimmed to the shorter."""
+    out = monopole_on_array(signals[0], fs, sources_xyz[0], mic_xyz, c)
+    total = out.shape[0]
+    for x, xyz in zip(signals[1:], sources_xyz[1:]):
+        x = np.asarray(x, dtype=np.float64)
+        if total != x.shape[0]:
+            total = min(total, x.shape[0])
+            out, x = out[:total], x[:total]
+        out = out + monopole_on_array(x, fs, xyz, mic_xyz, c)
+    return out
+
+
 # --------------------------------------------------------------------------- next row f3: single-FFT spectrum and CSM
 def spectrum_fft(x, fs, scaling="fftbackward", pad_to_fast_length=True):
     """FFT branch of `Signal.get_spectrum` (classes/signal.py:903-946, smoothing = 0, no time window): one rfft over
@@ -272,9 +336,13 @@ def csm_fft(spectrum, scaling, fs):
     scaling's factor evaluated -- as the reference does -- for a time length of `nb // 2 + 1`, and the amplitude
     scalings take the element-wise square root."""
     sp = np.asarray(spectrum, dtype=np.complex128)
-    csm = sp[:, :, None] * sp[:, None, :].conj()
+    full = sp[:, :, None] * sp[:, None, :].conj()
     idx = np.arange(sp.shape[1])
-    csm[:, idx, idx] = (np.abs(sp) ** 2).astype(np.complex128)
+    # built like the reference (:418-426): lower triangle with half the diagonal, plus its conjugate transpose --
+    # this fixes the sign of zero imaginary parts (real DC / Nyquist bins), i.e. the branch of the square root below
+    low = np.tril(full, -1)
+    low[:, idx, idx] = 0.5 * full[:, idx, idx]
+    csm = low + np.swapaxes(low, 1, 2).conj()
     sc = scaling.lower()
     if sc == "fftbackward":
         return csm

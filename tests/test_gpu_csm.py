@@ -206,6 +206,5 @@ def test_get_spectrum_welch_golden(golden_dir, scaling):
     # the auto-spectra are the diagonal of the CSM
     c = s.get_csm()[1]
     assert np.allclose(sp[1:], np.einsum("fii->fi", c).real[1:], rtol=1e-10)
-    s.spectrum_method = dsp.SpectrumMethod.FFT
-    with pytest.raises(NotImplementedError):
-        s.get_spectrum()
+    s.spectrum_method = dsp.SpectrumMethod.FFT               # the single-FFT branch (tests/test_gpu_fft_method.py)
+    assert s.get_spectrum()[1].shape[0] != sp.shape[0]

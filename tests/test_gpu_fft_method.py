@@ -72,6 +72,11 @@ def test_csm_fft_function(sc):
     """`_csm_fft` (reference _spectral_methods.py:374-443) as a function: host spectrum in, host matrix out."""
     rng = np.random.default_rng(5)
     sp = rng.standard_normal((1025, 7)) + 1j * rng.standard_normal((1025, 7))
+    # real DC / Nyquist bins of both signs: negative real products sit on the branch cut of the square root the
+    # amplitude scalings take, and the sign of the zero imaginary part (fixed by HOW the reference builds the matrix)
+    # decides between +i and -i
+    sp[0] = rng.standard_normal(7)
+    sp[-1] = rng.standard_normal(7)
     csm = _csm_fft(sp, getattr(dsp.SpectrumScaling, sc), None, 44100)
     ref = R.csm_fft(sp, sc, 44100)
     assert csm.shape == ref.shape == (1025, 7, 7) and csm.dtype == np.complex128

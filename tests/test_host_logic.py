@@ -216,3 +216,28 @@ def test_spectrum_holder_and_transfer_function_argument_checks():
         compute_transfer_function(dsp.Signal(None, np.c_[x, x[:, :1]], 8000), a, 256)
     with pytest.raises(ValueError):
         compute_transfer_function(a, a, 256, "H1")
+
+
+def test_fractional_delay_filters_and_source_checks():
+    """Host side of the source simulator (next row f2): the vectorised filter design against the oracle's
+    one-delay restatement of reference _standard_backend.py:430-493, and MonopoleSource's constructor asserts."""
+    from dsptoolbox_b200.standard._standard_backend import _fractional_delay_filter, fractional_delay_filters
+    rng = np.random.default_rng(0)
+    d = np.concatenate([rng.uniform(0, 400, 500), [0.3, 0.5, 0.93, 15.0, 1e-4, 7.5, 2.999999]])
+    shift, taps = fractional_delay_filters(d)
+    assert taps.shape == (len(d), 31) and shift.dtype == np.int64
+    for i, v in enumerate(d):
+        s0, h0 = R.fractional_delay_filter(v)
+        assert s0 == shift[i] and np.max(np.abs(h0 - taps[i])) < 4e-15
+    for order in (7, 12, 31):                       # odd orders take the other centring rule
+        s0, h0 = R.fractional_delay_filter(4.7, order, 40.0)
+        s1, h1 = _fractional_delay_filter(4.7, order, 40.0)
+        assert s0 == s1 and np.max(np.abs(h0 - h1)) < 4e-15
+    sig = dsp.Signal(None, rng.standard_normal(100), 8000)
+    assert dsp.beamforming.MonopoleSource(sig, [[0, 0, 1]]).coordinates.shape == (3,)
+    with pytest.raises(AssertionError):
+        dsp.beamforming.MonopoleSource(dsp.Signal(None, rng.standard_normal((100, 2)), 8000), [0, 0, 1])
+    with pytest.raises(AssertionError):
+        dsp.beamforming.MonopoleSource(sig, [0, 1])
+    with pytest.raises(AssertionError):
+        dsp.beamforming.mix_sources_on_array([], dsp.beamforming.MicArray(POINTS))

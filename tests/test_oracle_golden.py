@@ -188,3 +188,19 @@ def test_fft_method_next_row(golden_dir):
         _, spb = R.spectrum_fft(g[f"x_{i}"], int(g["fs"]), "fftbackward", fast)
         csm = R.csm_fft(spb, sc, int(g["fs"]))
         assert np.max(np.abs(csm - g[f"csm_{i}"])) <= 1e-13 * np.max(np.abs(g[f"csm_{i}"]))
+
+
+def test_sources_next_row(golden_dir):
+    """Next row f2: the oracle's fractional-delay source simulation against the reference's MonopoleSource /
+    mix_sources_on_array, including a source on a microphone (zero delay) and one 2 cm away (negative shift)."""
+    g = np.load(os.path.join(golden_dir, "sources_on_array.npz"))
+    fs, mic, src = int(g["fs"]), g["mic"], g["src"]
+    for i in range(int(g["n_src"])):
+        got = R.monopole_on_array(g[f"x_{i}"], fs, src[i], mic, float(g["c"]))
+        assert np.max(np.abs(got - g[f"on_array_{i}"])) <= 1e-13 * np.max(np.abs(g[f"on_array_{i}"]))
+    for tag in ("equal", "ragged", "ragged2"):
+        ids = g[f"mix_{tag}_ids"]
+        got = R.mix_sources_on_array([g[f"x_{i}"] for i in ids], [src[i] for i in ids], fs, mic, float(g["c"]))
+        assert got.shape == g[f"mix_{tag}"].shape
+        assert np.max(np.abs(got - g[f"mix_{tag}"])) <= 1e-13 * np.max(np.abs(g[f"mix_{tag}"]))
+    assert R.fractional_delay_filter(0.93)[0] == -14 and R.fractional_delay_filter(140.2)[0] == 125
