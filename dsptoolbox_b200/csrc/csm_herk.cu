@@ -293,8 +293,18 @@ __global__ void csm_rank1_kernel(const double2 *__restrict__ X, int M, int64_t n
     double2 v = make_double2(b.x * a.x + b.y * a.y, __dadd_rn(__dmul_rn(b.x, a.y), __dmul_rn(-b.y, a.x)));   // conj(b) a
     if (j < i) v.y = __dadd_rn(0.0, -v.y);
     if (i == j) v.y = 0.0;
-    if (halve_edges && (f == 0 || f == nb - 1)) { v.x *= 0.5; v.y *= 0.5; }
-    v.x *= factor; v.y *= factor;
+    if (halve_edges) {
+        // numpy divides / multiplies the complex matrix by a real number as by the complex number (x + 0i): for finite
+        // values that only touches zero imaginary parts -- (vi - vr * 0) / 2 turns a -0 behind a negative real part
+        // into +0 -- which is exactly what decides the branch of the square root below
+        if (f == 0 || f == nb - 1) {
+            v.y = __dmul_rn(__dsub_rn(v.y, __dmul_rn(v.x, 0.0)), 0.5);
+            v.x *= 0.5;
+        }
+        v.y = __dadd_rn(__dmul_rn(v.x, 0.0), __dmul_rn(v.y, factor));
+        v.x *= factor;
+    }
+    if (i == j) v.y = 0.0;
     if (amplitude_sqrt) v = (i == j) ? make_double2(sqrt(v.x), 0.0) : csqrt_principal(v);
     out[idx] = v;
 }

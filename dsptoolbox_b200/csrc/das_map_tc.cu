@@ -123,25 +123,38 @@ template <int NB, int PASSES> struct TcCfg {
     // Synthesis/reduction warp groups (chunks are dealt round-robin: group j synthesises chunks j, j + NG, ...).  A
     // group reduces a chunk DLAG of its OWN chunks after it synthesised it (it keeps the h' of DLAG chunks in
     // registers): synthesis -> fullA -> MMA issue -> tensor pipe -> tdone -> TMEM load is a dependent chain of
-    // ~2000 cycles, and with DLAG = 1 each group had exactly one chunk in flight -- the whole kernel then ran at
-    // NG chunks per chain latency however deep the rings were (ablation: 9.0 of 13.6 ms WITHOUT any MMA).
+    // ~2000 cycles.  With DLAG = 1 a group reduces chunk i - NG right before it synthesises chunk i, i.e. right
+    // after it synthesised chunk i - NG: it sits out that whole chain every time (ncu, r2: 31 % of the synthesis
+    // warps' samples on the tdone wait, tensor pipe 54 % busy).  With DLAG = 2 the chain has one own chunk
+    // (~2500 cycles of synthesis) to complete.
     // Before it synthesises chunk i a group passes the chunks (i - (DLAG + 1) NG, i - DLAG NG] of the event stream,
     // waiting on `tdone` of its own chunk and of any block's lowest chunk in that range.  mbarrier waits only see
-    // the PARITY of a phase, so the ring slot of such a chunk must not be able to complete a further use meanwhile:
-    // chunk c + NSA is only synthesised after chunk i when c + NSA > i, i.e. NSA >= (DLAG + 1) NG.
+    // the PARITY of a phase, so a tdone barrier must not complete a further use while a group still waits on it:
+    // the tdone barriers form their OWN ring of TD slots, indexed by the chunk sequence number.  The tensor pipe
+    // cannot run further ahead of the slowest group than the end of the accumulator after the one that group
+    // is reading (tempty), i.e. less than 2 NKC <= TD chunks (scripts/sim_protocol.py models it).  The A ring only
+    // has to cover synthesis -> MMA retirement: NSA >= DLAG NG keeps the groups from starving the issue warps.
 #ifndef B2_DLAG
-#define B2_DLAG 1
+#define B2_DLAG 2
 #endif
-    static constexpr int NG = (B2_DLAG + 1) * B2_NG <= NSA ? B2_NG : (2 * B2_NG <= NSA ? B2_NG : (NSA >= 4 ? 2 : 1));
-    static constexpr int DLAG = (B2_DLAG + 1) * NG <= NSA ? B2_DLAG : ((NSA / NG - 1) >= 1 ? (NSA / NG - 1) : 1);
-    static_assert(NG == 1 || (DLAG + 1) * NG <= NSA, "a ring slot could complete a further use while a group still waits for it");
+    static constexpr int TD = 2 * (MAX_MICS / KCH);
+    static_assert((TD & (TD - 1)) == 0, "the tdone ring is indexed with a mask");
+    static constexpr int NG = (B2_NG <= NSA && B2_DLAG * B2_NG <= NSA) ? B2_NG : (NSA >= 4 ? 2 : 1);
+    static constexpr int DLAG = B2_DLAG * NG <= NSA ? B2_DLAG : 1;
+    static_assert(NG <= NSA && DLAG * NG <= NSA, "the A ring is too shallow for the chunks the groups keep in flight");
     static constexpr int NGEN = TILE_G * NG;                           // warp w owns TMEM lanes 32 (w % 4) ...
     static constexpr int NS_WARPS = NGEN / 32;
     static constexpr int W_MMA = NS_WARPS;            // two MMA issue warps, then their two B loader warps
     static constexpr int THREADS = NGEN + 128;
     static constexpr int PARTIAL_ROWS = NG > 1 ? NG - 1 : 1;           // per-bin partial sums handed to the first group
     static constexpr int TMEM_COLS = 2 * UMMA_N;                       // two accumulator buffers
-    static constexpr int NBARS = 3 * NSA + 2 * NSB + 2;
+    // Register file split (setmaxnreg): the issue / loader warpgroup keeps REGS_IO registers per thread, the synthesis
+    // warpgroups take the rest of the 64 K registers -- the h' of DLAG chunks (32 registers per chunk) live there.
+    static constexpr bool SETMAXNREG = NG >= 3;      // 512 threads: 128 registers each at launch (fewer groups get enough without it)
+    static constexpr int REGS_IO = 48;
+    static constexpr int REGS_S_RAW = ((65536 - 128 * REGS_IO) / NGEN) / 8 * 8;
+    static constexpr int REGS_S = REGS_S_RAW > 232 ? 232 : REGS_S_RAW;
+    static constexpr int NBARS = 2 * NSA + TD + 2 * NSB + 2 + 8;     // ... + per-quadrant hand-off of the bin sums (full, free)
     static constexpr int SMEM = NSA * A_STAGE + NSB * B_STAGE + PARTIAL_ROWS * TILE_G * 4 + PROG_MAX * 2 + NBARS * 8 + 16;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -183,32 +196,65 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 // phase completes or the time hint expires, so waiting warps do not burn issue slots spinning.
 // Watchdog: a wait that lasts longer than ~4 s can only be a protocol bug; the kernel then traps (the launch
 // fails with an error) instead of hanging the GPU until somebody kills the process.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
-    unsigned long long t_begin, t_now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
-    uint32_t done = 0, spins = 0;
-    do {
+// B2_WAIT_HINT: pass a suspend-time hint (ptxas then emits TRYWAIT + NANOSLEEP.SYNCS + re-check); without it the
+// wait is a plain loop of hardware-bounded TRYWAITs, like CUTLASS' ClusterBarrier::wait.
+#ifdef B2_WAIT_HINT
+#define B2_TRY_WAIT "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#else
+#define B2_TRY_WAIT "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    // (inlined: a real call cannot be register-allocated in a kernel that uses setmaxnreg.)  The inner loop is
+    // nothing but try_wait + branch -- the poll loops of the issue / loader warps were 15 % of all instructions the
+    // kernel executed when every poll also kept a spin counter and sampled the timer every 16th time.
+    unsigned long long t_begin = 0, t_now;
+    for (;;) {
+        uint32_t done;
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
+            ".reg .u32 n;\n\t"
+            "mov.u32 n, 4096;\n\t"
+            "B2_POLL_%=:\n\t"
+            B2_TRY_WAIT
+            "@p bra B2_DONE_%=;\n\t"
+            "sub.u32 n, n, 1;\n\t"
+            "setp.ne.u32 p, n, 0;\n\t"
+            "@p bra B2_POLL_%=;\n\t"
+            "mov.u32 %0, 0;\n\t"
+            "bra B2_OUT_%=;\n\t"
+            "B2_DONE_%=:\n\t"
+            "mov.u32 %0, 1;\n\t"
+            "B2_OUT_%=:\n\t"
             "}"
             : "=r"(done)
             : "r"(bar), "r"(parity), "r"(0x989680u)
             : "memory");
-        if (!done && ((++spins & 15) == 0)) {
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-            if (t_now - t_begin > 4000000000ull) __trap();
-        }
-    } while (!done);
+        if (done) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+        if (t_begin == 0) t_begin = t_now;
+        else if (t_now - t_begin > 4000000000ull) __trap();
+    }
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {          // non-blocking: has the phase completed?
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        B2_TRY_WAIT
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(done)
@@ -411,8 +457,9 @@ __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__
 // synthesis warps do not re-derive the pair / block structure for every chunk:
 //   bits 0-5 kc | bit 6: the chunk's own columns belong to a block of this pair (reduce them here) |
 //   bits 7-9: accumulator of that block within the bin | bits 10-12: (first column of the chunk in its block) / 16 |
-//   bit 13: lowest chunk of its block (the accumulator has been read completely) | bit 14: last chunk of the bin
-constexpr uint32_t PG_RED = 1u << 6, PG_LASTBLK = 1u << 13, PG_ENDBIN = 1u << 14;
+//   bit 13: lowest chunk of its block (the accumulator has been read completely) | bit 14: last chunk of the bin |
+//   bit 15: one of the last NG chunks of its block (the group that owns it will not read this accumulator again)
+constexpr uint32_t PG_RED = 1u << 6, PG_LASTBLK = 1u << 13, PG_ENDBIN = 1u << 14, PG_LASTOWN = 1u << 15;
 
 template <int NB, int PASSES>
 __global__ void __launch_bounds__(TcCfg<NB, PASSES>::THREADS, 1)
@@ -434,7 +481,8 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
     const uint32_t smem_base = smem_u32(smem);
     // B barriers: ring 0 (NSB0 slots) then ring 1 (NSB1 slots)
     const uint32_t fullA = smem_u32(bars), emptyA = fullA + 8 * NSA, fullB = emptyA + 8 * NSA, emptyB = fullB + 8 * NSB;
-    const uint32_t tdone = emptyB + 8 * NSB, tempty = tdone + 8 * NSA;
+    const uint32_t tdone = emptyB + 8 * NSB, tempty = tdone + 8 * CF::TD;
+    const uint32_t pfull = tempty + 16, pfree = pfull + 32;              // one pair per quadrant of TMEM lanes
     const uint32_t b_ring = smem_base + NSA * CF::A_STAGE;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -457,10 +505,11 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         for (int s = 0; s < NSA; ++s) {
             mbar_init(fullA + 8 * s, 4);          // one arrival per warp of the group that owns the chunk
             mbar_init(emptyA + 8 * s, 2);         // both issue warps release every tile
-            mbar_init(tdone + 8 * s, 1);          // committed once per chunk by the warp that issues its last relevant step
         }
+        for (int s = 0; s < CF::TD; ++s) mbar_init(tdone + 8 * s, 1);   // committed once per chunk by the warp that issues its last relevant step
         for (int s = 0; s < NSB; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) mbar_init(tempty + 8 * b, NS_WARPS);
+        for (int q = 0; q < 4; ++q) { mbar_init(pfull + 8 * q, NG > 1 ? NG - 1 : 1); mbar_init(pfree + 8 * q, 1); }
         fence_barrier_init();
         // the per-bin chunk program
         int n = 0, accbase = 0;
@@ -473,6 +522,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                     const int accoff = accbase + ((blk == b1 || b1 < 0) ? 0 : 1);   // completion order: b1 (if any), then b0
                     e |= PG_RED | (uint32_t(accoff) << 7) | (uint32_t((kc * KCH - blk * NB) / KCH) << 10);
                     if (kc == first_chunk(blk)) e |= PG_LASTBLK;
+                    if (kc - first_chunk(blk) < NG) e |= PG_LASTOWN;
                 }
                 prog[n] = uint16_t(e);
             }
@@ -488,6 +538,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
 
     if (warp < NS_WARPS) {
         // =========================== steering synthesis -> A operand tiles, and the reduction of T ===========================
+        if constexpr (CF::SETMAXNREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CF::REGS_S));
         const int r = tid & 127, grp = tid >> 7, quad = warp & 3;
         const uint32_t lane_base = uint32_t(quad * 32) << 16;
         const uint32_t row_off = uint32_t((r >> 3) * 1024 + (r & 7) * 128);     // this row inside a swizzled tile
@@ -501,7 +552,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
 #ifdef B2_MAP_PROFILE
         const long long t_role0 = clock64();
 #endif
-        if (NG > 1 && grp == 0) asm volatile("bar.arrive %0, %1;" ::"r"(2 + quad), "n"(32 * NG) : "memory");   // hand-off slots start free
+        uint32_t hpar = 0;                                   // parity of the bin-sum hand-off phase (one phase per bin)
         for (int unit = blockIdx.x; unit < ntiles * nsplit; unit += gridDim.x) {
             B2_UNIT_DECODE
             const int64_t g = int64_t(tile) * TILE_G + r;
@@ -583,12 +634,13 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             uint32_t s_slot = (seq_base + uint32_t(grp)) % NSA, s_ph = ((seq_base + uint32_t(grp)) / NSA) & 1;
             // events / reduction: every chunk of the unit in order
             int e_idx = 0, e_cib = 0, e_fi = f_begin, e_mod = 0;
-            uint32_t e_slot = seq_base % NSA, e_ph = (seq_base / NSA) & 1;
+            uint32_t e_slot = seq_base % CF::TD, e_ph = (seq_base / CF::TD) & 1;          // tdone ring cursor
             float bf = s_fi < f_end ? float(freqs[s_fi] * inv_c) : 0.0f;
             float2 hkeep[DLAG][KCH];                          // h' of the last DLAG own chunks: (Re, Im) per microphone (pairs)
             float2 pacc = make_float2(0.f, 0.f);              // sum of Re T Re h' / of (-Im T) Im h', current bin
             float2 pre = make_float2(0.f, 0.f);               // planar layout: (sum Re T Re h', sum Im T Im h')
             double acc_map = 0.0;
+            bool arrived = false;                             // tempty arrival of the current block already made
 
             // distances of the next own chunk (4 x 16 bytes), fetched one own-chunk ahead
             float4 dnext[4];
@@ -600,8 +652,32 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             };
             if (grp < total) prefetch(s_cib);
 
+            // group 0: the bin whose sums of the other groups are still awaited
+            bool pending = false;
+            float pend_p = 0.f;
+            int pend_fi = 0;
+            uint32_t pend_par = 0;
+            auto finish_bin = [&](bool block) {
+                double extra = 0.0;
+                if (NG > 1) {
+                    if (block) mbar_wait(pfull + 8 * quad, pend_par);
+                    else if (!mbar_test(pfull + 8 * quad, pend_par)) return;
+#pragma unroll
+                    for (int k = 0; k < NG - 1; ++k) extra += double(partial[k * TILE_G + r]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pfree + 8 * quad);
+                }
+                double p = (double(pend_p) + extra) * c2;                              // |h|^2 scale of this grid point
+                if (PASSES == 4) p /= double(bin_scale[pend_fi]);                      // power-of-two scale of L_f
+                if (clamp_negative && p < 0.0) p = 0.0;                                // beamforming.py:871-872
+                acc_map += weights[pend_fi] * p;                                       // :875-876
+                if (per_bin != nullptr && g < G) per_bin[g * nbins + pend_fi] = p;
+                pending = false;
+            };
+
             // one chunk of the event stream: reduce it if it is ours, then the per-chunk events
             auto pass_chunk = [&](const float2 (&hk)[KCH]) {
+                if (NG > 1 && pending) finish_bin(false);
                 const uint32_t e = prog[e_cib];
                 const uint32_t buf = (accs + ((e >> 7) & 7u)) & 1u;
                 if (e_mod == grp && (e & PG_RED)) {
@@ -639,51 +715,57 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                         }
                     }
                     PROF_ADD(24 + 2, prof);
+                    if (e & PG_LASTOWN) {
+                        // this group's last own chunk of the block: it will not read this accumulator again and says so
+                        // NOW -- the issue warp that overwrites the buffer for the next bin then only waits for the
+                        // group that reads the block's lowest chunk, not for every group to walk its event stream up
+                        // to that chunk (they do so between two syntheses, thousands of cycles later)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty + 8 * buf);
+                        arrived = true;
+                    }
                 }
-                if (e & PG_LASTBLK) {                        // this warp has read all its columns of the accumulator
-                    // A group that does not own this chunk still waits until the accumulator is COMPLETE before it
-                    // declares it read: otherwise, when a bin has fewer chunks than a few groups' strides, its arrival
-                    // for the NEXT use of the TMEM buffer could be counted for this one (scripts/sim_protocol.py).
-                    if (e_mod != grp) mbar_wait(tdone + 8 * e_slot, e_ph);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty + 8 * buf);
+                if (e & PG_LASTBLK) {
+                    if (!arrived) {
+                        // A group without an own chunk in this block (fewer chunks than groups) waits until the
+                        // accumulator is COMPLETE before it declares it read: otherwise its arrival for the NEXT use of
+                        // the TMEM buffer could be counted for this one (scripts/sim_protocol.py).  [An own chunk's tdone
+                        // wait gives the same guarantee: the MMAs of this use were issued after the previous phase.]
+                        mbar_wait(tdone + 8 * e_slot, e_ph);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty + 8 * buf);
+                    }
+                    arrived = false;
                 }
                 if (e & PG_ENDBIN) {
-                    // end of the bin: combine the NG threads of the row, finish P[g, f] in fp64
+                    // end of the bin: the NG threads of a row combine their sums through shared memory.  Groups 1.. write
+                    // theirs and signal `pfull`; group 0 finishes P[g, f] in fp64 -- but does NOT wait for the others at
+                    // this point: it keeps its own sum pending and completes the bin at a later chunk, when `pfull` has
+                    // fired (finish_bin polls without blocking).  With the blocking named-barrier hand-off every group sat
+                    // out the skew between the groups once per bin (role profile r2: ~1800 cycles per own chunk).
                     const float ptot = CF::PLANAR ? pre.x - pre.y : pacc.x + pacc.y;
                     pacc = make_float2(0.f, 0.f);
                     pre = make_float2(0.f, 0.f);
-                    double extra = 0.0;
-                    if (NG > 1) {
-                        // hand-off through shared memory inside the quadrant's NG warps, two named barriers per quadrant:
-                        // "slots free" (2 + quad: the reader arrives, the writers wait) and "slots full" (6 + quad)
-                        if (grp > 0) {
-                            asm volatile("bar.sync %0, %1;" ::"r"(2 + quad), "n"(32 * NG) : "memory");
-                            partial[(grp - 1) * TILE_G + r] = ptot;
-                            __threadfence_block();
-                            asm volatile("bar.arrive %0, %1;" ::"r"(6 + quad), "n"(32 * NG) : "memory");
-                        } else {
-                            asm volatile("bar.sync %0, %1;" ::"r"(6 + quad), "n"(32 * NG) : "memory");
-#pragma unroll
-                            for (int k = 0; k < NG - 1; ++k) extra += double(partial[k * TILE_G + r]);
-                            asm volatile("bar.arrive %0, %1;" ::"r"(2 + quad), "n"(32 * NG) : "memory");
-                        }
+                    if (NG > 1 && grp > 0) {
+                        mbar_wait(pfree + 8 * quad, hpar ^ 1);              // group 0 has read the previous bin's sums
+                        partial[(grp - 1) * TILE_G + r] = ptot;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(pfull + 8 * quad);
+                    } else {
+                        if (pending) finish_bin(true);                      // (only if a whole bin went by without a poll succeeding)
+                        pend_p = ptot; pend_fi = e_fi; pend_par = hpar; pending = true;
+                        finish_bin(NG == 1);
                     }
-                    if (grp == 0) {
-                        double p = (double(ptot) + extra) * c2;                            // |h|^2 scale of this grid point
-                        if (PASSES == 4) p /= double(bin_scale[e_fi]);                     // power-of-two scale of L_f
-                        if (clamp_negative && p < 0.0) p = 0.0;                            // beamforming.py:871-872
-                        acc_map += weights[e_fi] * p;                                      // :875-876
-                        if (per_bin != nullptr && g < G) per_bin[g * nbins + e_fi] = p;
-                    }
+                    hpar ^= 1;
                     ++e_fi;
                     e_cib = -1;
                     accs += uint32_t(NBLK);
                 }
                 ++e_cib; ++e_idx;
                 if (++e_mod == NG) e_mod = 0;
-                if (++e_slot == NSA) { e_slot = 0; e_ph ^= 1; }
+                if (++e_slot == uint32_t(CF::TD)) { e_slot = 0; e_ph ^= 1; }
             };
 
             // synthesis of the own chunk at (s_fi, s_cib): 16 microphones of this row -> A tile + hk
@@ -694,10 +776,10 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                     dn[2 * gi] = make_float2(dnext[gi].x, dnext[gi].y);
                     dn[2 * gi + 1] = make_float2(dnext[gi].z, dnext[gi].w);
                 }
-                // the next own chunk: position, bin, distances (the loads have a whole chunk to land)
+                // the next own chunk: position and bin (its distances are fetched at the end of this synthesis, when the
+                // registers of this chunk's distances are free again; the reduction and the waits in between hide the L2 latency)
                 int n_cib = s_cib + NG, n_fi = s_fi;
                 while (n_cib >= cpb) { n_cib -= cpb; ++n_fi; }
-                if (n_fi < f_end) prefetch(n_cib);
                 PROF_T0();
                 mbar_wait(emptyA + 8 * s_slot, s_ph ^ 1);
                 PROF_ADD(24 + 3, prof);
@@ -772,6 +854,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 else if (akind == AMP_R) synth(std::integral_constant<int, AMP_R>{});
                 else synth(std::integral_constant<int, AMP_ONE>{});
                 PROF_ADD(24 + 4, prof);
+                if (n_fi < f_end) prefetch(n_cib);
                 // generic-proxy writes -> visible to the MMA (async proxy); one arrival per warp
                 fence_proxy_async();
                 __syncwarp();
@@ -800,6 +883,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 }
             }
             while (e_idx < total) pass_chunk(hkeep[0]);
+            if (pending) finish_bin(true);
             seq_base += uint32_t(total);
             // the bins of a tile may be split over several work units: the map is zeroed by the
             // launcher and every unit adds its weighted partial sum
@@ -808,9 +892,13 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
 #ifdef B2_MAP_PROFILE
         if (prof) atomicAdd(&g_map_prof[24], (unsigned long long)(clock64() - t_role0));
 #endif
-        // balance the reader's last "slots free" arrival so that no named barrier is left half-arrived
-        if (NG > 1 && grp > 0) asm volatile("bar.sync %0, %1;" ::"r"(2 + quad), "n"(32 * NG) : "memory");
-    } else if (warp == W_MMA || warp == W_MMA + 1) {
+        // (the two register-budget regions do not join again: each side has its own copy of the epilogue)
+        tc_fence_before();
+        __syncthreads();
+        return;
+    } else {
+      if constexpr (CF::SETMAXNREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CF::REGS_IO));   // the whole warpgroup, one instruction
+      if (warp == W_MMA || warp == W_MMA + 1) {
         // =========================== MMA issue ===========================
         // tcgen05.mma issue is back-pressured by the tensor pipe (the issuing thread advances at the pipe's rate), and
         // every step also costs its issuing thread a few hundred cycles the pipe cannot use (mbarrier waits, elect,
@@ -929,7 +1017,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                                 }
                             }
                             // tcgen05.commit: the barriers are signalled when the MMAs issued so far retire
-                            if (signal_done) umma_commit(tdone + 8 * sa);      // columns of chunk kc are final -> reduction
+                            if (signal_done) umma_commit(tdone + 8 * (seqA & uint32_t(CF::TD - 1)));   // columns of chunk kc are final -> reduction
                             umma_commit(emptyA + 8 * sa);                      // this warp is done with the A tile
                             umma_commit(emptyBm + 8 * sb);
                         }
@@ -981,6 +1069,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 }
             }
         }
+      }
     }
 
     tc_fence_before();

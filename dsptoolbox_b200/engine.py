@@ -268,7 +268,7 @@ def _csm_partial_sums(torch, lib, prec, device, x, length, wl, step, window, det
     host_bytes = (k1 - k0) * step * M * itemsize if on_host else 0
     chunks = _frame_chunks(k0, k1, tile, max_frames, host_bytes)
 
-    win = torch.from_numpy(np.ascontiguousarray(window, dtype=np.float64)).to(device).to(rdt)
+    win = _device_const(window, device).to(rdt)          # cached: a pageable upload would stall the host behind the stream
     tw = _twiddles(wl, prec, device)
     S = (torch.empty((nb, M), dtype=torch.float64, device=device) if diag_only
          else torch.empty((nb, packed_size(M)), dtype=torch.complex128, device=device))
@@ -369,7 +369,7 @@ def frame_spectra(x, length: int, wl: int, step: int, window: np.ndarray, detren
     tile = max(16, N.check(lib.b2_welch_frame_tile(wl, prec), "b2_welch_frame_tile"))
     bytes_per_frame = nb * M * (16 if prec == N.F64 else 8)
     max_frames = max(tile, (config.spectra_budget_bytes // bytes_per_frame) // tile * tile)
-    win = torch.from_numpy(np.ascontiguousarray(window, dtype=np.float64)).to(device).to(rdt)
+    win = _device_const(window, device).to(rdt)          # cached: a pageable upload would stall the host behind the stream
     tw = _twiddles(wl, prec, device)
     out = torch.empty((nb, K_total, M), dtype=torch.complex128, device=device)
     kc = 0
@@ -454,7 +454,7 @@ def rfft_frames(xc, Lp: int, M: int, wl: int, step: int, n_frames: int, n: int, 
     device = xc.device
     nb = n // 2 + 1
     out = torch.empty((nb, n_frames, M), dtype=torch.complex128, device=device)
-    win = torch.from_numpy(np.ascontiguousarray(window, dtype=np.float64)).to(device)
+    win = _device_const(window, device)
     code = N.F64 if xc.dtype == torch.float64 else N.F32
     with torch.cuda.device(device):
         plan = _fft_plan(n, device)
@@ -579,11 +579,13 @@ _const_cache: dict = {}
 
 
 def _device_const(arr, device):
-    """float64 device copy of a SMALL host array (bin frequencies, Simpson weights, microphone positions),
-    cached by content so that repeated map calls do not re-upload them from pageable memory."""
+    """float64 device copy of a SMALL host array (window, bin frequencies, Simpson weights, microphone positions),
+    cached by content so that repeated calls do not re-upload them from pageable memory: such a copy makes the host
+    wait until everything queued on the stream has finished, and the kernels enqueued after it then start late
+    (measured: +55 ms per step of stage 1 when it follows a 1.6 s map kernel, profiles/r2_stage1_host_stall.txt)."""
     torch = _torch()
     a = np.ascontiguousarray(arr, dtype=np.float64)
-    if a.nbytes > (1 << 18):
+    if a.nbytes > (1 << 20):
         return torch.from_numpy(a).to(device)
     key = (a.shape, a.tobytes(), str(device))
     t = _const_cache.get(key)

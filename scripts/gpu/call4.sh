@@ -1,0 +1,16 @@
+set -x
+mkdir -p gpurun_out
+cd $GRAFT_REPO_ROOT
+# new map kernel first: correctness on the map tests with a hard timeout (watchdog traps after 4 s per wait)
+timeout 900 python -m pytest tests/test_gpu_das.py tests/test_gpu_fullsize.py tests/test_gpu_cfg3.py -x -q > gpurun_out/r2c4_pytest_map.log 2>&1; echo "pytest map rc=$?" >> gpurun_out/r2c4_pytest_map.log
+tail -3 gpurun_out/r2c4_pytest_map.log
+for v in "" d1 ng2d2 ng2d3; do
+  echo "== variant [$v]" >> gpurun_out/r2c4_map.txt
+  if [ -n "$v" ]; then export B2DSP_LIB=$GRAFT_REPO_ROOT/dsptoolbox_b200/csrc/variants/libb2dsp_$v.so; else unset B2DSP_LIB; fi
+  timeout 120 python scripts/run_map.py 256 37888 512 f16x3 4 >> gpurun_out/r2c4_map.txt 2>&1; echo "rc=$?" >> gpurun_out/r2c4_map.txt
+done
+unset B2DSP_LIB
+cat gpurun_out/r2c4_map.txt
+timeout 1800 python -m pytest tests -m gpu -x -q > gpurun_out/r2c4_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2c4_pytest.log
+tail -5 gpurun_out/r2c4_pytest.log
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2c4_bench.json 2> gpurun_out/r2c4_bench.err; echo "bench rc=$?"

@@ -12,7 +12,7 @@ deadlock the model checks that every consumer sees the tile it expects, that the
 when a synthesis warp reads them (every step that writes them has been issued) and that an accumulator is not
 overwritten before every synthesis warp has read all of its columns.
 
-usage: python scripts/sim_protocol.py M NB NSA NSB0 NSB1 NG nbins [share=1] [runs=300] [DLAG=1]
+usage: python scripts/sim_protocol.py M NB NSA NSB0 NSB1 NG nbins [share=1] [runs=300] [DLAG=1] [ND=128]
 """
 import random
 import sys
@@ -35,7 +35,7 @@ class Bar:
         return (self.phase & 1) != parity
 
 
-def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet=True, units=2, DLAG=1):
+def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet=True, units=2, DLAG=1, ND=128):
     KCH = 16
     NKC = (M + KCH - 1) // KCH
     NBLK = (M + NB - 1) // NB
@@ -43,11 +43,12 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
     b0 = lambda p: 2 * p if share else p
     b1 = lambda p: (2 * p + 1) if (share and 2 * p + 1 < NBLK) else -1
     fc = lambda b: b * NB // KCH
-    assert NG == 1 or (DLAG + 1) * NG <= NSA, "a ring slot could complete a further use while a group still waits for it"
+    assert NSA >= NG and NSA >= DLAG * NG, "the A ring is too shallow for the chunks the groups keep in flight"
+    assert ND >= 2 * NKC, "a tdone barrier could complete a further use while a group still waits for it"
     NSBs = (NSB0, NSB1)
     fullA = [Bar(1) for _ in range(NSA)]; emptyA = [Bar(2) for _ in range(NSA)]      # one arrival per owning group / both issue warps release
     fullB = [[Bar(1) for _ in range(n)] for n in NSBs]; emptyB = [[Bar(1) for _ in range(n)] for n in NSBs]   # one ring per stream
-    tdone = [Bar(1) for _ in range(NSA)]; tempty = [Bar(NG), Bar(NG)]
+    tdone = [Bar(1) for _ in range(ND)]; tempty = [Bar(NG), Bar(NG)]      # tdone: its own ring, one barrier per chunk in flight
     inA = [None] * NSA; inB = [[None] * n for n in NSBs]   # what the producers last put into a stage
     issued = {}                   # accumulator sequence number -> set of chunks multiplied into it
     readers = {}                  # accumulator sequence number -> groups that have finished reading it
@@ -60,16 +61,16 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
                     yield (fi, p, kc)
 
     def group(j):
-        seq_base = 0; r_acc = 0
+        seq_base = 0; r_acc = 0; arrived = False
         for _u in range(units):
             todo = list(chunks_of_unit())
             total = len(todo)
             e = 0
 
             def pass_chunk():
-                nonlocal e, r_acc
+                nonlocal e, r_acc, arrived
                 fi, p, kc = todo[e]
-                seq = seq_base + e; slot = seq % NSA; par = (seq // NSA) & 1
+                seq = seq_base + e; slot = seq % ND; par = (seq // ND) & 1
                 blk = kc * KCH // NB
                 if blk in (b0(p), b1(p)):
                     acc = r_acc + (0 if (blk == b1(p) or b1(p) < 0) else 1)
@@ -78,11 +79,16 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
                         assert buf_owner[acc & 1] == acc, f"G{j} reads buffer of accumulator {buf_owner[acc & 1]}, wants {acc}"
                         need = set(range(kc, NKC))
                         assert need <= issued.get(acc, set()), f"G{j} reads columns of chunk {kc} of accumulator {acc} before {sorted(need - issued.get(acc, set()))}"
+                        if kc - fc(blk) < NG:     # this group's last own chunk of the block: it is done with the accumulator
+                            readers.setdefault(acc, set()).add(j)
+                            tempty[acc & 1].arrive()
+                            arrived = True
                     if kc == fc(blk):
-                        if e % NG != j:       # not ours: still wait until the accumulator is complete before calling it read
+                        if not arrived:           # no own chunk in this block: wait until the accumulator is complete before calling it read
                             while not tdone[slot].done(par): yield (f"G{j} wait tdone (lowest chunk)", slot, par, kc)
-                        readers.setdefault(acc, set()).add(j)
-                        tempty[acc & 1].arrive()
+                            readers.setdefault(acc, set()).add(j)
+                            tempty[acc & 1].arrive()
+                        arrived = False
                 if kc == fc(b0(p)):
                     r_acc += 2 if b1(p) >= 0 else 1
                 e += 1
@@ -148,7 +154,7 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
                             issued.setdefault(acc, set()).add(kc)
                             cblk = kc * KCH // NB
                             if cblk == myblk or (my == 0 and cblk != blk0 and cblk != blk1):
-                                tdone[sa].arrive()
+                                tdone[seqA % ND].arrive()
                             emptyA[sa].arrive(); emptyB[my][sb].arrive()
                             q += 1; sb += 1
                             if sb == NSBs[my]: sb = 0; phb ^= 1
@@ -188,10 +194,11 @@ if __name__ == "__main__":
     M, NB, NSA, NSB0, NSB1, NG, nbins = (int(x) for x in a[1:8])
     share = len(a) < 9 or a[8] != "0"
     dlag = int(a[10]) if len(a) > 10 else 1
+    nd = int(a[11]) if len(a) > 11 else 128
     bad = 0
     for seed in range(int(a[9]) if len(a) > 9 else 300):
         try:
-            ok = main(M, NB, NSA, NSB0, NSB1, NG, nbins, share, seed, DLAG=dlag)
+            ok = main(M, NB, NSA, NSB0, NSB1, NG, nbins, share, seed, DLAG=dlag, ND=nd)
         except AssertionError as e:
             print("BUG (seed %d):" % seed, e); ok = False
         if not ok:

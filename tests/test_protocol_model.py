@@ -15,16 +15,19 @@ _SPEC.loader.exec_module(sim)
 
 # (M, NB, NSA, NSB0, NSB1, NG, DLAG, bins, shared A tiles): the shapes of TcCfg in das_map_tc.cu
 SHAPES = [
-    (256, 128, 9, 3, 2, 2, 3, 4, True),      # cfg5: one pair of column blocks (FP16x3)
-    (256, 128, 6, 2, 2, 2, 2, 3, True),      # single-pass TF32
-    (300, 128, 9, 3, 2, 2, 3, 3, True),      # a pair plus a lone block, chunk count off the block size
-    (520, 128, 9, 3, 2, 2, 3, 2, True),      # two pairs plus a lone block
-    (144, 128, 9, 3, 2, 2, 3, 4, True),      # second block of one chunk
-    (64, 64, 10, 3, 2, 2, 3, 5, True),       # single block
-    (16, 32, 10, 3, 2, 2, 3, 9, True),       # one chunk per bin
-    (32, 32, 10, 3, 2, 2, 3, 7, True),       # two chunks per bin
-    (256, 128, 9, 3, 2, 3, 2, 3, True),      # three groups
+    (256, 128, 7, 4, 3, 3, 2, 4, True),      # cfg5: one pair of column blocks (FP16x3)
+    (256, 128, 6, 2, 2, 3, 2, 3, True),      # single-pass TF32
+    (300, 128, 7, 4, 3, 3, 2, 3, True),      # a pair plus a lone block, chunk count off the block size
+    (520, 128, 7, 4, 3, 3, 2, 2, True),      # two pairs plus a lone block
+    (1024, 128, 7, 4, 3, 3, 2, 2, True),     # the largest array: tdone ring of 2 NKC barriers
+    (144, 128, 7, 4, 3, 3, 2, 4, True),      # second block of one chunk
+    (64, 64, 10, 4, 3, 3, 2, 5, True),       # single block
+    (16, 32, 10, 4, 3, 3, 2, 9, True),       # one chunk per bin
+    (32, 32, 10, 4, 3, 3, 2, 7, True),       # two chunks per bin
+    (256, 128, 7, 4, 3, 3, 1, 3, True),      # one own chunk in flight
+    (256, 128, 7, 4, 3, 2, 3, 3, True),      # two groups, three own chunks in flight
     (256, 128, 3, 2, 0, 1, 2, 3, False),     # split-TF32 / mixed: shallow rings, no sharing, one group
+    (64, 64, 5, 2, 0, 2, 2, 4, False),
     (100, 128, 4, 2, 0, 2, 1, 4, False),
 ]
 
@@ -36,8 +39,11 @@ def test_protocol_has_no_deadlock_or_aliasing(shape):
         assert sim.main(M, NB, NSA, NSB0, NSB1, NG, nbins, share, seed, DLAG=DLAG), (shape, seed)
 
 
-def test_too_many_chunks_in_flight_for_the_ring_are_rejected_by_the_model():
-    """(DLAG + 1) NG > NSA lets a ring slot complete a further use while a group still has to wait for it (parity
-    aliasing): the kernel's configuration clamps NG / DLAG (TcCfg); the model refuses the shape."""
+def test_shapes_the_kernel_configuration_must_not_produce_are_rejected_by_the_model():
+    """An A ring shallower than the chunks the groups keep in flight (NSA < DLAG NG) starves the issue warps, and a
+    tdone ring shorter than 2 NKC barriers lets a barrier complete a further use while a group still waits on it
+    (parity aliasing): TcCfg clamps NG / DLAG and sizes the ring for the largest array; the model refuses such shapes."""
     with pytest.raises(AssertionError):
-        sim.main(256, 128, 3, 2, 0, 2, 2, False, 0, DLAG=1)
+        sim.main(256, 128, 3, 2, 0, 2, 2, False, 0, DLAG=2)
+    with pytest.raises(AssertionError):
+        sim.main(256, 128, 7, 4, 3, 3, 2, True, 0, DLAG=2, ND=16)
