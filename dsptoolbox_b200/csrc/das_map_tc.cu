@@ -134,12 +134,17 @@ template <int NB, int PASSES> struct TcCfg {
     // cannot run further ahead of the slowest group than the end of the accumulator after the one that group
     // is reading (tempty), i.e. less than 2 NKC <= TD chunks (scripts/sim_protocol.py models it).  The A ring only
     // has to cover synthesis -> MMA retirement: NSA >= DLAG NG keeps the groups from starving the issue warps.
+    // Measured (r2, final kernel): DLAG = 2 vs 1: 12.9 vs 13.1 ms (256 mics, 37 888 points x 512 bins), 12.1 vs 12.4 ms
+    // (64 mics, 148 000 points x 640 bins); DLAG = 3 needs a deeper A ring than fits.
 #ifndef B2_DLAG
 #define B2_DLAG 2
 #endif
     static constexpr int TD = 2 * (MAX_MICS / KCH);
     static_assert((TD & (TD - 1)) == 0, "the tdone ring is indexed with a mask");
-    static constexpr int NG = (B2_NG <= NSA && B2_DLAG * B2_NG <= NSA) ? B2_NG : (NSA >= 4 ? 2 : 1);
+    // NB = 32 (at most 32 microphones: one or two chunks per bin): ONE group.  With more groups than chunks per bin a
+    // group has bins without any chunk of its own, has to hand over several (empty) bin sums at once, and the blocking
+    // part of that hand-off can close a wait cycle with the accumulator release (scripts/sim_protocol.py finds it).
+    static constexpr int NG = NB == 32 ? 1 : ((B2_NG <= NSA && B2_DLAG * B2_NG <= NSA) ? B2_NG : (NSA >= 4 ? 2 : 1));
     static constexpr int DLAG = B2_DLAG * NG <= NSA ? B2_DLAG : 1;
     static_assert(NG <= NSA && DLAG * NG <= NSA, "the A ring is too shallow for the chunks the groups keep in flight");
     static constexpr int NGEN = TILE_G * NG;                           // warp w owns TMEM lanes 32 (w % 4) ...
@@ -155,7 +160,7 @@ template <int NB, int PASSES> struct TcCfg {
     static constexpr int REGS_S_RAW = ((65536 - 128 * REGS_IO) / NGEN) / 8 * 8;
     static constexpr int REGS_S = REGS_S_RAW > 232 ? 232 : REGS_S_RAW;
     static constexpr int NBARS = 2 * NSA + TD + 2 * NSB + 2 + 8;     // ... + per-quadrant hand-off of the bin sums (full, free)
-    static constexpr int SMEM = NSA * A_STAGE + NSB * B_STAGE + PARTIAL_ROWS * TILE_G * 4 + PROG_MAX * 2 + NBARS * 8 + 16;
+    static constexpr int SMEM = NSA * A_STAGE + NSB * B_STAGE + PARTIAL_ROWS * TILE_G * 4 + PROG_MAX * 2 + NBARS * 8 + 16 + 16;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -166,9 +171,20 @@ template <int NB, int PASSES> struct TcCfg {
 //  synthesis group 0 / warp 0: 24 + { 0 total, 1 wait tdone, 2 TMEM load + FMAs, 3 wait emptyA, 4 synthesis + stores, 5 fence + arrive,
 //                                     6 own chunks, 7 per-unit table }
 __device__ unsigned long long g_map_prof[32];
+// B2_MAP_TRACE (with B2_MAP_PROFILE): the same probe points also log (slot, clock64) of CTA 0's two issue warps and of
+// one warp per synthesis group, events [TRACE_SKIP, TRACE_SKIP + TRACE_LEN) of each role: a steady-state timeline.
+// (The probes themselves cost a few hundred cycles per step: read the timeline for its ORDER of events.)
+#ifdef B2_MAP_TRACE
+constexpr int TRACE_SKIP = 6000, TRACE_LEN = 2048;
+__device__ long long g_map_trace[5][TRACE_LEN][2];
+#define PROF_DECL long long _pt = 0; int _tn = 0
+#define TRACE_EV(slot) do { if (_tn >= TRACE_SKIP && _tn < TRACE_SKIP + TRACE_LEN) { g_map_trace[prof_role][_tn - TRACE_SKIP][0] = (slot); g_map_trace[prof_role][_tn - TRACE_SKIP][1] = clock64(); } ++_tn; } while (0)
+#else
 #define PROF_DECL long long _pt = 0
+#define TRACE_EV(slot)
+#endif
 #define PROF_T0() _pt = clock64()
-#define PROF_ADD(slot, cond) do { if (cond) { const long long _n = clock64(); atomicAdd(&g_map_prof[slot], (unsigned long long)(_n - _pt)); _pt = _n; } } while (0)
+#define PROF_ADD(slot, cond) do { if (cond) { const long long _n = clock64(); atomicAdd(&g_map_prof[slot], (unsigned long long)(_n - _pt)); _pt = _n; TRACE_EV(slot); } } while (0)
 #define PROF_CNT(slot, cond) do { if (cond) atomicAdd(&g_map_prof[slot], 1ull); } while (0)
 #else
 #define PROF_DECL
@@ -456,7 +472,7 @@ __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__
 // The chunk positions of ONE bin -- the same for every bin -- as a small program in shared memory, so that the
 // synthesis warps do not re-derive the pair / block structure for every chunk:
 //   bits 0-5 kc | bit 6: the chunk's own columns belong to a block of this pair (reduce them here) |
-//   bits 7-9: accumulator of that block within the bin | bits 10-12: (first column of the chunk in its block) / 16 |
+//   bits 7-9: accumulator of that block within the bin (other chunks: number of accumulators of the bin completed before them) | bits 10-12: (first column of the chunk in its block) / 16 |
 //   bit 13: lowest chunk of its block (the accumulator has been read completely) | bit 14: last chunk of the bin |
 //   bit 15: one of the last NG chunks of its block (the group that owns it will not read this accumulator again)
 constexpr uint32_t PG_RED = 1u << 6, PG_LASTBLK = 1u << 13, PG_ENDBIN = 1u << 14, PG_LASTOWN = 1u << 15;
@@ -464,7 +480,7 @@ constexpr uint32_t PG_RED = 1u << 6, PG_LASTBLK = 1u << 13, PG_ENDBIN = 1u << 14
 template <int NB, int PASSES>
 __global__ void __launch_bounds__(TcCfg<NB, PASSES>::THREADS, 1)
 das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scratch,
-                  const float *__restrict__ bin_scale, int M, int nbins,
+                  const float *__restrict__ bin_scale, const float *__restrict__ bin_kf, int M, int nbins,
                   const double *__restrict__ freqs, const double *__restrict__ weights, double inv_c,
                   const double *__restrict__ mic, double cx0, double cy0, double cz0,
                   const double *__restrict__ grid, int64_t G, int steering, int clamp_negative,
@@ -477,6 +493,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
     uint16_t *prog = reinterpret_cast<uint16_t *>(partial + PARTIAL_ROWS * TILE_G);              // [PROG_MAX]
     uint64_t *bars = reinterpret_cast<uint64_t *>(prog + PROG_MAX);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + CF::NBARS);
+    uint16_t *lastpos = reinterpret_cast<uint16_t *>(tmem_slot + 4);       // [8] position in the bin of each accumulator's lowest chunk
     // shared-space addresses of the barrier arrays (8 bytes per barrier)
     const uint32_t smem_base = smem_u32(smem);
     // B barriers: ring 0 (NSB0 slots) then ring 1 (NSB1 slots)
@@ -521,8 +538,10 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 if (blk == b0 || blk == b1) {
                     const int accoff = accbase + ((blk == b1 || b1 < 0) ? 0 : 1);   // completion order: b1 (if any), then b0
                     e |= PG_RED | (uint32_t(accoff) << 7) | (uint32_t((kc * KCH - blk * NB) / KCH) << 10);
-                    if (kc == first_chunk(blk)) e |= PG_LASTBLK;
+                    if (kc == first_chunk(blk)) { e |= PG_LASTBLK; lastpos[accoff] = uint16_t(n); }
                     if (kc - first_chunk(blk) < NG) e |= PG_LASTOWN;
+                } else {
+                    e |= uint32_t(accbase) << 7;          // a chunk above both blocks: the accumulators of the earlier pairs are complete
                 }
                 prog[n] = uint16_t(e);
             }
@@ -545,9 +564,15 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         const uint32_t rx = uint32_t(r & 7);
         const float *tabr = tab + r * 4;
         uint32_t seq_base = 0;                               // ring sequence number of the unit's first chunk
-        uint32_t accs = 0;                                   // accumulators handed out before the event cursor's bin
+        uint32_t accs = 0;                                   // accumulator uses handed out before this unit
+        uint32_t arrived_acc = 0;                            // accumulator uses this group has released (tempty) so far
         PROF_DECL;
+#ifdef B2_MAP_TRACE
+        const bool prof = blockIdx.x == 0 && lane == 0 && quad == 0;     // one warp per group (the cycle sums then add up over the groups)
+        const int prof_role = 2 + grp;
+#else
         const bool prof = blockIdx.x == 0 && tid == 0;
+#endif
         (void)prof;
 #ifdef B2_MAP_PROFILE
         const long long t_role0 = clock64();
@@ -632,15 +657,15 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
             int s_cib = grp, s_fi = f_begin;
             while (s_cib >= cpb) { s_cib -= cpb; ++s_fi; }
             uint32_t s_slot = (seq_base + uint32_t(grp)) % NSA, s_ph = ((seq_base + uint32_t(grp)) / NSA) & 1;
-            // events / reduction: every chunk of the unit in order
-            int e_idx = 0, e_cib = 0, e_fi = f_begin, e_mod = 0;
-            uint32_t e_slot = seq_base % CF::TD, e_ph = (seq_base / CF::TD) & 1;          // tdone ring cursor
-            float bf = s_fi < f_end ? float(freqs[s_fi] * inv_c) : 0.0f;
+            // reduction: this group's own chunks in order, DLAG own chunks behind the synthesis cursor
+            int r_cib = s_cib, r_fi = s_fi;
+            uint32_t r_seq = seq_base + uint32_t(grp);
+            int cur_bin = f_begin;                               // bin whose sums are being accumulated
+            float bf = s_fi < f_end ? bin_kf[s_fi] : 0.0f;
             float2 hkeep[DLAG][KCH];                          // h' of the last DLAG own chunks: (Re, Im) per microphone (pairs)
             float2 pacc = make_float2(0.f, 0.f);              // sum of Re T Re h' / of (-Im T) Im h', current bin
             float2 pre = make_float2(0.f, 0.f);               // planar layout: (sum Re T Re h', sum Im T Im h')
             double acc_map = 0.0;
-            bool arrived = false;                             // tempty arrival of the current block already made
 
             // distances of the next own chunk (4 x 16 bytes), fetched one own-chunk ahead
             float4 dnext[4];
@@ -675,16 +700,57 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 pending = false;
             };
 
-            // one chunk of the event stream: reduce it if it is ours, then the per-chunk events
-            auto pass_chunk = [&](const float2 (&hk)[KCH]) {
+            // the bins [cur_bin, upto) are complete as far as this group is concerned: hand their sums over.  Groups 1..
+            // write theirs to shared memory and signal `pfull`; group 0 finishes P[g, f] in fp64 -- not on the spot, it
+            // keeps its own sum pending and completes the bin at a later chunk, when `pfull` has fired (finish_bin polls
+            // without blocking), so that no group sits out the skew between the groups.
+            auto flush_bins = [&](int upto) {
+                while (cur_bin < upto) {
+                    const float ptot = CF::PLANAR ? pre.x - pre.y : pacc.x + pacc.y;     // (zero for a bin without an own chunk)
+                    pacc = make_float2(0.f, 0.f);
+                    pre = make_float2(0.f, 0.f);
+                    if (NG > 1 && grp > 0) {
+                        mbar_wait(pfree + 8 * quad, hpar ^ 1);                  // group 0 has read the previous bin's sums
+                        partial[(grp - 1) * TILE_G + r] = ptot;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(pfull + 8 * quad);
+                    } else {
+                        if (pending) finish_bin(true);                          // (a whole bin went by without a poll succeeding)
+                        pend_p = ptot; pend_fi = cur_bin; pend_par = hpar; pending = true;
+                        finish_bin(NG == 1);
+                    }
+                    hpar ^= 1;
+                    ++cur_bin;
+                }
+            };
+
+            // Reduction of this group's next own chunk (DLAG own chunks behind the synthesis).  There is no walk over the
+            // chunks of the other groups: everything that used to be an event of the chunk stream is derived from the own
+            // chunk -- the bin it belongs to (a new bin flushes the sums of the old one), the accumulator it reads
+            // (accumulator uses this group has NO chunk in are released first, after waiting for their lowest chunk: a
+            // release must not be counted for the previous use of the TMEM buffer, scripts/sim_protocol.py), and whether
+            // it is this group's last chunk of that accumulator (released right after the read).
+            auto reduce_own = [&](const float2 (&hk)[KCH]) {
                 if (NG > 1 && pending) finish_bin(false);
-                const uint32_t e = prog[e_cib];
-                const uint32_t buf = (accs + ((e >> 7) & 7u)) & 1u;
-                if (e_mod == grp && (e & PG_RED)) {
+                const uint32_t e = prog[r_cib];
+                const uint32_t accg = accs + uint32_t(r_fi - f_begin) * uint32_t(NBLK) + ((e >> 7) & 7u);
+                const uint32_t buf = accg & 1u;
+                {
+                    while (arrived_acc < accg) {                 // accumulator uses without a chunk of this group (blocks of < NG chunks)
+                        const uint32_t u = arrived_acc - accs;
+                        const uint32_t ls = seq_base + (u / uint32_t(NBLK)) * uint32_t(cpb) + lastpos[u % uint32_t(NBLK)];
+                        mbar_wait(tdone + 8 * (ls & uint32_t(CF::TD - 1)), (ls / uint32_t(CF::TD)) & 1);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty + 8 * (arrived_acc & 1u));
+                        ++arrived_acc;
+                    }
+                }
+                if (e & PG_RED) {
                     PROF_T0();
-                    mbar_wait(tdone + 8 * e_slot, e_ph);
+                    mbar_wait(tdone + 8 * (r_seq & uint32_t(CF::TD - 1)), (r_seq / uint32_t(CF::TD)) & 1);
                     PROF_ADD(24 + 1, prof);
                     tc_fence_after();
+                    flush_bins(r_fi);
                     if (CF::PLANAR) {
                         // accumulator of a block: Re T in columns [0, NB), Im T in [NB, 2 NB); hk = (Re h' of the 8
                         // microphone pairs, Im h' of them): P = sum Re T Re h' - Im T Im h'
@@ -717,55 +783,17 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                     PROF_ADD(24 + 2, prof);
                     if (e & PG_LASTOWN) {
                         // this group's last own chunk of the block: it will not read this accumulator again and says so
-                        // NOW -- the issue warp that overwrites the buffer for the next bin then only waits for the
-                        // group that reads the block's lowest chunk, not for every group to walk its event stream up
-                        // to that chunk (they do so between two syntheses, thousands of cycles later)
+                        // now -- the issue warp that overwrites the buffer for the next bin then only waits for the group
+                        // that reads the block's lowest chunk
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty + 8 * buf);
-                        arrived = true;
+                        arrived_acc = accg + 1;
                     }
                 }
-                if (e & PG_LASTBLK) {
-                    if (!arrived) {
-                        // A group without an own chunk in this block (fewer chunks than groups) waits until the
-                        // accumulator is COMPLETE before it declares it read: otherwise its arrival for the NEXT use of
-                        // the TMEM buffer could be counted for this one (scripts/sim_protocol.py).  [An own chunk's tdone
-                        // wait gives the same guarantee: the MMAs of this use were issued after the previous phase.]
-                        mbar_wait(tdone + 8 * e_slot, e_ph);
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty + 8 * buf);
-                    }
-                    arrived = false;
-                }
-                if (e & PG_ENDBIN) {
-                    // end of the bin: the NG threads of a row combine their sums through shared memory.  Groups 1.. write
-                    // theirs and signal `pfull`; group 0 finishes P[g, f] in fp64 -- but does NOT wait for the others at
-                    // this point: it keeps its own sum pending and completes the bin at a later chunk, when `pfull` has
-                    // fired (finish_bin polls without blocking).  With the blocking named-barrier hand-off every group sat
-                    // out the skew between the groups once per bin (role profile r2: ~1800 cycles per own chunk).
-                    const float ptot = CF::PLANAR ? pre.x - pre.y : pacc.x + pacc.y;
-                    pacc = make_float2(0.f, 0.f);
-                    pre = make_float2(0.f, 0.f);
-                    if (NG > 1 && grp > 0) {
-                        mbar_wait(pfree + 8 * quad, hpar ^ 1);              // group 0 has read the previous bin's sums
-                        partial[(grp - 1) * TILE_G + r] = ptot;
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(pfull + 8 * quad);
-                    } else {
-                        if (pending) finish_bin(true);                      // (only if a whole bin went by without a poll succeeding)
-                        pend_p = ptot; pend_fi = e_fi; pend_par = hpar; pending = true;
-                        finish_bin(NG == 1);
-                    }
-                    hpar ^= 1;
-                    ++e_fi;
-                    e_cib = -1;
-                    accs += uint32_t(NBLK);
-                }
-                ++e_cib; ++e_idx;
-                if (++e_mod == NG) e_mod = 0;
-                if (++e_slot == uint32_t(CF::TD)) { e_slot = 0; e_ph ^= 1; }
+                r_cib += NG;
+                while (r_cib >= cpb) { r_cib -= cpb; ++r_fi; }
+                r_seq += uint32_t(NG);
             };
 
             // synthesis of the own chunk at (s_fi, s_cib): 16 microphones of this row -> A tile + hk
@@ -864,25 +892,36 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 s_slot += NG;
                 if (s_slot >= uint32_t(NSA)) { s_slot -= NSA; s_ph ^= 1; }
                 s_cib = n_cib;
-                if (n_fi != s_fi) { s_fi = n_fi; if (s_fi < f_end) bf = float(freqs[s_fi] * inv_c); }
+                if (n_fi != s_fi) { s_fi = n_fi; if (s_fi < f_end) bf = bin_kf[s_fi]; }
             };
 
-            // own chunk i is synthesised after the chunks up to the own chunk i - DLAG NG have been passed (the h' of
-            // that chunk sits in the register slot that chunk i then takes); the tail passes the chunks behind this
-            // group's last own chunk
+            // own chunk i is synthesised after the own chunk i - DLAG NG has been reduced (its h' sits in the register
+            // slot that chunk i then takes); the tail reduces this group's last DLAG own chunks
 #pragma unroll 1
             for (int i0 = grp; i0 < total + DLAG * NG; i0 += DLAG * NG) {
 #pragma unroll
                 for (int d = 0; d < DLAG; ++d) {
                     const int i = i0 + d * NG;
                     if (i < total + DLAG * NG) {
-                        const int upto = i - DLAG * NG < total - 1 ? i - DLAG * NG : total - 1;
-                        while (e_idx <= upto) pass_chunk(hkeep[d]);
+                        if (i - DLAG * NG >= 0) reduce_own(hkeep[d]);
                         if (i < total) synth_chunk(hkeep[d]);
                     }
                 }
             }
-            while (e_idx < total) pass_chunk(hkeep[0]);
+            // uses of the unit's last accumulators without a chunk of this group, then the last bins
+            {
+                const uint32_t acc_end = accs + uint32_t(f_end - f_begin) * uint32_t(NBLK);
+                while (arrived_acc < acc_end) {
+                    const uint32_t u = arrived_acc - accs;
+                    const uint32_t ls = seq_base + (u / uint32_t(NBLK)) * uint32_t(cpb) + lastpos[u % uint32_t(NBLK)];
+                    mbar_wait(tdone + 8 * (ls & uint32_t(CF::TD - 1)), (ls / uint32_t(CF::TD)) & 1);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty + 8 * (arrived_acc & 1u));
+                    ++arrived_acc;
+                }
+                accs = acc_end;
+            }
+            flush_bins(f_end);
             if (pending) finish_bin(true);
             seq_base += uint32_t(total);
             // the bins of a tile may be split over several work units: the map is zeroed by the
@@ -922,6 +961,9 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         PROF_DECL;
         const bool prof = blockIdx.x == 0 && lane == 0;
         (void)prof;
+#ifdef B2_MAP_TRACE
+        const int prof_role = my;
+#endif
 #ifdef B2_MAP_PROFILE
         const long long t_role0 = clock64();
 #endif
@@ -1193,13 +1235,25 @@ template <int PASSES> int64_t images_bytes(int M, int nbins) {
     const int64_t btile = (PASSES == 4 ? 1 : 2) * nb * 128;       // planar FP16x3 image: one row per column
     return int64_t(nbins) * NBLK * NKC * ((PASSES == 1 || PASSES == 4) ? 1 : 2) * btile;
 }
-// operand buffer = [images][one distance table of 128 x Mk floats per persistent CTA][per-bin scales]
+// f / c of every bin as fp32 (rounded once from the fp64 product): the synthesis warps read it when they enter a bin --
+// with the fp64 multiply in their loop (predicated, but issued with every chunk) 4 % of all warp samples of the kernel sat
+// on that one DMUL (ncu source page, r2)
+__global__ void das_binfreq_kernel(const double *__restrict__ freqs, double inv_c, int nbins, float *__restrict__ out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < nbins) out[f] = float(freqs[f] * inv_c);
+}
+
+// operand buffer = [images][one distance table of 128 x Mk floats per persistent CTA][per-bin scales][per-bin f / c]
 inline int64_t tables_bytes(int M) { return int64_t(MAX_CTAS) * TILE_G * ((M + KCH - 1) / KCH) * KCH * 4; }
 template <int PASSES> float *tables_ptr(const void *op, int M, int nbins) {
     return reinterpret_cast<float *>((unsigned char *)op + images_bytes<PASSES>(M, nbins));
 }
 template <int PASSES> float *scales_ptr(const void *op, int M, int nbins) {
     return reinterpret_cast<float *>((unsigned char *)op + images_bytes<PASSES>(M, nbins) + tables_bytes(M));
+}
+
+template <int PASSES> float *binkf_ptr(const void *op, int M, int nbins) {
+    return scales_ptr<PASSES>(op, M, nbins) + ((int64_t(nbins) * 4 + 255) & ~int64_t(255)) / 4;
 }
 
 template <int NB, int PASSES>
@@ -1267,7 +1321,10 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
     const int nblocks = int(units < cap ? units : cap);
     B2_CUDA_OK(cudaMemsetAsync(map_out, 0, size_t(G) * sizeof(double), st));
     float *scratch = tables_ptr<PASSES>(op, M, nbins);
-    kern<<<nblocks, CF::THREADS, CF::SMEM, st>>>((const unsigned char *)op, scratch, scales_ptr<PASSES>(op, M, nbins), M, nbins,
+    float *bin_kf = binkf_ptr<PASSES>(op, M, nbins);
+    das_binfreq_kernel<<<(nbins + 255) / 256, 256, 0, st>>>((const double *)freqs, 1.0 / c, nbins, bin_kf);
+    B2_LAUNCH_OK("b2_das_map(bin frequencies)");
+    kern<<<nblocks, CF::THREADS, CF::SMEM, st>>>((const unsigned char *)op, scratch, scales_ptr<PASSES>(op, M, nbins), bin_kf, M, nbins,
                                                 (const double *)freqs,
                                                 (const double *)weights, 1.0 / c, (const double *)mic, center[0],
                                                 center[1], center[2], (const double *)grid, G, steering,
@@ -1277,11 +1334,18 @@ int launch_map(const void *op, int M, int nbins, const void *freqs, const void *
 }
 
 template <int PASSES> int64_t operand_bytes(int M, int nbins) {
-    return images_bytes<PASSES>(M, nbins) + tables_bytes(M) + ((int64_t(nbins) * 4 + 255) & ~int64_t(255));
+    return images_bytes<PASSES>(M, nbins) + tables_bytes(M) + 2 * ((int64_t(nbins) * 4 + 255) & ~int64_t(255));
 }
 
 }  // namespace
 
+#ifdef B2_MAP_TRACE
+extern "C" int b2_debug_map_trace(long long *out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_map_trace, sizeof(long long) * 5 * TRACE_LEN * 2);
+    return 0;
+}
+#endif
 #ifdef B2_MAP_PROFILE
 extern "C" int b2_debug_map_profile(unsigned long long *out) {
     cudaDeviceSynchronize();

@@ -624,7 +624,7 @@ def das_map(op, M: int, freqs: np.ndarray, weights: np.ndarray, c: float, mic_xy
         N.check(lib.b2_das_map(N.ptr(op), M, nbins, N.ptr(f_dev), N.ptr(w_dev), float(c), N.ptr(mic_dev),
                                N.vec3(center_xyz), N.ptr(g_dev), G, steering, int(bool(clamp_negative)),
                                N.ptr(out), N.ptr(pb), mode, N.stream_handle()), "b2_das_map")
-    _count()
+    _count(2 if mode in (N.MAP_TC_TF32, N.MAP_TC_TF32X3, N.MAP_TC_MIXED, N.MAP_TC_F16X3) else 1)     # bin-frequency table + map kernel
     return out, pb
 
 

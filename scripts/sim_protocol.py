@@ -49,6 +49,8 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
     fullA = [Bar(1) for _ in range(NSA)]; emptyA = [Bar(2) for _ in range(NSA)]      # one arrival per owning group / both issue warps release
     fullB = [[Bar(1) for _ in range(n)] for n in NSBs]; emptyB = [[Bar(1) for _ in range(n)] for n in NSBs]   # one ring per stream
     tdone = [Bar(1) for _ in range(ND)]; tempty = [Bar(NG), Bar(NG)]      # tdone: its own ring, one barrier per chunk in flight
+    pfull = Bar(max(1, NG - 1)); pfree = Bar(1)               # hand-off of the bin sums (one quadrant's pair of barriers)
+    handoff = {'hpar': [0] * NG}
     inA = [None] * NSA; inB = [[None] * n for n in NSBs]   # what the producers last put into a stage
     issued = {}                   # accumulator sequence number -> set of chunks multiplied into it
     readers = {}                  # accumulator sequence number -> groups that have finished reading it
@@ -61,43 +63,85 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
                     yield (fi, p, kc)
 
     def group(j):
-        seq_base = 0; r_acc = 0; arrived = False
+        # no walk over the other groups' chunks: per own chunk the group waits for its tdone, first releases the
+        # accumulator uses it has no chunk in (after waiting for their lowest chunk), reads, and releases the
+        # accumulator right away if this was its last chunk of the block
+        seq_base = 0; accs = 0; arrived_acc = 0
+        accoff = {}; lastpos = {}; n = 0; accbase = 0
+        for p in range(NPAIR):
+            for kc in range(NKC - 1, fc(b0(p)) - 1, -1):
+                blk = kc * KCH // NB
+                if blk in (b0(p), b1(p)):
+                    off = accbase + (0 if (blk == b1(p) or b1(p) < 0) else 1)
+                    accoff[n] = off
+                    if kc == fc(blk): lastpos[off] = n
+                else:
+                    accoff[n] = accbase + 8      # above both blocks: the accumulators of the earlier pairs are complete (8 = not a read)
+                n += 1
+            accbase += 2 if b1(p) >= 0 else 1
+        cpb = n
+        pend = {'on': False, 'par': 0}
         for _u in range(units):
             todo = list(chunks_of_unit())
             total = len(todo)
-            e = 0
+            cur = {'bin': 0}
 
-            def pass_chunk():
-                nonlocal e, r_acc, arrived
-                fi, p, kc = todo[e]
-                seq = seq_base + e; slot = seq % ND; par = (seq // ND) & 1
-                blk = kc * KCH // NB
-                if blk in (b0(p), b1(p)):
-                    acc = r_acc + (0 if (blk == b1(p) or b1(p) < 0) else 1)
-                    if e % NG == j:
-                        while not tdone[slot].done(par): yield (f"G{j} wait tdone", slot, par, kc)
-                        assert buf_owner[acc & 1] == acc, f"G{j} reads buffer of accumulator {buf_owner[acc & 1]}, wants {acc}"
-                        need = set(range(kc, NKC))
-                        assert need <= issued.get(acc, set()), f"G{j} reads columns of chunk {kc} of accumulator {acc} before {sorted(need - issued.get(acc, set()))}"
-                        if kc - fc(blk) < NG:     # this group's last own chunk of the block: it is done with the accumulator
-                            readers.setdefault(acc, set()).add(j)
-                            tempty[acc & 1].arrive()
-                            arrived = True
-                    if kc == fc(blk):
-                        if not arrived:           # no own chunk in this block: wait until the accumulator is complete before calling it read
-                            while not tdone[slot].done(par): yield (f"G{j} wait tdone (lowest chunk)", slot, par, kc)
-                            readers.setdefault(acc, set()).add(j)
-                            tempty[acc & 1].arrive()
-                        arrived = False
-                if kc == fc(b0(p)):
-                    r_acc += 2 if b1(p) >= 0 else 1
-                e += 1
+            def finish_bin(block):
+                if NG > 1:
+                    if block:
+                        while not pfull.done(pend['par']): yield (f"G{j} wait pfull", pend['par'])
+                    elif not pfull.done(pend['par']):
+                        return
+                    pfree.arrive()
+                pend['on'] = False
+
+            def flush_bins(upto):
+                while cur['bin'] < upto:
+                    hp = handoff['hpar'][j]
+                    if NG > 1 and j > 0:
+                        while not pfree.done(hp ^ 1): yield (f"G{j} wait pfree", hp ^ 1)
+                        pfull.arrive()
+                    else:
+                        if pend['on']: yield from finish_bin(True)
+                        pend['on'] = True; pend['par'] = hp
+                        yield from finish_bin(NG == 1)
+                    handoff['hpar'][j] ^= 1
+                    cur['bin'] += 1
+
+            def release_skipped(upto):
+                nonlocal arrived_acc
+                while arrived_acc < upto:
+                    u = arrived_acc - accs
+                    ls = seq_base + (u // NBLK) * cpb + lastpos[u % NBLK]
+                    while not tdone[ls % ND].done((ls // ND) & 1): yield (f"G{j} wait tdone (lowest chunk of a skipped use)", ls)
+                    readers.setdefault(arrived_acc, set()).add(j)
+                    tempty[arrived_acc & 1].arrive()
+                    arrived_acc += 1
+
+            def reduce_own(idx):
+                nonlocal arrived_acc
+                fi, p, kc = todo[idx]
+                cib = idx % cpb
+                if NG > 1 and pend['on']: yield from finish_bin(False)
+                yield from release_skipped(accs + fi * NBLK + accoff[cib] % 8)
+                if accoff[cib] < 8:
+                    blk = kc * KCH // NB
+                    acc = accs + fi * NBLK + accoff[cib]
+                    seq = seq_base + idx
+                    while not tdone[seq % ND].done((seq // ND) & 1): yield (f"G{j} wait tdone", seq, kc)
+                    yield from flush_bins(fi)
+                    assert buf_owner[acc & 1] == acc, f"G{j} reads buffer of accumulator {buf_owner[acc & 1]}, wants {acc}"
+                    need = set(range(kc, NKC))
+                    assert need <= issued.get(acc, set()), f"G{j} reads columns of chunk {kc} of accumulator {acc} before {sorted(need - issued.get(acc, set()))}"
+                    if kc - fc(blk) < NG:         # this group's last own chunk of the block
+                        readers.setdefault(acc, set()).add(j)
+                        tempty[acc & 1].arrive()
+                        arrived_acc = acc + 1
 
             i = j
             while i < total + DLAG * NG:
-                upto = min(i - DLAG * NG, total - 1)
-                while e <= upto:
-                    yield from pass_chunk()
+                if i - DLAG * NG >= 0:
+                    yield from reduce_own(i - DLAG * NG)
                 if i < total:
                     seq = seq_base + i; slot = seq % NSA; par = (seq // NSA) & 1
                     while not emptyA[slot].done(par ^ 1): yield (f"G{j} wait emptyA", slot, par ^ 1)
@@ -105,8 +149,10 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
                     fullA[slot].arrive()
                 yield None
                 i += NG
-            while e < total:
-                yield from pass_chunk()
+            yield from release_skipped(accs + nbins * NBLK)
+            accs += nbins * NBLK
+            yield from flush_bins(nbins)
+            if pend['on']: yield from finish_bin(True)
             seq_base += total
 
     def loader(st):

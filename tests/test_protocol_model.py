@@ -22,8 +22,10 @@ SHAPES = [
     (1024, 128, 7, 4, 3, 3, 2, 2, True),     # the largest array: tdone ring of 2 NKC barriers
     (144, 128, 7, 4, 3, 3, 2, 4, True),      # second block of one chunk
     (64, 64, 10, 4, 3, 3, 2, 5, True),       # single block
-    (16, 32, 10, 4, 3, 3, 2, 9, True),       # one chunk per bin
-    (32, 32, 10, 4, 3, 3, 2, 7, True),       # two chunks per bin
+    (16, 32, 10, 4, 3, 1, 2, 9, True),       # one chunk per bin: one group (NB = 32)
+    (10, 32, 10, 4, 3, 1, 1, 9, True),
+    (32, 32, 10, 4, 3, 1, 2, 7, True),       # two chunks per bin
+    (40, 64, 10, 4, 3, 3, 1, 6, True),       # as many chunks per bin as groups
     (256, 128, 7, 4, 3, 3, 1, 3, True),      # one own chunk in flight
     (256, 128, 7, 4, 3, 2, 3, 3, True),      # two groups, three own chunks in flight
     (256, 128, 3, 2, 0, 1, 2, 3, False),     # split-TF32 / mixed: shallow rings, no sharing, one group
@@ -47,3 +49,9 @@ def test_shapes_the_kernel_configuration_must_not_produce_are_rejected_by_the_mo
         sim.main(256, 128, 3, 2, 0, 2, 2, False, 0, DLAG=2)
     with pytest.raises(AssertionError):
         sim.main(256, 128, 7, 4, 3, 3, 2, True, 0, DLAG=2, ND=16)
+
+
+def test_more_groups_than_chunks_per_bin_can_deadlock_in_the_model():
+    """Why NB = 32 runs with one group: with one chunk per bin and three groups, a group hands over the sums of bins it
+    has no chunk in while it still holds an unreleased accumulator -- the model finds the wait cycle."""
+    assert not all(sim.main(10, 32, 10, 4, 3, 3, 9, True, seed, DLAG=1) for seed in range(40))
