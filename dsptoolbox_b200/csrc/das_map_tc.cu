@@ -32,19 +32,20 @@
 //
 // Warp roles: NG groups of 4 synthesis+reduction warps (a group covers the 128 TMEM lanes; warp w owns lanes
 // 32 (w % 4) ...), 2 MMA issue warps (one per accumulator stream; the first also owns the TMEM allocation),
-// 1 operand loader warp.  The groups take the chunks ROUND-ROBIN: group j synthesises the whole tile of
-// chunks j, j + NG, ... (16 microphones per thread).  Every per-chunk hand-shake (ring slot wait, proxy
-// fence, barrier arrival, tdone wait, TMEM load) is a serial latency of the warp that executes it; with
-// every warp taking part in every chunk (the first two generations of this kernel) that latency, ~1400
-// cycles, WAS the chunk period -- whatever the number of warps or of microphones per thread.  Round-robin
-// groups give each warp NG chunk periods for it and 4x more arithmetic per hand-shake.
-// Pipelines: two shared-memory rings with full/empty mbarriers -- A (synthesis -> MMA) and B (loader -> MMA),
-// both released by tcgen05.commit --, one `tdone` mbarrier per A ring slot (MMA -> reduction of that chunk's
-// columns) and one `tempty` mbarrier per TMEM accumulator (all its columns read -> the next bin may overwrite
-// it).  The bin-independent part of the steering vector (the distance difference r0 - r_m of every (grid
-// point, microphone) pair of the tile) is computed once per work unit in fp64 and parked in an L2-resident
-// scratch table, so the per-bin work is one phase product, one sincos, one rcp and the operand split, in
-// packed fp32 arithmetic (FMUL2 / FADD2 / FFMA2) two microphones at a time.
+// 2 operand loader threads (one B ring per stream).  The groups take the chunks ROUND-ROBIN: group j synthesises the
+// whole tile of chunks j, j + NG, ... (16 microphones per thread) and reduces exactly those chunks DLAG own chunks
+// later.  Every per-chunk hand-shake (ring slot wait, proxy fence, barrier arrival, tdone wait, TMEM load) is a
+// serial latency of the warp that executes it; with every warp taking part in every chunk (the first two
+// generations of this kernel) that latency, ~1400 cycles, WAS the chunk period.
+// Pipelines: shared-memory rings with full/empty mbarriers -- A (synthesis -> MMA) and one B ring per stream
+// (loader -> MMA), released by tcgen05.commit --, a ring of `tdone` mbarriers indexed by the chunk sequence number
+// (MMA -> reduction of that chunk's columns), one `tempty` mbarrier per TMEM accumulator (all its columns read ->
+// the next bin may overwrite it: a group releases an accumulator right after its last own chunk of the block) and
+// a non-blocking hand-off of the per-bin partial sums between the groups.  setmaxnreg gives the synthesis
+// warpgroups the registers the issue / loader warpgroup does not need.  The bin-independent part of the steering
+// vector (the distance difference r0 - r_m of every (grid point, microphone) pair of the tile) is computed once per
+// work unit in fp64 and parked in an L2-resident scratch table, so the per-bin work is one phase product, one
+// sincos, one rcp and the operand split, in packed fp32 arithmetic (FMUL2 / FADD2 / FFMA2) two microphones at a time.
 // scripts/sim_protocol.py models the barrier protocol.
 //
 // Split-TF32 (PASSES = 3): every operand is split x = hi + lo (both TF32-exact) and
