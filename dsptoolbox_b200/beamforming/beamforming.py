@@ -473,8 +473,12 @@ class BeamformerCleanSC(_QuadraticFormBeamformer):
         active = torch.ones(F, dtype=torch.bool, device=dev)
         cols = torch.arange(F, device=dev)
         k = fsel * np.pi * 2 / self.c
-        gxyz = self.grid._coordinates
-        for _ in range(maximum_iterations):
+        k_dev = torch.from_numpy(np.ascontiguousarray(k, dtype=np.float64)).to(dev)
+        mic_dev = torch.from_numpy(np.ascontiguousarray(self.mics._coordinates, dtype=np.float64)).to(dev)
+        ctr_dev = torch.from_numpy(np.ascontiguousarray(self.mics.array_center_coordinates, dtype=np.float64)).to(dev)
+        g_dev = self.grid._device_coordinates(dev)
+        form = _steering_code(self.st_vec)
+        for it in range(maximum_iterations):
             peak = torch.argmax(dirty, dim=0)                                     # (F,)
             pmax = dirty[peak, cols]
             second[peak[active], cols[active]] += pmax[active] * safety_factor
@@ -482,14 +486,12 @@ class BeamformerCleanSC(_QuadraticFormBeamformer):
             n1 = D1.abs().sum(dim=1).amax(dim=1)
             n0 = D0.abs().sum(dim=1).amax(dim=1)
             active = active & ~(n1 >= n0)
-            if not bool(active.any()):
+            # the only host round trip of the loop, every 8th iteration: finished bins are masked out below, so running
+            # a few iterations past the last active bin changes nothing
+            if it % 8 == 7 and not bool(active.any()):
                 break
-            # steering vectors of every bin to its own peak point
-            pk = peak.cpu().numpy()
-            uniq, inv = np.unique(pk, return_inverse=True)
-            h_u = engine.steering_vector(k, self.mics._coordinates, self.mics.array_center_coordinates,
-                                         gxyz[uniq], _steering_code(self.st_vec))      # (F, M, U)
-            w_max = h_u[cols, :, torch.as_tensor(inv, device=dev)]                     # (F, M)
+            # steering vector of every bin to its own peak point, on the device (F x M values)
+            w_max = _steering_pairs(k_dev, g_dev[peak], mic_dev, ctr_dev, form)        # (F, M)
             w2 = (w_max.conj() * w_max)
             D_ = torch.einsum("fmn,fn->fm", D1, w_max) / pmax[:, None]
             h_ = w_max.clone()
@@ -504,6 +506,29 @@ class BeamformerCleanSC(_QuadraticFormBeamformer):
             D0 = torch.where(active[:, None, None], D1, D0)
             D1 = D1 - safety_factor * Gm
         return self._finish(second, fsel)
+
+
+def _steering_pairs(k_dev, points, mic_dev, center_dev, steering: int):
+    """Steering vectors h[f, m] of bin f towards ITS OWN point `points[f]` (reference beamforming.py:1515-1703,
+    distances by the expansion formula of helpers/other.py:131-153) as a few fp64 device operations -- what CLEAN-SC
+    needs per iteration (the dense (F, M, G) kernel would compute F times too much)."""
+    import torch
+
+    def dist(a, b):                    # (F, 3) x (M, 3) -> (F, M)
+        return torch.sqrt((a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2.0 * a @ b.T)
+
+    M = mic_dev.shape[0]
+    rti = dist(points, mic_dev)
+    rt0 = dist(points, center_dev[None, :])[:, 0]
+    phase = torch.exp(-1j * k_dev[:, None] * (rti - rt0[:, None]))
+    if steering == N.STEER_CLASSIC:
+        return phase / M
+    if steering == N.STEER_INVERSE:
+        return rti / M / rt0[:, None] * phase
+    rtj = (1.0 / rti ** 2).sum(dim=1)
+    if steering == N.STEER_TRUE_POWER:
+        return 1.0 / rt0[:, None] / rti / rtj[:, None] * phase
+    return 1.0 / rti / torch.sqrt(M * rtj[:, None]) * phase
 
 
 # =========================================================================== source simulation (next row f2)
