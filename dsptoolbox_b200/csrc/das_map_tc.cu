@@ -279,6 +279,51 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (!done) mbar_wait_slow(bar, parity);
 }
+// Several barriers at once: the try_waits are in flight together (a try_wait that succeeds at once still costs ~150
+// cycles of round trip; the issue warp paid it once per barrier, one after the other).
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+        "and.pred p, p, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b)
+        : "memory");
+    if (!done) {
+        mbar_wait(bar_a, par_a);
+        mbar_wait(bar_b, par_b);
+    }
+}
+__device__ __forceinline__ void mbar_wait4(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b, uint32_t bar_c,
+                                           uint32_t par_c, uint32_t bar_d, uint32_t par_d) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q, r, t;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 r, [%5], %6;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 t, [%7], %8;\n\t"
+        "and.pred p, p, q;\n\t"
+        "and.pred r, r, t;\n\t"
+        "and.pred p, p, r;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b), "r"(bar_c), "r"(par_c), "r"(bar_d), "r"(par_d)
+        : "memory");
+    if (!done) {
+        mbar_wait(bar_a, par_a);
+        mbar_wait(bar_b, par_b);
+        mbar_wait(bar_c, par_c);
+        mbar_wait(bar_d, par_d);
+    }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -503,7 +548,9 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
     const uint32_t pfull = tempty + 16, pfree = pfull + 32;              // one pair per quadrant of TMEM lanes
     const uint32_t b_ring = smem_base + NSA * CF::A_STAGE;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the warp index through a shuffle: the compiler then KNOWS it is warp-uniform and keeps the role loops' state in
+    // uniform registers
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int NKC = (M + KCH - 1) / KCH;          // K chunks
     const int Mk = NKC * KCH;
     const int NBLK = (M + NB - 1) / NB;           // column blocks
@@ -982,8 +1029,74 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                     const uint32_t d_tmem = tmem_base + buf * UMMA_N;
                     const int kbase = my ? kcB : kcA;
                     const int myblk = my ? blk1 : blk0;
+                    // the tcgen05 instructions and commits of ONE chunk (elected lane only)
+                    auto issue_chunk = [&](int kc, uint32_t seq, uint32_t sa, uint32_t sbk) {
+                        // columns of this block that chunk kc can reach (lower triangle): w
+                        const int w = min(NB, KCH * (kc - kbase + 1));
+                        // Every chunk signals tdone exactly once per use of its ring slot: on the step that makes its
+                        // own columns final (the block that contains it), or -- for a chunk above both blocks of the
+                        // pair, whose columns belong to another pair -- on the step of stream 0.
+                        const int cblk = (kc * KCH) / NB;
+                        const bool signal_done = cblk == myblk || (my == 0 && cblk != blk0 && cblk != blk1);
+                        // low words of the operand descriptors: first image, second (correction) image
+                        const uint32_t a1 = a0 + sa * (CF::A_STAGE >> 4), b1 = b0d + sbk * (CF::B_STAGE >> 4);
+                        const uint32_t a2 = a1 + (CF::NSPLIT - 1) * (A_TILE >> 4), b2 = b1 + (CF::NSPLIT - 1) * (CF::B_TILE >> 4);
+                        const uint32_t first = kc != NKC - 1 ? 1u : 0u;    // 0: the first MMA overwrites the accumulator
+#ifdef B2_ABL_NOMMA
+                        if (false) {
+#else
+                        if (PASSES == 4) {
+#endif
+                            // rows = [x1 Re | x1 Im | x2 Re | x2 Im] of the chunk's 16 microphones, 32 B (K = 16 halfs)
+                            // each; x = f (A: steering) resp. g (B: matrix); three products f1 g1 + f1 g2 + f2 g1:
+                            //   Re T += fr gr^T + fi gi^T,   Im T += fr gi^T + (-fi) gr^T
+                            // The A slice of a pair of MMAs is read from shared memory once (collector).
+                            const uint32_t idp = idesc_f16(TILE_G, w), idn = idp | IDESC_NEGATE_A;
+                            const uint32_t d_re = d_tmem, d_im = d_tmem + NB;
+                            const uint64_t f1r = desc64(a1), f1i = desc64(a1 + 2), f2r = desc64(a1 + 4), f2i = desc64(a1 + 6);
+                            const uint64_t g1r = desc64(b1), g1i = desc64(b1 + 2), g2r = desc64(b1 + 4), g2i = desc64(b1 + 6);
+                            umma_f16_afill(d_re, f1r, g1r, idp, first);
+                            umma_f16_alastuse(d_re, f1r, g2r, idp, 1u);
+                            umma_f16_afill(d_im, f1r, g1i, idp, first);
+                            umma_f16_alastuse(d_im, f1r, g2i, idp, 1u);
+                            umma_f16_afill(d_re, f1i, g1i, idp, 1u);
+                            umma_f16_alastuse(d_re, f1i, g2i, idp, 1u);
+                            umma_f16_afill(d_im, f1i, g1r, idn, 1u);
+                            umma_f16_alastuse(d_im, f1i, g2r, idn, 1u);
+                            umma_f16_afill(d_re, f2r, g1r, idp, 1u);
+                            umma_f16_alastuse(d_im, f2r, g1i, idp, 1u);
+                            umma_bf16(d_re, f2i, g1i, idp, 1u);
+                            umma_bf16(d_im, f2i, g1r, idn, 1u);
+#ifdef B2_ABL_NOMMA
+                        } else if (false) {
+#else
+                        } else {
+#endif
+                            const uint32_t idesc = idesc_tf32(TILE_G, 2 * w);
+#pragma unroll
+                            for (uint32_t ks = 0; ks < 4; ++ks) {          // UMMA K = 8 tf32 = 32 bytes
+                                const uint32_t adv = ks * 2;
+                                umma_tf32(d_tmem, desc64(a1 + adv), desc64(b1 + adv), idesc, ks > 0 ? 1u : first);
+                                if (PASSES == 3) {
+                                    umma_tf32(d_tmem, desc64(a2 + adv), desc64(b1 + adv), idesc, 1u);
+                                    umma_tf32(d_tmem, desc64(a1 + adv), desc64(b2 + adv), idesc, 1u);
+                                }
+                                // mixed mode: both corrections as one BF16 product of depth 64 (4 x K=16)
+                                if (PASSES == 2)
+                                    umma_bf16(d_tmem, desc64(a2 + adv), desc64(b2 + adv), idesc_bf16(TILE_G, 2 * w), 1u);
+                            }
+                        }
+                        // tcgen05.commit: the barriers are signalled when the MMAs issued so far retire
+                        if (signal_done) umma_commit(tdone + 8 * (seq & uint32_t(CF::TD - 1)));   // columns of chunk kc are final -> reduction
+                        umma_commit(emptyA + 8 * sa);                      // this warp is done with the A tile
+                        umma_commit(emptyBm + 8 * sbk);
+                    };
+                    // Up to TWO chunks per step: every step costs its warp ~450 cycles that the tensor pipe cannot use
+                    // (two barrier round trips of ~150 cycles even when the tiles are there, fences, elect, descriptors,
+                    // commits -- role profile r2) and the tcgen05 queue is too shallow to cover them; with the barriers of
+                    // two chunks looked at in ONE round trip and 24 MMAs behind them, that cost is paid once per two chunks.
 #pragma unroll 1
-                    for (int kc = NKC - 1; kc >= kcA; --kc, ++seqA) {
+                    for (int kc = NKC - 1; kc >= kcA;) {
                         PROF_T0();
                         const uint32_t sa = seqA % NSA, pha = (seqA / NSA) & 1;
                         if (my == 1 && kc < kcB) {
@@ -993,81 +1106,49 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                             if (elect_one_sync()) mbar_arrive(emptyA + 8 * sa);
                             __syncwarp();
                             PROF_ADD(8 * my + 5, prof);
+                            --kc; ++seqA;
                             continue;
                         }
                         // first MMA of this accumulator: have the synthesis warps read its previous contents?
                         if (kc == NKC - 1) mbar_wait(tempty + 8 * buf, ((acc >> 1) & 1) ^ 1);
                         PROF_ADD(8 * my + 1, prof);
-                        // columns of this block that chunk kc can reach (lower triangle): w
-                        const int w = min(NB, KCH * (kc - kbase + 1));
-                        // Every chunk signals tdone exactly once per use of its ring slot: on the step that makes its
-                        // own columns final (the block that contains it), or -- for a chunk above both blocks of the
-                        // pair, whose columns belong to another pair -- on the step of stream 0.
-                        const int cblk = (kc * KCH) / NB;
-                        const bool signal_done = cblk == myblk || (my == 0 && cblk != blk0 && cblk != blk1);
-                        mbar_wait(fullBm + 8 * sb, phb);
-                        PROF_ADD(8 * my + 2, prof);
-                        mbar_wait(fullA + 8 * sa, pha);
+#ifndef B2_CHUNKS_PER_STEP
+#define B2_CHUNKS_PER_STEP 2
+#endif
+                        // chunks of this step: the next ones are this warp's next multiply steps too, and the B ring keeps
+                        // at least one stage for the loader to prefetch into
+                        // (measured: 256 mics 12.95 / 12.3 / 12.6 ms for 1 / 2 / 3 chunks per step; 64 mics -- 4 chunks
+                        // per bin -- 12.6 / 12.9 / 14.1 ms: short bins keep one chunk per step)
+                        int adv = kc - kbase + 1;
+                        constexpr int MAXADV = NB >= 128 ? B2_CHUNKS_PER_STEP : 1;     // (compile-time for the small-array kernels)
+                        if (adv > MAXADV) adv = MAXADV;
+                        if (NKC < 8) adv = 1;
+                        if (adv > nsb_my - 1) adv = nsb_my - 1 > 0 ? nsb_my - 1 : 1;
+                        const uint32_t sa2 = (seqA + 1) % NSA, pha2 = ((seqA + 1) / NSA) & 1;
+                        const uint32_t sa3 = (seqA + 2) % NSA, pha3 = ((seqA + 2) / NSA) & 1;
+                        const uint32_t sb2 = sb + 1 == uint32_t(nsb_my) ? 0u : sb + 1, phb2 = sb2 ? phb : phb ^ 1u;
+                        const uint32_t sb3 = sb2 + 1 == uint32_t(nsb_my) ? 0u : sb2 + 1, phb3 = sb3 ? phb2 : phb2 ^ 1u;
+                        if (adv >= 3) {
+                            mbar_wait4(fullBm + 8 * sb, phb, fullA + 8 * sa, pha, fullBm + 8 * sb2, phb2, fullA + 8 * sa2, pha2);
+                            mbar_wait2(fullBm + 8 * sb3, phb3, fullA + 8 * sa3, pha3);
+                        } else if (adv == 2) {
+                            mbar_wait4(fullBm + 8 * sb, phb, fullA + 8 * sa, pha, fullBm + 8 * sb2, phb2, fullA + 8 * sa2, pha2);
+                        } else {
+                            mbar_wait2(fullBm + 8 * sb, phb, fullA + 8 * sa, pha);
+                        }
                         PROF_ADD(8 * my + 3, prof);
                         tc_fence_after();
-                        // low words of the operand descriptors: first image, second (correction) image
-                        const uint32_t a1 = a0 + sa * (CF::A_STAGE >> 4), b1 = b0d + sb * (CF::B_STAGE >> 4);
-                        const uint32_t a2 = a1 + (CF::NSPLIT - 1) * (A_TILE >> 4), b2 = b1 + (CF::NSPLIT - 1) * (CF::B_TILE >> 4);
-                        const uint32_t first = kc != NKC - 1 ? 1u : 0u;    // 0: the first MMA overwrites the accumulator
                         if (elect_one_sync()) {
-#ifdef B2_ABL_NOMMA
-                            if (false) {
-#else
-                            if (PASSES == 4) {
-#endif
-                                // rows = [x1 Re | x1 Im | x2 Re | x2 Im] of the chunk's 16 microphones, 32 B (K = 16 halfs)
-                                // each; x = f (A: steering) resp. g (B: matrix); three products f1 g1 + f1 g2 + f2 g1:
-                                //   Re T += fr gr^T + fi gi^T,   Im T += fr gi^T + (-fi) gr^T
-                                // The A slice of a pair of MMAs is read from shared memory once (collector).
-                                const uint32_t idp = idesc_f16(TILE_G, w), idn = idp | IDESC_NEGATE_A;
-                                const uint32_t d_re = d_tmem, d_im = d_tmem + NB;
-                                const uint64_t f1r = desc64(a1), f1i = desc64(a1 + 2), f2r = desc64(a1 + 4), f2i = desc64(a1 + 6);
-                                const uint64_t g1r = desc64(b1), g1i = desc64(b1 + 2), g2r = desc64(b1 + 4), g2i = desc64(b1 + 6);
-                                umma_f16_afill(d_re, f1r, g1r, idp, first);
-                                umma_f16_alastuse(d_re, f1r, g2r, idp, 1u);
-                                umma_f16_afill(d_im, f1r, g1i, idp, first);
-                                umma_f16_alastuse(d_im, f1r, g2i, idp, 1u);
-                                umma_f16_afill(d_re, f1i, g1i, idp, 1u);
-                                umma_f16_alastuse(d_re, f1i, g2i, idp, 1u);
-                                umma_f16_afill(d_im, f1i, g1r, idn, 1u);
-                                umma_f16_alastuse(d_im, f1i, g2r, idn, 1u);
-                                umma_f16_afill(d_re, f2r, g1r, idp, 1u);
-                                umma_f16_alastuse(d_im, f2r, g1i, idp, 1u);
-                                umma_bf16(d_re, f2i, g1i, idp, 1u);
-                                umma_bf16(d_im, f2i, g1r, idn, 1u);
-#ifdef B2_ABL_NOMMA
-                            } else if (false) {
-#else
-                            } else {
-#endif
-                                const uint32_t idesc = idesc_tf32(TILE_G, 2 * w);
-#pragma unroll
-                                for (uint32_t ks = 0; ks < 4; ++ks) {          // UMMA K = 8 tf32 = 32 bytes
-                                    const uint32_t adv = ks * 2;
-                                    umma_tf32(d_tmem, desc64(a1 + adv), desc64(b1 + adv), idesc, ks > 0 ? 1u : first);
-                                    if (PASSES == 3) {
-                                        umma_tf32(d_tmem, desc64(a2 + adv), desc64(b1 + adv), idesc, 1u);
-                                        umma_tf32(d_tmem, desc64(a1 + adv), desc64(b2 + adv), idesc, 1u);
-                                    }
-                                    // mixed mode: both corrections as one BF16 product of depth 64 (4 x K=16)
-                                    if (PASSES == 2)
-                                        umma_bf16(d_tmem, desc64(a2 + adv), desc64(b2 + adv), idesc_bf16(TILE_G, 2 * w), 1u);
-                                }
-                            }
-                            // tcgen05.commit: the barriers are signalled when the MMAs issued so far retire
-                            if (signal_done) umma_commit(tdone + 8 * (seqA & uint32_t(CF::TD - 1)));   // columns of chunk kc are final -> reduction
-                            umma_commit(emptyA + 8 * sa);                      // this warp is done with the A tile
-                            umma_commit(emptyBm + 8 * sb);
+                            issue_chunk(kc, seqA, sa, sb);
+                            if (adv >= 2) issue_chunk(kc - 1, seqA + 1, sa2, sb2);
+                            if (adv >= 3) issue_chunk(kc - 2, seqA + 2, sa3, sb3);
                         }
                         __syncwarp();
                         PROF_ADD(8 * my + 4, prof);
                         PROF_CNT(8 * my + 6, prof);
-                        if (++sb == uint32_t(nsb_my)) { sb = 0; phb ^= 1; }
+                        kc -= adv; seqA += uint32_t(adv);
+                        for (int q = 0; q < adv; ++q)
+                            if (++sb == uint32_t(nsb_my)) { sb = 0; phb ^= 1; }
                     }
                 }
             }

@@ -171,7 +171,9 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
                         yield None
 
     def issuer(my):
+        # up to TWO chunks per step: the warp waits for the B and A tiles of both before it issues either
         sb = phb = 0; seqA = 0; acc_it = 0; q = 0
+        nsb_my = NSBs[my]
         for _u in range(units):
             for fi in range(nbins):
                 for p in range(NPAIR):
@@ -181,30 +183,43 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
                     acc_it += 2 if blk1 >= 0 else 1
                     buf = acc & 1; use_par = (acc >> 1) & 1
                     myblk = blk1 if my else blk0
-                    for kc in range(NKC - 1, kcA - 1, -1):
+                    kbase = kcB if my else kcA
+                    kc = NKC - 1
+                    while kc >= kcA:
                         sa = seqA % NSA; pha = (seqA // NSA) & 1
                         if my == 1 and kc < kcB:                            # release of a tile only b0 uses
                             while not fullA[sa].done(pha): yield (f"W{my} wait fullA (release)", sa, pha, kc)
                             assert inA[sa] == seqA, f"W{my} releases A tile {inA[sa]} instead of {seqA}"
                             emptyA[sa].arrive()
-                        else:
-                            if kc == NKC - 1:                               # previous contents read by everybody?
-                                while not tempty[buf].done(use_par ^ 1): yield (f"W{my} wait tempty", buf)
-                                prev = buf_owner[buf]
-                                assert prev is None or len(readers.get(prev, ())) == NG, f"accumulator {prev} overwritten before it was read"
-                                buf_owner[buf] = acc
-                            while not fullB[my][sb].done(phb): yield (f"W{my} wait fullB", sb, phb, kc)
-                            assert inB[my][sb] == q, f"W{my} sees B tile {inB[my][sb]} instead of {q}"
-                            while not fullA[sa].done(pha): yield (f"W{my} wait fullA", sa, pha, kc)
-                            assert inA[sa] == seqA, f"W{my} sees A tile {inA[sa]} instead of {seqA}"
-                            issued.setdefault(acc, set()).add(kc)
-                            cblk = kc * KCH // NB
+                            kc -= 1; seqA += 1
+                            yield None
+                            continue
+                        if kc == NKC - 1:                                   # previous contents read by everybody?
+                            while not tempty[buf].done(use_par ^ 1): yield (f"W{my} wait tempty", buf)
+                            prev = buf_owner[buf]
+                            assert prev is None or len(readers.get(prev, ())) == NG, f"accumulator {prev} overwritten before it was read"
+                            buf_owner[buf] = acc
+                        two = kc - 1 >= kbase and nsb_my >= 3
+                        steps = []
+                        s_b, p_b = sb, phb
+                        for d in range(2 if two else 1):
+                            sq = seqA + d
+                            steps.append((kc - d, sq, sq % NSA, (sq // NSA) & 1, s_b, p_b, q + d))
+                            s_b += 1
+                            if s_b == nsb_my: s_b = 0; p_b ^= 1
+                        for (k_, sq, sa_, pha_, sb_, phb_, q_) in steps:   # all waits first
+                            while not fullB[my][sb_].done(phb_): yield (f"W{my} wait fullB", sb_, phb_, k_)
+                            assert inB[my][sb_] == q_, f"W{my} sees B tile {inB[my][sb_]} instead of {q_}"
+                            while not fullA[sa_].done(pha_): yield (f"W{my} wait fullA", sa_, pha_, k_)
+                            assert inA[sa_] == sq, f"W{my} sees A tile {inA[sa_]} instead of {sq}"
+                        for (k_, sq, sa_, pha_, sb_, phb_, q_) in steps:   # then issue + commits, chunk by chunk
+                            issued.setdefault(acc, set()).add(k_)
+                            cblk = k_ * KCH // NB
                             if cblk == myblk or (my == 0 and cblk != blk0 and cblk != blk1):
-                                tdone[seqA % ND].arrive()
-                            emptyA[sa].arrive(); emptyB[my][sb].arrive()
-                            q += 1; sb += 1
-                            if sb == NSBs[my]: sb = 0; phb ^= 1
-                        seqA += 1
+                                tdone[sq % ND].arrive()
+                            emptyA[sa_].arrive(); emptyB[my][sb_].arrive()
+                        n = len(steps)
+                        kc -= n; seqA += n; q += n; sb, phb = s_b, p_b
                         yield None
 
     roles = {"loader0": loader(0), "W0": issuer(0), "W1": issuer(1)}
