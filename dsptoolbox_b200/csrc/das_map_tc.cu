@@ -436,6 +436,16 @@ __device__ __forceinline__ void umma_f16_alastuse(uint32_t d_tmem, uint64_t ades
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16_ause(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {   // lo_elem first in memory
     __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);
     return *reinterpret_cast<uint32_t *>(&v);
@@ -1055,10 +1065,17 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                             const uint32_t d_re = d_tmem, d_im = d_tmem + NB;
                             const uint64_t f1r = desc64(a1), f1i = desc64(a1 + 2), f2r = desc64(a1 + 4), f2i = desc64(a1 + 6);
                             const uint64_t g1r = desc64(b1), g1i = desc64(b1 + 2), g2r = desc64(b1 + 4), g2i = desc64(b1 + 6);
+#ifdef B2_CHAIN4
+                            umma_f16_afill(d_re, f1r, g1r, idp, first);
+                            umma_f16_ause(d_re, f1r, g2r, idp, 1u);
+                            umma_f16_ause(d_im, f1r, g1i, idp, first);
+                            umma_f16_alastuse(d_im, f1r, g2i, idp, 1u);
+#else
                             umma_f16_afill(d_re, f1r, g1r, idp, first);
                             umma_f16_alastuse(d_re, f1r, g2r, idp, 1u);
                             umma_f16_afill(d_im, f1r, g1i, idp, first);
                             umma_f16_alastuse(d_im, f1r, g2i, idp, 1u);
+#endif
                             umma_f16_afill(d_re, f1i, g1i, idp, 1u);
                             umma_f16_alastuse(d_re, f1i, g2i, idp, 1u);
                             umma_f16_afill(d_im, f1i, g1r, idn, 1u);
