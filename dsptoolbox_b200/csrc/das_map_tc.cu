@@ -144,7 +144,8 @@ template <int NB, int PASSES> struct TcCfg {
     static_assert((TD & (TD - 1)) == 0, "the tdone ring is indexed with a mask");
     // NB = 32 (at most 32 microphones: one or two chunks per bin): ONE group.  With more groups than chunks per bin a
     // group has bins without any chunk of its own, has to hand over several (empty) bin sums at once, and the blocking
-    // part of that hand-off can close a wait cycle with the accumulator release (scripts/sim_protocol.py finds it).
+    // part of that hand-off can close a wait cycle with the accumulator release (scripts/sim_protocol.py found it with two
+    // accumulator buffers; with four it has not shown up, but three groups have nothing to gain on one or two chunks).
     static constexpr int NG = NB == 32 ? 1 : ((B2_NG <= NSA && B2_DLAG * B2_NG <= NSA) ? B2_NG : (NSA >= 4 ? 2 : 1));
     static constexpr int DLAG = B2_DLAG * NG <= NSA ? B2_DLAG : 1;
     static_assert(NG <= NSA && DLAG * NG <= NSA, "the A ring is too shallow for the chunks the groups keep in flight");
@@ -153,14 +154,18 @@ template <int NB, int PASSES> struct TcCfg {
     static constexpr int W_MMA = NS_WARPS;            // two MMA issue warps, then their two B loader warps
     static constexpr int THREADS = NGEN + 128;
     static constexpr int PARTIAL_ROWS = NG > 1 ? NG - 1 : 1;           // per-bin partial sums handed to the first group
-    static constexpr int TMEM_COLS = 2 * UMMA_N;                       // two accumulator buffers
+    // accumulator buffers: as many as the 512 TMEM columns hold, at most 4 (two for 128-column blocks; four for the
+    // small-array kernels, whose bins are only a few chunks long -- the issue warp then runs up to three bins ahead of
+    // the reduction instead of waiting for a buffer at the start of every other bin)
+    static constexpr int NBUF = 512 / UMMA_N >= 4 ? 4 : 2;
+    static constexpr int TMEM_COLS = NBUF * UMMA_N;
     // Register file split (setmaxnreg): the issue / loader warpgroup keeps REGS_IO registers per thread, the synthesis
     // warpgroups take the rest of the 64 K registers -- the h' of DLAG chunks (32 registers per chunk) live there.
     static constexpr bool SETMAXNREG = NG >= 3;      // 512 threads: 128 registers each at launch (fewer groups get enough without it)
     static constexpr int REGS_IO = 48;
     static constexpr int REGS_S_RAW = ((65536 - 128 * REGS_IO) / NGEN) / 8 * 8;
     static constexpr int REGS_S = REGS_S_RAW > 232 ? 232 : REGS_S_RAW;
-    static constexpr int NBARS = 2 * NSA + TD + 2 * NSB + 2 + 8;     // ... + per-quadrant hand-off of the bin sums (full, free)
+    static constexpr int NBARS = 2 * NSA + TD + 2 * NSB + NBUF + 8;     // ... + per-quadrant hand-off of the bin sums (full, free)
     static constexpr int SMEM = NSA * A_STAGE + NSB * B_STAGE + PARTIAL_ROWS * TILE_G * 4 + PROG_MAX * 2 + NBARS * 8 + 16 + 16;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
@@ -555,7 +560,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
     // B barriers: ring 0 (NSB0 slots) then ring 1 (NSB1 slots)
     const uint32_t fullA = smem_u32(bars), emptyA = fullA + 8 * NSA, fullB = emptyA + 8 * NSA, emptyB = fullB + 8 * NSB;
     const uint32_t tdone = emptyB + 8 * NSB, tempty = tdone + 8 * CF::TD;
-    const uint32_t pfull = tempty + 16, pfree = pfull + 32;              // one pair per quadrant of TMEM lanes
+    const uint32_t pfull = tempty + 8 * CF::NBUF, pfree = pfull + 32;              // one pair per quadrant of TMEM lanes
     const uint32_t b_ring = smem_base + NSA * CF::A_STAGE;
 
     // the warp index through a shuffle: the compiler then KNOWS it is warp-uniform and keeps the role loops' state in
@@ -583,7 +588,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
         }
         for (int s = 0; s < CF::TD; ++s) mbar_init(tdone + 8 * s, 1);   // committed once per chunk by the warp that issues its last relevant step
         for (int s = 0; s < NSB; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) mbar_init(tempty + 8 * b, NS_WARPS);
+        for (int b = 0; b < CF::NBUF; ++b) mbar_init(tempty + 8 * b, NS_WARPS);
         for (int q = 0; q < 4; ++q) { mbar_init(pfull + 8 * q, NG > 1 ? NG - 1 : 1); mbar_init(pfree + 8 * q, 1); }
         fence_barrier_init();
         // the per-bin chunk program
@@ -792,14 +797,14 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                 if (NG > 1 && pending) finish_bin(false);
                 const uint32_t e = prog[r_cib];
                 const uint32_t accg = accs + uint32_t(r_fi - f_begin) * uint32_t(NBLK) + ((e >> 7) & 7u);
-                const uint32_t buf = accg & 1u;
+                const uint32_t buf = accg & uint32_t(CF::NBUF - 1);
                 {
                     while (arrived_acc < accg) {                 // accumulator uses without a chunk of this group (blocks of < NG chunks)
                         const uint32_t u = arrived_acc - accs;
                         const uint32_t ls = seq_base + (u / uint32_t(NBLK)) * uint32_t(cpb) + lastpos[u % uint32_t(NBLK)];
                         mbar_wait(tdone + 8 * (ls & uint32_t(CF::TD - 1)), (ls / uint32_t(CF::TD)) & 1);
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty + 8 * (arrived_acc & 1u));
+                        if (lane == 0) mbar_arrive(tempty + 8 * (arrived_acc & uint32_t(CF::NBUF - 1)));
                         ++arrived_acc;
                     }
                 }
@@ -974,7 +979,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                     const uint32_t ls = seq_base + (u / uint32_t(NBLK)) * uint32_t(cpb) + lastpos[u % uint32_t(NBLK)];
                     mbar_wait(tdone + 8 * (ls & uint32_t(CF::TD - 1)), (ls / uint32_t(CF::TD)) & 1);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty + 8 * (arrived_acc & 1u));
+                    if (lane == 0) mbar_arrive(tempty + 8 * (arrived_acc & uint32_t(CF::NBUF - 1)));
                     ++arrived_acc;
                 }
                 accs = acc_end;
@@ -1035,7 +1040,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                     // accumulators are handed out in the order b1 (if any), then b0
                     const uint32_t acc = my ? acc_it : acc_it + (blk1 >= 0 ? 1u : 0u);
                     acc_it += blk1 >= 0 ? 2u : 1u;
-                    const uint32_t buf = acc & 1;
+                    const uint32_t buf = acc & uint32_t(CF::NBUF - 1);
                     const uint32_t d_tmem = tmem_base + buf * UMMA_N;
                     const int kbase = my ? kcB : kcA;
                     const int myblk = my ? blk1 : blk0;
@@ -1127,7 +1132,7 @@ das_map_tc_kernel(const unsigned char *__restrict__ op, float *__restrict__ scra
                             continue;
                         }
                         // first MMA of this accumulator: have the synthesis warps read its previous contents?
-                        if (kc == NKC - 1) mbar_wait(tempty + 8 * buf, ((acc >> 1) & 1) ^ 1);
+                        if (kc == NKC - 1) mbar_wait(tempty + 8 * buf, ((acc / uint32_t(CF::NBUF)) & 1) ^ 1);
                         PROF_ADD(8 * my + 1, prof);
 #ifndef B2_CHUNKS_PER_STEP
 #define B2_CHUNKS_PER_STEP 2

@@ -51,14 +51,21 @@ def compute_transfer_function(output: Signal, input: Signal, window_length_sampl
     g_xx = csm[:, xi, xi].real.cpu().numpy()          # _welch(x, None)
     g_yy = csm[:, yi, yi].real.cpu().numpy()          # _welch(y, None)
     g_xy = csm[:, yi, xi].cpu().numpy()               # _welch(x, y) = mean conj(X) Y
-    if mode == TransferFunctionType.H1:
-        tf = g_xy / g_xx
-    elif mode == TransferFunctionType.H2:
-        g_yx = csm[:, xi, yi].cpu().numpy()           # _welch(y, x)
-        tf = g_yy / g_yx
-    else:
-        tf = g_xy / np.abs(g_xy) * (g_yy / g_xx) ** 0.5
-    coherence = np.abs(g_xy) ** 2 / g_xx / g_yy
+    # With detrend the Welch kernels write the DC bin of every spectrum as an exact 0 (the DFT of a de-meaned frame;
+    # the reference carries rounding noise of ~1e-17 there and divides noise by noise).  0 / 0 is defined as 0 here:
+    # transfer function and coherence of a bin without any energy.
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if mode == TransferFunctionType.H1:
+            tf = g_xy / g_xx
+        elif mode == TransferFunctionType.H2:
+            g_yx = csm[:, xi, yi].cpu().numpy()       # _welch(y, x)
+            tf = g_yy / g_yx
+        else:
+            tf = g_xy / np.abs(g_xy) * (g_yy / g_xx) ** 0.5
+        coherence = np.abs(g_xy) ** 2 / g_xx / g_yy
+    dead = (g_xx == 0) | (g_yy == 0)
+    tf = np.where(dead, 0.0, tf)
+    coherence = np.where(dead, 0.0, coherence)
     spec = Spectrum(np.fft.rfftfreq(window_length_samples, 1 / input.sampling_rate_hz), tf.astype(np.complex128))
     spec.set_coherence(coherence)
     return spec

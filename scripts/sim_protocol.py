@@ -46,15 +46,16 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
     assert NSA >= NG and NSA >= DLAG * NG, "the A ring is too shallow for the chunks the groups keep in flight"
     assert ND >= 2 * NKC, "a tdone barrier could complete a further use while a group still waits for it"
     NSBs = (NSB0, NSB1)
+    NBUF = 4 if NB <= 64 else 2                # TMEM accumulator buffers (512 columns / 2 NB, at most 4)
     fullA = [Bar(1) for _ in range(NSA)]; emptyA = [Bar(2) for _ in range(NSA)]      # one arrival per owning group / both issue warps release
     fullB = [[Bar(1) for _ in range(n)] for n in NSBs]; emptyB = [[Bar(1) for _ in range(n)] for n in NSBs]   # one ring per stream
-    tdone = [Bar(1) for _ in range(ND)]; tempty = [Bar(NG), Bar(NG)]      # tdone: its own ring, one barrier per chunk in flight
+    tdone = [Bar(1) for _ in range(ND)]; tempty = [Bar(NG) for _ in range(NBUF)]      # tdone: its own ring, one barrier per chunk in flight
     pfull = Bar(max(1, NG - 1)); pfree = Bar(1)               # hand-off of the bin sums (one quadrant's pair of barriers)
     handoff = {'hpar': [0] * NG}
     inA = [None] * NSA; inB = [[None] * n for n in NSBs]   # what the producers last put into a stage
     issued = {}                   # accumulator sequence number -> set of chunks multiplied into it
     readers = {}                  # accumulator sequence number -> groups that have finished reading it
-    buf_owner = [None, None]      # accumulator currently held by a TMEM buffer
+    buf_owner = [None] * NBUF     # accumulator currently held by a TMEM buffer
 
     def chunks_of_unit():
         for fi in range(nbins):
@@ -115,7 +116,7 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
                     ls = seq_base + (u // NBLK) * cpb + lastpos[u % NBLK]
                     while not tdone[ls % ND].done((ls // ND) & 1): yield (f"G{j} wait tdone (lowest chunk of a skipped use)", ls)
                     readers.setdefault(arrived_acc, set()).add(j)
-                    tempty[arrived_acc & 1].arrive()
+                    tempty[arrived_acc % NBUF].arrive()
                     arrived_acc += 1
 
             def reduce_own(idx):
@@ -130,12 +131,12 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
                     seq = seq_base + idx
                     while not tdone[seq % ND].done((seq // ND) & 1): yield (f"G{j} wait tdone", seq, kc)
                     yield from flush_bins(fi)
-                    assert buf_owner[acc & 1] == acc, f"G{j} reads buffer of accumulator {buf_owner[acc & 1]}, wants {acc}"
+                    assert buf_owner[acc % NBUF] == acc, f"G{j} reads buffer of accumulator {buf_owner[acc % NBUF]}, wants {acc}"
                     need = set(range(kc, NKC))
                     assert need <= issued.get(acc, set()), f"G{j} reads columns of chunk {kc} of accumulator {acc} before {sorted(need - issued.get(acc, set()))}"
                     if kc - fc(blk) < NG:         # this group's last own chunk of the block
                         readers.setdefault(acc, set()).add(j)
-                        tempty[acc & 1].arrive()
+                        tempty[acc % NBUF].arrive()
                         arrived_acc = acc + 1
 
             i = j
@@ -181,7 +182,7 @@ def main(M, NB, NSA, NSB0, NSB1, NG, nbins, share=True, seed=0, stall=0.9, quiet
                     kcA = fc(blk0); kcB = fc(blk1) if blk1 >= 0 else NKC
                     acc = acc_it if my else acc_it + (1 if blk1 >= 0 else 0)
                     acc_it += 2 if blk1 >= 0 else 1
-                    buf = acc & 1; use_par = (acc >> 1) & 1
+                    buf = acc % NBUF; use_par = (acc // NBUF) & 1
                     myblk = blk1 if my else blk0
                     kbase = kcB if my else kcA
                     kc = NKC - 1

@@ -55,6 +55,10 @@ def test_golden_transfer_functions(golden_dir):
         _close(spec.spectral_data, g[f"tf_{i}"], bool(det))
         _close(spec.coherence, g[f"coh_{i}"], bool(det))
         assert spec.number_of_channels == 3
+        # the DC bin of de-meaned frames holds no energy: defined as 0 here (0 / 0), never NaN
+        assert np.all(np.isfinite(spec.spectral_data)) and np.all(np.isfinite(spec.coherence))
+        if det:
+            assert np.all(spec.spectral_data[0] == 0) and np.all(spec.coherence[0] == 0)
 
 
 @pytest.mark.parametrize("mode", ["H1", "H2", "H3"])

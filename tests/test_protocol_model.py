@@ -49,9 +49,3 @@ def test_shapes_the_kernel_configuration_must_not_produce_are_rejected_by_the_mo
         sim.main(256, 128, 3, 2, 0, 2, 2, False, 0, DLAG=2)
     with pytest.raises(AssertionError):
         sim.main(256, 128, 7, 4, 3, 3, 2, True, 0, DLAG=2, ND=16)
-
-
-def test_more_groups_than_chunks_per_bin_can_deadlock_in_the_model():
-    """Why NB = 32 runs with one group: with one chunk per bin and three groups, a group hands over the sums of bins it
-    has no chunk in while it still holds an unreleased accumulator -- the model finds the wait cycle."""
-    assert not all(sim.main(10, 32, 10, 4, 3, 3, 9, True, seed, DLAG=1) for seed in range(40))
