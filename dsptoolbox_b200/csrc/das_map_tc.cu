@@ -32,7 +32,8 @@
 //
 // Warp roles: NG groups of 4 synthesis+reduction warps (a group covers the 128 TMEM lanes; warp w owns lanes
 // 32 (w % 4) ...), 2 MMA issue warps (one per accumulator stream; the first also owns the TMEM allocation),
-// 2 operand loader threads (one B ring per stream).  The groups take the chunks ROUND-ROBIN: group j synthesises the
+// 2 operand loader threads (one B ring per stream).  An issue warp takes two chunks per step (all their barriers in
+// one round trip, then 24 MMAs).  The groups take the chunks ROUND-ROBIN: group j synthesises the
 // whole tile of chunks j, j + NG, ... (16 microphones per thread) and reduces exactly those chunks DLAG own chunks
 // later.  Every per-chunk hand-shake (ring slot wait, proxy fence, barrier arrival, tdone wait, TMEM load) is a
 // serial latency of the warp that executes it; with every warp taking part in every chunk (the first two
