@@ -14,12 +14,14 @@
 //     B[2n,     2m+{0,1}] = ( Re L[m,n],  Im L[m,n])                    -> D[:, 2n]     =  Re T
 //     B[2n + 1, 2m+{0,1}] = (-Im L[m,n],  Re L[m,n])                    -> D[:, 2n + 1] = -Im T
 // (operand images pre-swizzled by b2_das_prepare and streamed with cp.async.bulk), accumulated
-// in TMEM as fp32.  L is lower triangular: K chunks (16 microphones) entirely above the diagonal
+// in TMEM as fp32.  [This interleaved form is what the TF32 modes use; the default FP16x3 mode uses the PLANAR
+// form described at TcCfg: rows [Re | Im] per FP16 half, one B row per matrix column, Re T and Im T as separate
+// column ranges of the accumulator, the minus sign of (-Hi) Lr^T in the instruction descriptor.]  L is lower triangular: K chunks (16 microphones) entirely above the diagonal
 // are skipped, and a chunk that straddles it only touches its first w = 16, 32, ... columns, so
 // the MMA is issued with N = 2w and only the first 2w operand rows are fetched.  Chunks are
 // walked from the last one down, so that the first MMA of an accumulator (the one that overwrites
 // instead of accumulating) is the widest; two neighbouring column blocks share their A tiles
-// (walk_pair below).
+// (one MMA stream per block, see the issue role).
 //
 // There is NO separate epilogue role.  Columns [16 kc, 16 kc + 16) of T are final as soon as chunk kc
 // itself has been multiplied in (chunks are walked downwards, L is lower triangular), so the thread that
