@@ -27,6 +27,8 @@ PROTOTYPES = {
     "b2_last_error": (c_char_p, []),
     "b2_welch_frames": (c_int, [c_int64, c_int, c_int, POINTER(c_int64), POINTER(c_int64)]),
     "b2_welch_frame_tile": (c_int, [c_int, c_int]),
+    "b2_welch_spectra_elems": (c_int64, [c_int, c_int, c_int64]),
+    "b2_welch_bin_slot": (c_int, [c_int, c_int]),
     "b2_fft_twiddles": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "b2_prepare_channels": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p,
                                     c_int64, c_int, c_void_p]),

@@ -82,6 +82,25 @@ template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
 template <typename C> __device__ __forceinline__ C cmul_mi(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
 template <typename C> __device__ __forceinline__ C cconj(C a) { C r; r.x = a.x; r.y = -a.y; return r; }
 
+// ------------------------------------------------------------------ spectra layout (K1 writes, K2 / auto-power read)
+// [frame chunk of 16][slot group][channel][8 frame pairs][4 slots][2 frames], one complex value each.
+// A "slot" is a permuted bin index: the real-FFT untangling produces bins p and NC - p together (NC = wl / 2,
+// p = 0 .. NC/2 - 1), so bin p takes slot p and bin NC - p slot NC/2 + p (the upper half of the spectrum in
+// DESCENDING order, starting with the Nyquist bin); the self-paired bin NC/2 follows at slot NC.  Four
+// neighbouring slots x one frame pair are one 128-byte line (fp64): the four lanes that untangle four neighbouring p
+// of a frame pair fill whole lines with their 32-byte stores, for both halves of the spectrum.
+__host__ __device__ __forceinline__ int b2_bin_slot(int f, int NC) {
+    if (2 * f < NC) return f;
+    if (2 * f == NC) return NC;
+    return NC / 2 + (NC - f);
+}
+__host__ __device__ __forceinline__ int b2_slot_groups(int NC) { return (NC + 1 + 3) / 4; }
+constexpr int B2_GROUP_ELEMS = 64;                                   // 8 frame pairs x 4 slots x 2 frames
+// element offset of (slot s, frame k of the chunk) inside a (chunk, group, channel) block
+__host__ __device__ __forceinline__ int b2_slot_frame_offset(int s, int k) {
+    return (k >> 1) * 8 + (s & 3) * 2 + (k & 1);
+}
+
 static inline int ilog2_exact(int64_t v) {
     int l = 0;
     while ((int64_t(1) << l) < v) ++l;

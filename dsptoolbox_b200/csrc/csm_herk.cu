@@ -9,8 +9,10 @@
 // a 32x32 sub-block as 4x4 m8n8k4 FP64 MMA tiles with real and imaginary accumulators.
 // The complex product is mapped onto real DMMAs:
 //   Sr += Ar*Br^T + Ai*Bi^T          Si += Ai*Br^T + Ar*(-Bi)^T
-// Frames are streamed in chunks of 16 through a cp.async double buffer; the spectra layout
-// [frame chunk][bin][channel][16 frames] makes every 64-row tile one contiguous 16 KB run.
+// Frames are streamed in chunks of 16 through a cp.async double buffer.  Spectra layout (common.cuh):
+// [frame chunk][slot group][channel][8 frame pairs][4 slots][2 frames] -- a 64-row tile of one bin is 64 x 8 runs of
+// 32 bytes (fp64), one per (channel, frame pair); the CTAs of the four bins of a slot group run next to each other
+// (blockIdx.y) and use up the 128-byte lines between them in L2.
 // The sums are kept PACKED: S[f][j (j + 1) / 2 + i] for j >= i (row-major lower triangle, M (M + 1) / 2
 // complex128 values per bin) -- half the bytes of the square, and exactly the payload of the
 // multi-GPU all-reduce (dist.py), which therefore needs no pack / unpack pass.
@@ -54,8 +56,8 @@ template <> __device__ __forceinline__ double2 load_frag<float>(const unsigned c
 }
 
 // Issue the cp.async copies of one 64-row x KC-frame tile (rows >= M are left untouched: they
-// were zeroed once before the main loop).  Xc points at [chunk][bin] of the chunk-major spectra
-// layout, i.e. at an (M x 16) row-major block whose rows are 16 consecutive frames.
+// were zeroed once before the main loop).  Xc points at this bin's slot inside [chunk][slot group]: channel m
+// starts B2_GROUP_ELEMS elements further, frame pair p 8 elements further, the odd frame of a pair 1 element.
 template <typename TIN>
 __device__ __forceinline__ void load_tile(unsigned char *dst, const cx<TIN> *__restrict__ Xc, int row0,
                                           int M, int tid) {
@@ -67,8 +69,8 @@ __device__ __forceinline__ void load_tile(unsigned char *dst, const cx<TIN> *__r
         int r = s / SEG_PER_ROW, seg = s - r * SEG_PER_ROW;
         int row = row0 + r;
         if (row < M) {
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(Xc + int64_t(row) * KC) + seg * 16;
-            cp_async16(dst + r * SM::PITCH + seg * 16, src);
+            const int k = seg * (16 / SM::ELEM);               // first frame of this 16-byte segment
+            cp_async16(dst + r * SM::PITCH + seg * 16, Xc + int64_t(row) * B2_GROUP_ELEMS + b2_slot_frame_offset(0, k));
         }
     }
 }
@@ -91,8 +93,9 @@ herk_dmma_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, int b
     const bool diag = (bi == bj);
     const int f = bin0 + blockIdx.y;
     const int rowA0 = bj * BM, rowB0 = bi * BM;
-    const cx<TIN> *Xf = X + int64_t(f) * M * KC;          // chunk 0 of this bin
-    const int64_t chunk_stride = int64_t(nb) * M * KC;   // elements between frame chunks
+    const int slot = b2_bin_slot(f, nb - 1);
+    const cx<TIN> *Xf = X + int64_t(slot >> 2) * M * B2_GROUP_ELEMS + (slot & 3) * 2;      // chunk 0 of this bin
+    const int64_t chunk_stride = int64_t(b2_slot_groups(nb - 1)) * M * B2_GROUP_ELEMS;      // elements between frame chunks
 
     unsigned char *As[2] = {smem, smem + 2 * SM::TILE};
     unsigned char *Bs[2] = {diag ? As[0] : smem + SM::TILE, diag ? As[1] : smem + 3 * SM::TILE};
@@ -233,8 +236,7 @@ csm_finalize_kernel(const double2 *__restrict__ S, int M, int nb, double inv_fra
 
 // Auto-spectra only (the CSM diagonal): P[f][m] (+)= sum_k |X_f[m,k]|^2.  Replaces `_welch(x, None)`
 // (standard/_spectral_methods.py:146-152) for Signal.get_spectrum's Welch branch, where the full
-// rank-K update would be M times too much work.  One warp per pair of channels of one bin: the
-// 2 x 16 frames of a chunk are one contiguous run, read as one coalesced warp access.
+// rank-K update would be M times too much work.  One warp per pair of channels of one bin and 16 frames.
 template <typename TIN>
 __global__ void __launch_bounds__(256)
 autopower_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, double *__restrict__ P, int accumulate) {
@@ -246,8 +248,9 @@ autopower_kernel(const cx<TIN> *__restrict__ X, int M, int64_t Kp, int nb, doubl
     const int nchunks = int(Kp / KC);
     double acc = 0.0;
     if (m < M) {
-        const cx<TIN> *src = X + (int64_t(f) * M + m) * KC + (lane & 15);
-        const int64_t chunk_stride = int64_t(nb) * M * KC;
+        const int slot = b2_bin_slot(f, nb - 1);
+        const cx<TIN> *src = X + (int64_t(slot >> 2) * M + m) * B2_GROUP_ELEMS + b2_slot_frame_offset(slot, lane & 15);
+        const int64_t chunk_stride = int64_t(b2_slot_groups(nb - 1)) * M * B2_GROUP_ELEMS;
         for (int c = 0; c < nchunks; ++c) {
             const cx<TIN> v = src[int64_t(c) * chunk_stride];
             acc += double(v.x) * double(v.x) + double(v.y) * double(v.y);
@@ -327,7 +330,7 @@ int launch_herk(const void *X, int M, int64_t Kp, int nb, int bin0, int nbins, v
 extern "C" int b2_csm_herk(const void *X_dev, int M, int64_t Kp, int nb, int bin0, int nbins, void *S_dev,
                            int accumulate, int precision, void *stream) {
     B2_REQUIRE(X_dev && S_dev, B2_EINVAL, "b2_csm_herk: null pointer");
-    B2_REQUIRE(M > 0 && nb > 0, B2_EINVAL, "b2_csm_herk: bad M=%d / nb=%d", M, nb);
+    B2_REQUIRE(M > 0 && nb >= 5 && (nb - 1) % 4 == 0, B2_EINVAL, "b2_csm_herk: bad M=%d / nb=%d (nb = wl/2 + 1, wl a power of two >= 8)", M, nb);
     B2_REQUIRE(bin0 >= 0 && nbins >= 0 && bin0 + nbins <= nb && nbins <= 65535, B2_EINVAL,
                "b2_csm_herk: bin range [%d, %d) outside [0, %d) (at most 65535 bins per call)", bin0, bin0 + nbins, nb);
     B2_REQUIRE(Kp > 0 && Kp % KC == 0, B2_EINVAL, "b2_csm_herk: Kp=%lld must be a positive multiple of %d", (long long)Kp, KC);
@@ -354,7 +357,7 @@ extern "C" int b2_csm_finalize(const void *S_dev, int M, int nb, double inv_fram
 extern "C" int b2_welch_autopower(const void *X_dev, int M, int64_t Kp, int nb, void *P_dev, int accumulate,
                                   int precision, void *stream) {
     B2_REQUIRE(X_dev && P_dev, B2_EINVAL, "b2_welch_autopower: null pointer");
-    B2_REQUIRE(M > 0 && nb > 0, B2_EINVAL, "b2_welch_autopower: bad M=%d / nb=%d", M, nb);
+    B2_REQUIRE(M > 0 && nb >= 5 && (nb - 1) % 4 == 0, B2_EINVAL, "b2_welch_autopower: bad M=%d / nb=%d (nb = wl/2 + 1, wl a power of two >= 8)", M, nb);
     B2_REQUIRE(Kp > 0 && Kp % KC == 0, B2_EINVAL, "b2_welch_autopower: Kp=%lld must be a positive multiple of %d", (long long)Kp, KC);
     const int64_t items = int64_t(nb) * ((M + 1) / 2);
     const unsigned blocks = (unsigned)((items + 7) / 8);

@@ -8,9 +8,9 @@
 // read from the channel-major padded copy with vector loads, multiplied by the window on the
 // way into shared memory, packed as wl/2 complex points (z[n] = y[2n] + i*y[2n+1]), and
 // transformed by an in-place shared-memory Stockham FFT (radix 8/4/2, register-staged,
-// autosorting).  The real-FFT untangling is fused into the store, which writes, for every
-// bin, the FR frames as one contiguous run of the [frame chunk][bin][channel][16 frames] spectra
-// layout that the rank-K kernel consumes without transposition.
+// autosorting).  The real-FFT untangling is fused into the store, which writes frame pairs of four neighbouring
+// bin slots as whole 128-byte lines of the [frame chunk][slot group][channel][8 pairs][4 slots][2 frames] spectra
+// layout (common.cuh) that the rank-K kernel consumes without transposition.
 #include "common.cuh"
 #include "fft_small.cuh"
 
@@ -60,7 +60,41 @@ __device__ __forceinline__ void store_pair(float2 *p, float2 a, float2 b) {
     *reinterpret_cast<float4 *>(p) = make_float4(a.x, a.y, b.x, b.y);
 }
 
+// v[r] *= w^r, r = 1 .. R-1: one table value, the powers by products (depth <= 3 multiplications, so the error
+// stays at a few ulp)
+template <typename T, int R> __device__ __forceinline__ void twiddle_powers(cx<T> *v, const cx<T> w1) {
+    if constexpr (R == 2) {
+        v[1] = cmul(v[1], w1);
+    } else {
+        const cx<T> w2 = cmul(w1, w1), w3 = cmul(w1, w2);
+        v[1] = cmul(v[1], w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], w3);
+        if constexpr (R >= 8) {
+            const cx<T> w4 = cmul(w2, w2);
+            v[4] = cmul(v[4], w4);
+            v[5] = cmul(v[5], cmul(w4, w1));
+            v[6] = cmul(v[6], cmul(w4, w2));
+            v[7] = cmul(v[7], cmul(w4, w3));
+            if constexpr (R == 16) {
+                const cx<T> w8 = cmul(w4, w4);
+                v[8] = cmul(v[8], w8);
+                v[9] = cmul(v[9], cmul(w8, w1));
+                v[10] = cmul(v[10], cmul(w8, w2));
+                v[11] = cmul(v[11], cmul(w8, w3));
+                const cx<T> w12 = cmul(w8, w4);
+                v[12] = cmul(v[12], w12);
+                v[13] = cmul(v[13], cmul(w12, w1));
+                v[14] = cmul(v[14], cmul(w12, w2));
+                v[15] = cmul(v[15], cmul(w12, w3));
+            }
+        }
+    }
+}
+
 // One Stockham pass over all FR frames in the CTA: radix R, NS = product of earlier radices.
+// The LAST pass (NS * R == NC) leaves its trailing barrier to the caller, which issues the twiddle loads of the
+// untangling step in front of it.
 template <typename T, int LOG2NC, int R, int NS>
 __device__ __forceinline__ void stockham_pass(cx<T> *s, const cx<T> *__restrict__ tw, int tid) {
     using G = Geo<T, LOG2NC>;
@@ -81,34 +115,7 @@ __device__ __forceinline__ void stockham_pass(cx<T> *s, const cx<T> *__restrict_
                 // twiddles w^r, w = exp(-2 pi i k / (NS R)): one table read, powers by products
                 // (depth <= 3 multiplications, so the error stays at a few ulp)
                 constexpr int TSTEP = G::N / (NS * R);
-                const cx<T> w1 = __ldg(tw + k * TSTEP);
-                if constexpr (R == 2) {
-                    v[it][1] = cmul(v[it][1], w1);
-                } else {
-                    const cx<T> w2 = cmul(w1, w1), w3 = cmul(w1, w2);
-                    v[it][1] = cmul(v[it][1], w1);
-                    v[it][2] = cmul(v[it][2], w2);
-                    v[it][3] = cmul(v[it][3], w3);
-                    if constexpr (R >= 8) {
-                        const cx<T> w4 = cmul(w2, w2);
-                        v[it][4] = cmul(v[it][4], w4);
-                        v[it][5] = cmul(v[it][5], cmul(w4, w1));
-                        v[it][6] = cmul(v[it][6], cmul(w4, w2));
-                        v[it][7] = cmul(v[it][7], cmul(w4, w3));
-                        if constexpr (R == 16) {
-                            const cx<T> w8 = cmul(w4, w4);
-                            v[it][8] = cmul(v[it][8], w8);
-                            v[it][9] = cmul(v[it][9], cmul(w8, w1));
-                            v[it][10] = cmul(v[it][10], cmul(w8, w2));
-                            v[it][11] = cmul(v[it][11], cmul(w8, w3));
-                            const cx<T> w12 = cmul(w8, w4);
-                            v[it][12] = cmul(v[it][12], w12);
-                            v[it][13] = cmul(v[it][13], cmul(w12, w1));
-                            v[it][14] = cmul(v[it][14], cmul(w12, w2));
-                            v[it][15] = cmul(v[it][15], cmul(w12, w3));
-                        }
-                    }
-                }
+                twiddle_powers<T, R>(v[it], __ldg(tw + k * TSTEP));
             }
             dftR<T, R>(v[it]);
         }
@@ -126,7 +133,7 @@ __device__ __forceinline__ void stockham_pass(cx<T> *s, const cx<T> *__restrict_
             for (int r = 0; r < R; ++r) base[padidx<G::PADSH>(j0 + r * NS)] = v[it][r];
         }
     }
-    __syncthreads();
+    if constexpr (NS * R < NC) __syncthreads();
 }
 
 // First pass fused with the load: every butterfly reads its R inputs straight from global memory
@@ -180,23 +187,126 @@ __device__ __forceinline__ void first_pass_from_global(cx<T> *s, const T *__rest
     __syncthreads();
 }
 
-// Run the remaining passes: radix 16 while >= 16 points remain, then one radix 8 / 4 / 2 pass.
-template <typename T, int LOG2NC, int NS>
+// Radix of the pass that follows when NS points are already combined (0: none left).
+template <typename T, int LOG2NC> __host__ __device__ constexpr int next_radix(int ns) {
+    const int rem = (1 << LOG2NC) / ns;
+    if (rem <= 1) return 0;
+    if (rem >= 16) return Geo<T, LOG2NC>::RMAX >= 16 ? 16 : 8;
+    return rem;
+}
+// Radix of the LAST pass after a first pass of radix r1 (0: the first pass is the only one).
+template <typename T, int LOG2NC> __host__ __device__ constexpr int last_radix(int r1) {
+    int ns = r1, r = 0;
+    while (next_radix<T, LOG2NC>(ns) != 0) { r = next_radix<T, LOG2NC>(ns); ns *= r; }
+    return r;
+}
+
+// Run the remaining passes: radix 16 while >= 16 points remain, then one radix 8 / 4 / 2 pass.  With SKIP_LAST the
+// last pass is left to last_pass_untangle().
+template <typename T, int LOG2NC, int NS, bool SKIP_LAST>
 __device__ __forceinline__ void stockham_all(cx<T> *s, const cx<T> *__restrict__ tw, int tid) {
-    constexpr int NC = 1 << LOG2NC;
-    constexpr int REM = NC / NS;
-    if constexpr (REM >= 16 && Geo<T, LOG2NC>::RMAX >= 16) {
-        stockham_pass<T, LOG2NC, 16, NS>(s, tw, tid);
-        stockham_all<T, LOG2NC, NS * 16>(s, tw, tid);
-    } else if constexpr (REM >= 16) {
-        stockham_pass<T, LOG2NC, 8, NS>(s, tw, tid);
-        stockham_all<T, LOG2NC, NS * 8>(s, tw, tid);
-    } else if constexpr (REM == 8) {
-        stockham_pass<T, LOG2NC, 8, NS>(s, tw, tid);
-    } else if constexpr (REM == 4) {
-        stockham_pass<T, LOG2NC, 4, NS>(s, tw, tid);
-    } else if constexpr (REM == 2) {
-        stockham_pass<T, LOG2NC, 2, NS>(s, tw, tid);
+    constexpr int R = next_radix<T, LOG2NC>(NS);
+    if constexpr (R != 0) {
+        constexpr bool last = next_radix<T, LOG2NC>(NS * R) == 0;
+        if constexpr (!(last && SKIP_LAST)) {
+            stockham_pass<T, LOG2NC, R, NS>(s, tw, tid);
+            stockham_all<T, LOG2NC, NS * R, SKIP_LAST>(s, tw, tid);
+        }
+    }
+}
+
+// X[p] = 0.5 (a + conj b) - 0.5 i w_p (a - conj b),  a = Z[p], b = Z[NC-p], w_p = exp(-2 pi i p / wl)
+// and, because w_{NC-p} = -conj(w_p), X[NC-p] = conj(0.5 (a + conj b) + 0.5 i w_p (a - conj b)).
+// `bc` is conj(b); p = 0 gives the DC bin (lo) and the Nyquist bin (hi).
+template <typename T>
+__device__ __forceinline__ void untangle_pair(cx<T> a, cx<T> bc, cx<T> w, T half, cx<T> &lo, cx<T> &hi) {
+    const cx<T> sum = cadd(a, bc), dif = cmul(w, csub(a, bc));
+    lo = mk<T>((sum.x + dif.y) * half, (sum.y - dif.x) * half);
+    hi = mk<T>((sum.x - dif.y) * half, -(sum.y + dif.x) * half);
+}
+
+// Last Stockham pass (radix R, NS = NC / R) fused with the untangling.  After its butterfly a thread holds
+// Z[j + J r], r = 0 .. R-1 (J = NC / R), of BOTH frames of a pair; the partner of p = j + J r is
+// NC - p = (J - j) + J (R-1-r), held by thread J - j.  Every thread publishes its upper half (r >= R/2) in shared
+// memory, reads the partner values of its lower half from there and writes bins p and NC - p for r < R/2: half the
+// shared-memory traffic of a full pass plus an untangling pass, and one latency chain less.  Thread j = 0 pairs with
+// itself (r <-> R - r) and owns the DC / Nyquist pair (r = 0) and the self-paired bin NC/2 (r = R/2).
+template <typename T, int LOG2NC, int R>
+__device__ __forceinline__ void last_pass_untangle(cx<T> *s, const cx<T> *__restrict__ tw, int tid, T half, int detrend,
+                                                   cx<T> *Xc, int64_t gstride, int64_t k0) {
+    using G = Geo<T, LOG2NC>;
+    using C = cx<T>;
+    constexpr int NC = G::NC, J = NC / R, H = R / 2, NP = G::FR / 2;
+    constexpr int TOTAL = NP * J;
+    constexpr int ITEMS = (TOTAL + G::NT - 1) / G::NT;
+    C v[ITEMS][2][R];
+    C wu[ITEMS][H];
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int item = tid + it * G::NT;
+        if (item < TOTAL) {
+            const int pr = item / J, j = item - pr * J;
+            const C w1 = __ldg(tw + 2 * j);               // exp(-2 pi i j / NC)
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                const C *base = s + (2 * pr + f) * G::PITCH;
+#pragma unroll
+                for (int r = 0; r < R; ++r) v[it][f][r] = base[padidx<G::PADSH>(j + r * J)];
+                twiddle_powers<T, R>(v[it][f], w1);
+                dftR<T, R>(v[it][f]);
+            }
+#pragma unroll
+            for (int r = 0; r < H; ++r) wu[it][r] = __ldg(tw + j + r * J);
+        }
+    }
+    __syncthreads();
+    // exchange buffer E[(frame, q)][j], q = r - R/2: lanes write and read consecutive elements, no padding needed
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int item = tid + it * G::NT;
+        if (item < TOTAL) {
+            const int pr = item / J, j = item - pr * J;
+#pragma unroll
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+                for (int q = 0; q < H; ++q) s[((2 * pr + f) * H + q) * J + j] = v[it][f][H + q];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int item = tid + it * G::NT;
+        if (item < TOTAL) {
+            const int pr = item / J, j = item - pr * J;
+            const bool self = (j == 0);
+            const int jj = self ? 0 : J - j;
+            const int64_t k = k0 + 2 * pr;
+            C *dst = Xc + b2_slot_frame_offset(0, int(k & 15));
+#pragma unroll
+            for (int r = 0; r < H; ++r) {
+                const int p = j + r * J;
+                const int q = self ? H - r : H - 1 - r;                 // partner's r' - R/2 (unused for p = 0)
+                C lo[2], hi[2];
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    const C a = v[it][f][r];
+                    const C bc = (self && r == 0) ? cconj(a) : cconj(s[((2 * pr + f) * H + (q < H ? q : 0)) * J + jj]);
+                    untangle_pair<T>(a, bc, wu[it][r], half, lo[f], hi[f]);
+                }
+                // Removing the frame mean (_spectral_methods.py:136-137) changes the DC bin only: the DFT of a
+                // constant vanishes at every other bin.  The reference's own DC value is rounding noise.
+                if (detrend && p == 0) lo[0] = lo[1] = mk<T>(T(0), T(0));
+                store_pair(dst + (p >> 2) * gstride + (p & 3) * 2, lo[0], lo[1]);
+                store_pair(dst + ((NC / 2 + p) >> 2) * gstride + ((NC / 2 + p) & 3) * 2, hi[0], hi[1]);
+            }
+            if (self) {                                                  // bin NC/2: a = Z[NC/2], b = a, w = -i
+                C lo[2], hi[2];
+#pragma unroll
+                for (int f = 0; f < 2; ++f)
+                    untangle_pair<T>(v[it][f][H], cconj(v[it][f][H]), mk<T>(T(0), T(-1)), half, lo[f], hi[f]);
+                store_pair(dst + (NC >> 2) * gstride + (NC & 3) * 2, lo[0], lo[1]);
+            }
+        }
     }
 }
 
@@ -204,7 +314,7 @@ template <typename T, int LOG2NC>
 __global__ void __launch_bounds__(Geo<T, LOG2NC>::NT, Geo<T, LOG2NC>::MINB)
 welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframes,
                   const T *__restrict__ window, const cx<T> *__restrict__ tw, int detrend,
-                  T scale, cx<T> *__restrict__ X, int M, int64_t Kp, int vec_ok) {
+                  T scale, cx<T> *__restrict__ X, int M, int vec_ok) {
     using G = Geo<T, LOG2NC>;
     using C = cx<T>;
     constexpr int NC = G::NC, FR = G::FR, NT = G::NT;
@@ -221,50 +331,77 @@ welch_rfft_kernel(const T *__restrict__ xc, int64_t Lp, int step, int64_t nframe
     const int64_t rest = bid / GPC;
     const int m = int(rest % M);
     const int64_t k0 = (rest / M) * 16 + int64_t(gi) * FR;
-    const int64_t nb = NC + 1;
     const T *xrow = xc + int64_t(m) * Lp;
 
     // ---- wl/2-point complex FFT of every frame; the first pass reads global memory directly ----
     constexpr int R1 = NC >= G::RMAX ? G::RMAX : NC;
+    constexpr int RL = last_radix<T, LOG2NC>(R1);
+#ifndef B2_FFT_FUSED
+#define B2_FFT_FUSED 1
+#endif
+    constexpr bool FUSED = B2_FFT_FUSED && FR >= 2 && RL >= 2;
     first_pass_from_global<T, LOG2NC, R1>(s, xrow, step, k0, nframes, window, vec_ok, tid);
-    stockham_all<T, LOG2NC, R1>(s, tw, tid);
+    stockham_all<T, LOG2NC, R1, FUSED>(s, tw, tid);
 
-    // ---- untangle to the wl/2+1 real-FFT bins and store; bins k and wl/2-k share one pair of reads ----
-    // X[k] = 0.5 (a + conj b) - 0.5 i w_k (a - conj b),  a = Z[k], b = Z[NC-k], w_k = exp(-2 pi i k / wl)
-    // and, because w_{NC-k} = -conj(w_k), X[NC-k] = conj(0.5 (a + conj b) + 0.5 i w_k (a - conj b)).
-    // Spectra layout [frame chunk of 16][bin][channel][16 frames]: all CTAs of one frame chunk write
-    // inside one (nb * M * 16)-element window and the rank-K kernel reads whole tiles contiguously.
+    // ---- untangle to the wl/2+1 real-FFT bins and store; bins p and wl/2-p share one pair of reads ----
+    // Spectra layout (common.cuh): [frame chunk][slot group][channel][8 frame pairs][4 slots][2 frames]; the lanes
+    // of a warp take neighbouring p, so that four of them fill one 128-byte line with the frame pair of four
+    // neighbouring slots -- for the lower half of the spectrum (slot p) and for the upper half (slot NC/2 + p, bins
+    // descending) alike.  In the [bin][channel][16 frames] order of r1 every 32-byte store of a warp went to a line
+    // of its own: 55 LSU wavefronts per store instruction, 43 % of the wavefronts of the kernel, whose LSU data
+    // pipe was 87 % busy (profiles/r2_welch_rfft_ncu_full_v2.json).
     const T half = T(0.5) * scale;
-    // Removing the frame mean (_spectral_methods.py:136-137) changes the DC bin only: the DFT of a constant
-    // vanishes at every other bin.  The reference's own DC value is rounding noise.
-    auto untangle = [&](const C *base, int kp, C &lo, C &hi) {
-        const C a = base[padidx<G::PADSH>(kp)];
-        const C b = cconj(base[padidx<G::PADSH>((NC - kp) & (NC - 1))]);
-        const C w = __ldg(tw + kp);
-        const C sum = cadd(a, b), dif = cmul(w, csub(a, b));      // dif = w (a - conj b)
-        lo = mk<T>((sum.x + dif.y) * half, (sum.y - dif.x) * half);
-        hi = mk<T>((sum.x - dif.y) * half, -(sum.y + dif.x) * half);   // bin NC - kp (kp = 0: the Nyquist bin)
-        if (detrend && kp == 0) lo = mk<T>(T(0), T(0));
-    };
-    if constexpr (FR >= 2) {
-        // two neighbouring frames of one bin per thread: one 32-byte (fp64) / 16-byte (fp32) store instead of two --
-        // the scattered 16-byte stores were 40 % of the LSU wavefronts of this kernel
-        constexpr int NP = FR / 2;
-        for (int idx = tid; idx < (NC / 2 + 1) * NP; idx += NT) {
-            const int pr = idx % NP, kp = idx / NP;
-            C lo0, hi0, lo1, hi1;
-            untangle(s + (2 * pr) * G::PITCH, kp, lo0, hi0);
-            untangle(s + (2 * pr + 1) * G::PITCH, kp, lo1, hi1);
-            const int64_t k = k0 + 2 * pr;
-            store_pair(X + (((k >> 4) * nb + kp) * M + m) * 16 + (k & 15), lo0, lo1);
-            if (2 * kp != NC) store_pair(X + (((k >> 4) * nb + (NC - kp)) * M + m) * 16 + (k & 15), hi0, hi1);
-        }
+    constexpr int NG = (NC + 1 + 3) / 4;
+    C *Xc = X + ((k0 >> 4) * int64_t(NG) * M + m) * B2_GROUP_ELEMS;       // (chunk, group 0, channel m)
+    const int64_t gstride = int64_t(M) * B2_GROUP_ELEMS;
+    if constexpr (FUSED) {
+        last_pass_untangle<T, LOG2NC, RL>(s, tw, tid, half, detrend, Xc, gstride, k0);
     } else {
-        for (int kp = tid; kp < NC / 2 + 1; kp += NT) {
-            C lo, hi;
-            untangle(s, kp, lo, hi);
-            X[(((k0 >> 4) * nb + kp) * M + m) * 16 + (k0 & 15)] = lo;
-            if (2 * kp != NC) X[(((k0 >> 4) * nb + (NC - kp)) * M + m) * 16 + (k0 & 15)] = hi;
+        auto zat = [&](int fr, int p) { return s[fr * G::PITCH + padidx<G::PADSH>(p)]; };
+        auto slot_ptr = [&](int slot, int64_t k) { return Xc + (slot >> 2) * gstride + b2_slot_frame_offset(slot, int(k & 15)); };
+        constexpr int NP = FR >= 2 ? FR / 2 : 1;              // frame pairs (FR = 1: single frames)
+        constexpr int ITEMS = (NC / 2) * NP;                  // (p = 0 .. NC/2 - 1) x pairs
+        constexpr int ITER = (ITEMS + NT - 1) / NT;
+        C w[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int idx = tid + it * NT;
+            w[it] = __ldg(tw + (idx < ITEMS ? idx / NP : 0));
+        }
+        __syncthreads();                                      // the barrier the last FFT pass left out
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int idx = tid + it * NT;
+            if (idx < ITEMS) {
+                const int pr = idx % NP, p = idx / NP, pn = (NC - p) & (NC - 1);
+                if constexpr (FR >= 2) {
+                    C lo0, hi0, lo1, hi1;
+                    untangle_pair<T>(zat(2 * pr, p), cconj(zat(2 * pr, pn)), w[it], half, lo0, hi0);
+                    untangle_pair<T>(zat(2 * pr + 1, p), cconj(zat(2 * pr + 1, pn)), w[it], half, lo1, hi1);
+                    if (detrend && p == 0) lo0 = lo1 = mk<T>(T(0), T(0));
+                    const int64_t k = k0 + 2 * pr;
+                    store_pair(slot_ptr(p, k), lo0, lo1);
+                    store_pair(slot_ptr(NC / 2 + p, k), hi0, hi1);
+                } else {
+                    C lo, hi;
+                    untangle_pair<T>(zat(0, p), cconj(zat(0, pn)), w[it], half, lo, hi);
+                    if (detrend && p == 0) lo = mk<T>(T(0), T(0));
+                    *slot_ptr(p, k0) = lo;
+                    *slot_ptr(NC / 2 + p, k0) = hi;
+                }
+            }
+        }
+        if (tid < NP) {                                       // the self-paired bin NC/2: w = -i
+            const C mi = mk<T>(T(0), T(-1));
+            C lo0, hi0, lo1, hi1;
+            if constexpr (FR >= 2) {
+                untangle_pair<T>(zat(2 * tid, NC / 2), cconj(zat(2 * tid, NC / 2)), mi, half, lo0, hi0);
+                untangle_pair<T>(zat(2 * tid + 1, NC / 2), cconj(zat(2 * tid + 1, NC / 2)), mi, half, lo1, hi1);
+                store_pair(slot_ptr(NC, k0 + 2 * tid), lo0, lo1);
+            } else {
+                untangle_pair<T>(zat(0, NC / 2), cconj(zat(0, NC / 2)), mi, half, lo0, hi0);
+                *slot_ptr(NC, k0) = lo0;
+            }
         }
     }
 }
@@ -347,7 +484,7 @@ int launch_rfft(const void *xc, int64_t Lp, int M, int step, int64_t nframes, co
     B2_REQUIRE(Kp % 16 == 0 && nblk <= 0x7fffffff, B2_EINVAL, "b2_welch_rfft: Kp=%lld must be a multiple of 16 (grid too large otherwise)", (long long)Kp);
     dim3 grid((unsigned)nblk);
     kern<<<grid, G::NT, G::SMEM, st>>>((const T *)xc, Lp, step, nframes, (const T *)window,
-                                      (const cx<T> *)tw, detrend, T(scale), (cx<T> *)X, M, Kp, vec_ok);
+                                      (const cx<T> *)tw, detrend, T(scale), (cx<T> *)X, M, vec_ok);
     B2_LAUNCH_OK("b2_welch_rfft");
     return B2_OK;
 }
@@ -390,6 +527,22 @@ extern "C" int b2_welch_frame_tile(int wl, int precision) {
     int l2 = ilog2_exact(wl);
     if (l2 < 3 || l2 > 14) { b2_set_error("b2_welch_frame_tile: unsupported window length %d", wl); return B2_EUNSUPPORTED; }
     return precision == B2_F64 ? frame_tile<double>(l2 - 1) : frame_tile<float>(l2 - 1);
+}
+
+extern "C" int64_t b2_welch_spectra_elems(int wl, int M, int64_t Kp) {
+    if (ilog2_exact(wl) < 3 || M <= 0 || Kp <= 0 || Kp % 16 != 0) {
+        b2_set_error("b2_welch_spectra_elems: wl=%d must be a power of two >= 8, M=%d positive, Kp=%lld a positive multiple of 16", wl, M, (long long)Kp);
+        return -1;
+    }
+    return (Kp / 16) * int64_t(b2_slot_groups(wl / 2)) * M * B2_GROUP_ELEMS;
+}
+
+extern "C" int b2_welch_bin_slot(int wl, int bin) {
+    if (ilog2_exact(wl) < 3 || bin < 0 || bin > wl / 2) {
+        b2_set_error("b2_welch_bin_slot: bin %d outside [0, %d] or wl not a power of two >= 8", bin, wl / 2);
+        return -1;
+    }
+    return b2_bin_slot(bin, wl / 2);
 }
 
 extern "C" int b2_fft_twiddles(int wl, int precision, void *twiddle_dev, void *stream) {

@@ -261,7 +261,7 @@ def _csm_partial_sums(torch, lib, prec, device, x, length, wl, step, window, det
 
     tile = N.check(lib.b2_welch_frame_tile(wl, prec), "b2_welch_frame_tile")
     tile = max(16, tile)
-    bytes_per_frame = nb * M * (16 if prec == N.F64 else 8)
+    bytes_per_frame = (nb + 3) * M * (16 if prec == N.F64 else 8)      # bins + 3 unused slots (spectra layout)
     max_frames = max(tile, (config.spectra_budget_bytes // bytes_per_frame) // tile * tile)
     on_host = not (isinstance(x, torch.Tensor) and x.device.type == "cuda")
     itemsize = x.element_size() if isinstance(x, torch.Tensor) else int(getattr(getattr(x, "dtype", None), "itemsize", 8))
@@ -314,7 +314,7 @@ def _csm_partial_sums(torch, lib, prec, device, x, length, wl, step, window, det
                 "b2_prepare_channels")
         _count()
         timer.mark("k0_prepare")
-        X = _workspace_tensor("spectra", (nb, M, Kp), cdt, device)
+        X = _workspace_tensor("spectra", (_spectra_elems(lib, wl, M, Kp),), cdt, device)
         N.check(lib.b2_welch_rfft(N.ptr(xc), Lp, M, wl, step, nfr, N.ptr(win), N.ptr(tw), int(bool(detrend)),
                                   float(fft_scale), N.ptr(X), Kp, prec, st), "b2_welch_rfft")
         _count()
@@ -348,13 +348,20 @@ def _csm_partial_sums(torch, lib, prec, device, x, length, wl, step, window, det
     return S, K_total
 
 
+def _spectra_elems(lib, wl: int, M: int, Kp: int) -> int:
+    n = int(lib.b2_welch_spectra_elems(wl, M, Kp))
+    if n < 0:
+        raise N.NativeError(lib.b2_last_error().decode())
+    return n
+
+
 def frame_spectra(x, length: int, wl: int, step: int, window: np.ndarray, detrend: bool, fft_scale: float,
                   precision: str | None = None, device=None):
     """Spectra of ALL frames, complex128 CUDA tensor (bins, frames, channels): the framing / window /
     mean-removal / rFFT kernels of the Welch stage (K0, K1) without the averaging -- what the STFT
     (reference `_stft`, _spectral_methods.py:176-282) keeps.  Frames follow helpers/other.py:181-213
     (ceil(L/step) frames, zero-padded tail).  torch is only used to re-order the kernel's chunk-major
-    spectra [frames/16][bins][channels][16] into the reference's (bins, frames, channels).
+    spectra layout (include/b2dsp.h, b2_welch_rfft) into the reference's (bins, frames, channels).
     """
     torch = _torch()
     lib = N.lib()
@@ -367,8 +374,9 @@ def frame_spectra(x, length: int, wl: int, step: int, window: np.ndarray, detren
     cdt = torch.complex128 if prec == N.F64 else torch.complex64
     st = N.stream_handle()
     tile = max(16, N.check(lib.b2_welch_frame_tile(wl, prec), "b2_welch_frame_tile"))
-    bytes_per_frame = nb * M * (16 if prec == N.F64 else 8)
+    bytes_per_frame = (nb + 3) * M * (16 if prec == N.F64 else 8)
     max_frames = max(tile, (config.spectra_budget_bytes // bytes_per_frame) // tile * tile)
+    slots = _device_const(np.array([lib.b2_welch_bin_slot(wl, f) for f in range(nb)], dtype=np.float64), device).long()
     win = _device_const(window, device).to(rdt)          # cached: a pageable upload would stall the host behind the stream
     tw = _twiddles(wl, prec, device)
     out = torch.empty((nb, K_total, M), dtype=torch.complex128, device=device)
@@ -386,11 +394,13 @@ def frame_spectra(x, length: int, wl: int, step: int, window: np.ndarray, detren
         N.check(lib.b2_prepare_channels(N.ptr(xs), code, s_t, s_m, 0, t1 - t0, M, N.ptr(xc), Lp, prec, st),
                 "b2_prepare_channels")
         _count()
-        X = torch.empty((Kp // 16, nb, M, 16), dtype=cdt, device=device)
+        X = torch.empty((Kp // 16, _spectra_elems(lib, wl, M, Kp) // (Kp // 16 * M * 64), M, 8, 4, 2), dtype=cdt, device=device)
         N.check(lib.b2_welch_rfft(N.ptr(xc), Lp, M, wl, step, nfr, N.ptr(win), N.ptr(tw), int(bool(detrend)),
                                   float(fft_scale), N.ptr(X), Kp, prec, st), "b2_welch_rfft")
         _count()
-        out[:, kc:kn, :] = X.permute(1, 0, 3, 2).reshape(nb, Kp, M)[:, :nfr, :]
+        # [chunk][group][channel][pair][slot][frame] -> (slots, frames, channels), then the bins' slots
+        by_slot = X.permute(1, 4, 0, 3, 5, 2).reshape(-1, Kp, M)
+        out[:, kc:kn, :] = by_slot.index_select(0, slots)[:, :nfr, :]
         kc = kn
         del xs, xc, X
     return out

@@ -85,19 +85,26 @@ int b2_prepare_channels(const void *x_dev, int in_dtype, int64_t stride_t, int64
  *   xc_dev      (M, Lp) channel-major samples from b2_prepare_channels, Lp >= (Kp-1)*step+wl
  *   window_dev  wl window values in the precision's real type
  *   fft_scale   1, 1/wl or 1/sqrt(wl): the rfft norm of enums.py:53-75
- *   X_out_dev   spectra, Kp * (wl/2+1) * M complex values laid out
- *               [Kp/16 frame chunks][wl/2+1 bins][M channels][16 frames]; frames >= nframes
- *               are written as zeros so the rank-K update may run over whole chunks. */
+ *   X_out_dev   spectra, b2_welch_spectra_elems(wl, M, Kp) complex values laid out
+ *               [Kp/16 frame chunks][G slot groups][M channels][8 frame pairs][4 slots][2 frames],
+ *               G = wl/8 + 1; bin f lives in slot b2_welch_bin_slot(wl, f) (bins 0..wl/4-1 ascending, then
+ *               bins wl/2..wl/4+1 descending, then bin wl/4: the order in which the real-FFT untangling
+ *               produces them, so that every 32-byte store of the kernel is a quarter of a fully written 128-byte
+ *               line); frames >= nframes are written as zeros so the rank-K update may run over whole chunks. */
 int b2_welch_rfft(const void *xc_dev, int64_t Lp, int M, int wl, int step, int64_t nframes,
                   const void *window_dev, const void *twiddle_dev, int detrend,
                   double fft_scale, void *X_out_dev, int64_t Kp, int precision, void *stream);
+
+/* Size (complex elements) of the spectra buffer of b2_welch_rfft, and the slot of a bin in it (-1 on bad arguments). */
+int64_t b2_welch_spectra_elems(int wl, int M, int64_t Kp);
+int b2_welch_bin_slot(int wl, int bin);
 
 /* K2: per-bin Hermitian rank-K accumulation S_f (+)= X_f X_f^H of the bins [bin0, bin0 + nbins).
  * Replaces the M(M+1)/2 `_welch` calls of _csm_welch (_spectral_methods.py:351-369) and the
  * frame sum of np.mean (:152); the division by the frame count happens in b2_csm_finalize
  * so partial sums of frame shards can be all-reduced first -- bin range by bin range, which is
  * what lets the reduction of one range overlap the accumulation of the next.
- *   X_dev   spectra in the [Kp/16][nb][M][16] layout written by b2_welch_rfft
+ *   X_dev   spectra in the layout written by b2_welch_rfft (nb = wl/2 + 1)
  *   S_dev   PACKED lower triangle, [nb][M(M+1)/2] complex128: S_f[j][i] (j >= i) at
  *           f*M(M+1)/2 + j(j+1)/2 + i.  The pointer is the base of the whole [nb] buffer.
  *   accumulate  0: overwrite, 1: add to the existing sums */

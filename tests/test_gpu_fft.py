@@ -32,12 +32,17 @@ def run_k0_k1(x, wl, step, window, detrend, scale, prec, transposed_storage=Fals
     tw = torch.empty(wl, dtype=cdt, device=dev)
     N.check(lib.b2_fft_twiddles(wl, prec, N.ptr(tw), st))
     win = torch.from_numpy(window).to(dev).to(rdt)
-    X = torch.full((wl // 2 + 1, M, Kp), float("nan"), dtype=cdt, device=dev)
+    nb = wl // 2 + 1
+    ng = wl // 8 + 1
+    assert lib.b2_welch_spectra_elems(wl, M, Kp) == Kp // 16 * ng * M * 64
+    X = torch.full((Kp // 16, ng, M, 8, 4, 2), float("nan"), dtype=cdt, device=dev)
     N.check(lib.b2_welch_rfft(N.ptr(xc), Lp, M, wl, step, K, N.ptr(win), N.ptr(tw), int(detrend), scale,
                               N.ptr(X), Kp, prec, st))
     torch.cuda.synchronize()
-    # device layout [Kp/16][nb][M][16] -> (nb, M, Kp)
-    Xn = X.cpu().numpy().reshape(Kp // 16, wl // 2 + 1, M, 16).transpose(1, 2, 0, 3).reshape(wl // 2 + 1, M, Kp)
+    # device layout [Kp/16][slot group][M][8 frame pairs][4 slots][2 frames] -> (slots, M, Kp) -> the bins' slots
+    slots = np.array([lib.b2_welch_bin_slot(wl, f) for f in range(nb)])
+    assert len(set(slots)) == nb and slots.max() < 4 * ng
+    Xn = X.cpu().numpy().transpose(1, 4, 2, 0, 3, 5).reshape(4 * ng, M, Kp)[slots]
     return xc.cpu().numpy(), Xn, K, tw.cpu().numpy()
 
 
