@@ -400,10 +400,15 @@ class BeamformerFunctional(_QuadraticFormBeamformer):
 class BeamformerOrthogonal(_QuadraticFormBeamformer):
     """Orthogonal beamforming (Sarradj 2010): per bin, each of the largest eigenpairs of the CSM is
     mapped with |h^H v|^2 = h^H (v v^H) h and its eigenvalue is assigned to the grid point where
-    that map peaks.  The peak location is an arg-max over the grid, so the quadratic forms run on
-    the fp64 CUDA-core kernel (`simt_f64`): a tensor-core rounding difference could move it."""
+    that map peaks.  The O(G F E M^2) maps run on the tensor-core kernel; the peak location is an
+    arg-max over the grid that a rounding difference of that kernel (~1e-6 of a column's maximum)
+    could move, so every grid point within 1e-3 of its column's maximum is re-evaluated in fp64
+    (a few device operations on the (point, bin) pairs) and the arg-max and the assigned power are
+    taken from those values.  With a map mode forced by the caller the whole map runs on that
+    kernel's fp64 CUDA-core sibling instead (`simt_f64`)."""
 
     beamformer_type = "Orthogonal"
+    _recheck_margin = 1e-3
 
     def get_beamformer_map(self, center_frequency_hz: float, octave_fraction: int = 3,
                            number_eigenvalues: int | None = None):
@@ -417,18 +422,39 @@ class BeamformerOrthogonal(_QuadraticFormBeamformer):
             assert number_eigenvalues > 0, "At least one eigenvalue of the CSM must be regarded"
         fsel, csm = self._band(center_frequency_hz, octave_fraction)
         F, G = len(fsel), self.grid.number_of_points
+        dev = csm.device
         w, v = torch.linalg.eigh(csm)                          # ascending eigenvalues
         print("...Apply...")
-        out = torch.zeros((G, F), dtype=torch.float64, device=csm.device)
-        cols = torch.arange(F, device=csm.device)
+        out = torch.zeros((G, F), dtype=torch.float64, device=dev)
+        cols = torch.arange(F, device=dev)
+        tensor_cores = engine.config.map_mode.lower() == "auto" and engine.tc_map_available()
+        if tensor_cores:
+            k_dev = torch.from_numpy(np.ascontiguousarray(fsel * np.pi * 2 / self.c, dtype=np.float64)).to(dev)
+            mic_dev = torch.from_numpy(np.ascontiguousarray(self.mics._coordinates, dtype=np.float64)).to(dev)
+            ctr_dev = torch.from_numpy(np.ascontiguousarray(self.mics.array_center_coordinates, dtype=np.float64)).to(dev)
+            g_dev = self.grid._device_coordinates(dev)
+            form = _steering_code(self.st_vec)
         # a few eigenpairs at a time keeps the batch of rank-1 matrices small: (chunk * F, M, M)
         chunk = max(1, min(number_eigenvalues, (1 << 28) // max(1, F * csm.shape[1] ** 2 * 16)))
         for e0 in range(0, number_eigenvalues, chunk):
             es = range(e0, min(number_eigenvalues, e0 + chunk))
             vecs = torch.stack([v[:, :, -e - 1] for e in es])                         # (E, F, M)
             rank1 = vecs[..., :, None] * vecs.conj()[..., None, :]                    # (E, F, M, M)
-            power = self._per_bin_power(np.tile(fsel, len(es)), rank1.reshape(-1, *rank1.shape[2:]),
-                                        mode="simt_f64")                              # (G, E*F)
+            rank1 = rank1.reshape(-1, *rank1.shape[2:])
+            power = None
+            if tensor_cores:
+                power = self._per_bin_power(np.tile(fsel, len(es)), rank1)            # (G, E*F), FP16x3
+                top = power.amax(dim=0)
+                pts, cs = (power >= top - self._recheck_margin * top.abs()).nonzero(as_tuple=True)
+                if pts.numel() <= 64 * power.shape[1] + 4096:
+                    h = _steering_pairs(k_dev[cs % F], g_dev[pts], mic_dev, ctr_dev, form)      # (pairs, M)
+                    exact = (h.conj() * vecs.reshape(-1, vecs.shape[-1])[cs]).sum(dim=1).abs() ** 2
+                    power.fill_(-float("inf"))
+                    power[pts, cs] = exact
+                else:
+                    power = None               # a flat column (no distinct peak): whole map in fp64
+            if power is None:
+                power = self._per_bin_power(np.tile(fsel, len(es)), rank1, mode="simt_f64")
             power = power.reshape(G, len(es), F)
             for i, e in enumerate(es):                                                 # eigenpair order matters
                 peak = torch.argmax(power[:, i, :], dim=0)                             # (F,)
