@@ -386,8 +386,11 @@ class BeamformerFunctional(_QuadraticFormBeamformer):
         import torch
 
         fsel, csm = self._band(center_frequency_hz, octave_fraction)
-        u, s, vh = torch.linalg.svd(csm)
-        powered = (u * (s ** (1.0 / gamma)).to(u.dtype)[:, None, :]) @ vh
+        # The reference takes u s^(1/gamma) v^H from an SVD (:1201).  The singular triplets of a Hermitian matrix
+        # are (|lambda|, sign(lambda) v, v), so the same matrix comes out of the eigen-decomposition -- which stays
+        # Hermitian also where the SVD of a rank-deficient CSM returns unrelated u and v for the null space.
+        lam, v = engine.hermitian_eig(csm)
+        powered = (v * (torch.sign(lam) * lam.abs() ** (1.0 / gamma)).to(v.dtype)[:, None, :]) @ v.mH
         print("...Apply...")
         power = self._per_bin_power(fsel, powered)
         # steering normalisation h^H h = sum_m |h_m|^2 does not depend on the bin: identity matrix, one bin
@@ -423,7 +426,7 @@ class BeamformerOrthogonal(_QuadraticFormBeamformer):
         fsel, csm = self._band(center_frequency_hz, octave_fraction)
         F, G = len(fsel), self.grid.number_of_points
         dev = csm.device
-        w, v = torch.linalg.eigh(csm)                          # ascending eigenvalues
+        w, v = engine.hermitian_eig(csm)                       # ascending eigenvalues
         print("...Apply...")
         out = torch.zeros((G, F), dtype=torch.float64, device=dev)
         cols = torch.arange(F, device=dev)

@@ -534,6 +534,27 @@ def delay_mix(signals, taps: np.ndarray, shifts: np.ndarray, out_length: int, de
     return out
 
 
+def hermitian_eig(matrices):
+    """(w, v) of a batch of Hermitian matrices, complex128 CUDA tensor (nb, M, M): eigenvalues in ASCENDING order
+    (nb, M) float64 and the eigenvectors as columns (nb, M, M) -- the contract of np.linalg.eigh, which the reference
+    calls per bin (beamforming/beamforming.py:1107).  Only the lower triangle is read.  Orders up to
+    `b2_heig_max_order()` run in the shared-memory Jacobi kernel (all bins at once, one CTA each); larger matrices
+    go to torch.linalg.eigh (cuSOLVER), one of the O(F M^3) per-bin factorisations outside the hot loop."""
+    torch = _torch()
+    lib = N.lib()
+    nb, M = int(matrices.shape[0]), int(matrices.shape[1])
+    if M > int(lib.b2_heig_max_order()):
+        return torch.linalg.eigh(matrices)
+    a = matrices.contiguous()
+    w = torch.empty((nb, M), dtype=torch.float64, device=a.device)
+    v = torch.empty((nb, M, M), dtype=torch.complex128, device=a.device)
+    with torch.cuda.device(a.device):
+        N.check(lib.b2_heig_jacobi(N.ptr(a), M, nb, N.ptr(w), N.ptr(v), None, N.stream_handle()), "b2_heig_jacobi")
+    _count()
+    w, order = torch.sort(w, dim=1)
+    return w, torch.gather(v, 2, order[:, None, :].expand(nb, M, M))
+
+
 def csm_rank1(spectrum_dev, factor: float, halve_edges: bool, amplitude_sqrt: bool):
     """(nb, M, M) complex128 CSM of one spectrum per channel -- `_csm_fft` (_spectral_methods.py:374-443)."""
     torch = _torch()

@@ -127,6 +127,19 @@ int b2_welch_autopower(const void *X_dev, int M, int64_t Kp, int nb, void *P_dev
 int b2_auto_finalize(const void *P_dev, int M, int nb, double inv_frames, double factor, int halve_edges,
                      int amplitude_sqrt, void *out_dev, void *stream);
 
+/* Batched Hermitian eigen-decomposition of small matrices, one CTA per matrix (parallel two-sided Jacobi in shared
+ * memory, float64).  Replaces the per-bin `np.linalg.eigh(csm)` of BeamformerOrthogonal (beamforming/beamforming.py:
+ * 1107) and the `np.linalg.svd(csm)` of BeamformerFunctional (:1201; for a Hermitian matrix the singular
+ * triplets are (|lambda|, sign(lambda) v, v)).
+ *   A_dev        [nb][M][M] complex128, Hermitian: the lower triangle (and the real part of the diagonal) is read
+ *   w_out_dev    [nb][M] float64 eigenvalues, NOT sorted
+ *   V_out_dev    [nb][M][M] complex128, column j = eigenvector of w[j]
+ *   sweeps_out_dev  optional [nb] int32: Jacobi sweeps each matrix took
+ * M <= b2_heig_max_order() (the matrix and the vectors stay in shared memory), else B2_EUNSUPPORTED. */
+int b2_heig_max_order(void);
+int b2_heig_jacobi(const void *A_dev, int M, int nb, void *w_out_dev, void *V_out_dev, void *sweeps_out_dev,
+                   void *stream);
+
 /* Large / arbitrary-length real FFT along the time axis, batched over rows (float64 arithmetic).  Replaces
  * `np.fft.rfft(time_data, axis=0, n=fft_length)` of the single-FFT spectrum (classes/signal.py:903-911;
  * fft_length = scipy.fft.next_fast_len(L, True) or L itself -- not a power of two) and
