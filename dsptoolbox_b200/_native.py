@@ -38,6 +38,10 @@ PROTOTYPES = {
     "b2_csm_finalize": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_void_p]),
     "b2_welch_autopower": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_void_p]),
     "b2_auto_finalize": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_void_p]),
+    "b2_cleansc_component": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     POINTER(c_double), c_void_p, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2_das_rank1_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_double, c_void_p, POINTER(c_double),
+                                    c_void_p, c_int64, c_int, c_int, c_double, c_void_p, c_void_p]),
     "b2_heig_max_order": (c_int, []),
     "b2_heig_jacobi": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2_fft_plan_bytes": (c_int64, [c_int64]),

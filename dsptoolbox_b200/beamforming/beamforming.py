@@ -470,10 +470,12 @@ class BeamformerCleanSC(_QuadraticFormBeamformer):
 
     The reference deconvolves one bin after the other (`_clean_sc_deconvolve`,
     beamforming/_beamforming.py:194-297); here all bins of the band iterate in lock-step: every
-    iteration is one arg-max per bin, a handful of M-vector updates (torch, on the device) and ONE
-    launch of the map kernel that subtracts the coherent source component h^H G_f h of every bin
-    from its dirty map.  The peak search makes the iteration sensitive to rounding, so the
-    quadratic forms use the fp64 CUDA-core kernel."""
+    iteration is one arg-max per bin, ONE launch that forms the source component of every bin
+    (`b2_cleansc_component`: stopping criterion, steering vector to the peak, the 20 fixed-point
+    steps, the degraded CSM) and ONE launch that subtracts Re(h^H G_f h) of the rank-one G_f from
+    every bin's dirty map in O(G F M) (`b2_das_rank1_update`).  The peak search makes the
+    iteration sensitive to rounding, so everything stays in fp64 (the first, full-rank map runs on
+    the fp64 CUDA-core kernel)."""
 
     beamformer_type = "CleanSC"
 
@@ -496,44 +498,35 @@ class BeamformerCleanSC(_QuadraticFormBeamformer):
         if remove_csm_diagonal:
             csm[:, diag, diag] = 0
         print("...Create and deconvolve map...")
-        dirty = self._per_bin_power(fsel, csm, mode="simt_f64").clone()          # (G, F)
+        dirty = self._per_bin_power(fsel, csm, mode="simt_f64").clone().contiguous()          # (G, F)
         second = torch.zeros_like(dirty)
-        D0, D1 = 2 * csm, csm.clone()
+        D0, D1 = (2 * csm).contiguous(), csm.clone().contiguous()
         active = torch.ones(F, dtype=torch.bool, device=dev)
         cols = torch.arange(F, device=dev)
-        k = fsel * np.pi * 2 / self.c
-        k_dev = torch.from_numpy(np.ascontiguousarray(k, dtype=np.float64)).to(dev)
+        zero = torch.zeros((), dtype=torch.float64, device=dev)
+        k_dev = torch.from_numpy(np.ascontiguousarray(fsel * np.pi * 2 / self.c, dtype=np.float64)).to(dev)
+        f_dev = torch.from_numpy(np.ascontiguousarray(fsel, dtype=np.float64)).to(dev)
         mic_dev = torch.from_numpy(np.ascontiguousarray(self.mics._coordinates, dtype=np.float64)).to(dev)
-        ctr_dev = torch.from_numpy(np.ascontiguousarray(self.mics.array_center_coordinates, dtype=np.float64)).to(dev)
+        ctr = np.ascontiguousarray(self.mics.array_center_coordinates, dtype=np.float64)
         g_dev = self.grid._device_coordinates(dev)
         form = _steering_code(self.st_vec)
+        h_src = torch.empty((F, M), dtype=torch.complex128, device=dev)
+        scale = torch.empty(F, dtype=torch.float64, device=dev)
         for it in range(maximum_iterations):
             peak = torch.argmax(dirty, dim=0)                                     # (F,)
             pmax = dirty[peak, cols]
-            second[peak[active], cols[active]] += pmax[active] * safety_factor
-            # stopping criterion of the reference: the degraded CSM stopped shrinking (matrix 1-norm)
-            n1 = D1.abs().sum(dim=1).amax(dim=1)
-            n0 = D0.abs().sum(dim=1).amax(dim=1)
-            active = active & ~(n1 >= n0)
-            # the only host round trip of the loop, every 8th iteration: finished bins are masked out below, so running
-            # a few iterations past the last active bin changes nothing
+            # the reference stores the peak BEFORE it looks at the stopping criterion (:250-260)
+            second.index_put_((peak, cols), torch.where(active, pmax * safety_factor, zero), accumulate=True)
+            # stopping criterion, steering vector to the peak, source component h, degraded CSM: one launch for all bins
+            engine.cleansc_component(D0, D1, peak, pmax, active, k_dev, mic_dev, ctr, g_dev, form, safety_factor,
+                                     remove_csm_diagonal, h_src, scale)
+            # the only host round trip of the loop, every 8th iteration: finished bins are masked out (scale 0), so
+            # running a few iterations past the last active bin changes nothing
             if it % 8 == 7 and not bool(active.any()):
                 break
-            # steering vector of every bin to its own peak point, on the device (F x M values)
-            w_max = _steering_pairs(k_dev, g_dev[peak], mic_dev, ctr_dev, form)        # (F, M)
-            w2 = (w_max.conj() * w_max)
-            D_ = torch.einsum("fmn,fn->fm", D1, w_max) / pmax[:, None]
-            h_ = w_max.clone()
-            for _ in range(20):
-                H = h_.conj() * h_
-                h_ = (D_ + H * w_max) / torch.sqrt(1 + (H * w2).sum(dim=1, keepdim=True))
-            Gm = h_[:, :, None] * h_.conj()[:, None, :] * pmax[:, None, None]
-            if remove_csm_diagonal:
-                Gm[:, diag, diag] = 0
-            Gm = torch.where(active[:, None, None], Gm, torch.zeros_like(Gm))       # finished bins stay put
-            dirty -= self._per_bin_power(fsel, Gm, mode="simt_f64") * safety_factor
-            D0 = torch.where(active[:, None, None], D1, D0)
-            D1 = D1 - safety_factor * Gm
+            # dirty -= Re(h_g^H G h_g) * safety_factor with the rank-one G = h h^H P_max of every bin
+            engine.das_rank1_update(h_src, scale, f_dev, self.c, mic_dev, ctr, g_dev, form, remove_csm_diagonal,
+                                    -safety_factor, dirty)
         return self._finish(second, fsel)
 
 

@@ -534,6 +534,32 @@ def delay_mix(signals, taps: np.ndarray, shifts: np.ndarray, out_length: int, de
     return out
 
 
+def cleansc_component(D0, D1, peak, pmax, active, k_dev, mic_dev, center_xyz, grid_dev, steering: int,
+                      safety_factor: float, remove_diag: bool, h_out, scale_out):
+    """One CLEAN-SC step of every bin on the degraded CSMs (in place): see b2_cleansc_component in include/b2dsp.h."""
+    F, M = int(D1.shape[0]), int(D1.shape[1])
+    assert D0.is_contiguous() and D1.is_contiguous() and h_out.is_contiguous() and active.dtype == _torch().bool
+    with _torch().cuda.device(D1.device):
+        N.check(N.lib().b2_cleansc_component(N.ptr(D0), N.ptr(D1), M, F, N.ptr(peak), N.ptr(pmax), N.ptr(active),
+                                             N.ptr(k_dev), N.ptr(mic_dev), N.vec3(center_xyz), N.ptr(grid_dev),
+                                             int(steering), float(safety_factor), int(bool(remove_diag)), N.ptr(h_out),
+                                             N.ptr(scale_out), N.stream_handle()), "b2_cleansc_component")
+    _count()
+
+
+def das_rank1_update(vectors, scale, freqs_dev, c: float, mic_dev, center_xyz, grid_dev, steering: int,
+                     remove_diag: bool, alpha: float, out):
+    """out[g, f] += alpha * scale[f] * Re(h_g^H (v_f v_f^H [minus its diagonal]) h_g), float64, in O(G F M)."""
+    F, M = int(vectors.shape[0]), int(vectors.shape[1])
+    G = int(grid_dev.shape[0])
+    assert out.is_contiguous() and tuple(out.shape) == (G, F) and vectors.is_contiguous()
+    with _torch().cuda.device(out.device):
+        N.check(N.lib().b2_das_rank1_update(N.ptr(vectors), N.ptr(scale), M, F, N.ptr(freqs_dev), float(c), N.ptr(mic_dev),
+                                            N.vec3(center_xyz), N.ptr(grid_dev), G, int(steering), int(bool(remove_diag)),
+                                            float(alpha), N.ptr(out), N.stream_handle()), "b2_das_rank1_update")
+    _count()
+
+
 def hermitian_eig(matrices):
     """(w, v) of a batch of Hermitian matrices, complex128 CUDA tensor (nb, M, M): eigenvalues in ASCENDING order
     (nb, M) float64 and the eigenvectors as columns (nb, M, M) -- the contract of np.linalg.eigh, which the reference

@@ -127,6 +127,31 @@ int b2_welch_autopower(const void *X_dev, int M, int64_t Kp, int nb, void *P_dev
 int b2_auto_finalize(const void *P_dev, int M, int nb, double inv_frames, double factor, int halve_edges,
                      int amplitude_sqrt, void *out_dev, void *stream);
 
+/* CLEAN-SC (float64), all bins of a band in lock-step; one iteration of `_clean_sc_deconvolve`
+ * (beamforming/_beamforming.py:246-295) is these two launches plus the arg-max of the dirty map.
+ *
+ * b2_cleansc_component, one CTA per bin: stopping criterion ||D1||_1 >= ||D0||_1 (:259; a finished bin clears its
+ * `active` flag and stays finished), steering vector w to the bin's peak point (distances by the expansion formula of
+ * helpers/other.py:131-153, amplitudes of beamforming.py:1515-1703), d = D1 w / P_max, the 20 fixed-point steps
+ * h = (d + |h|^2 w) / sqrt(1 + sum |h|^2 |w|^2) (:274-278), G = h h^H P_max (diagonal removed on request, :280-283),
+ * D0 <- D1, D1 <- D1 - safety_factor G (:291-294).
+ *   D0_dev, D1_dev   [nbins][M][M] complex128, updated in place
+ *   peak_dev         [nbins] int64 grid-point index of each bin's maximum;  pmax_dev [nbins] float64 its power
+ *   active_dev       [nbins] bytes (in / out)
+ *   h_out_dev        [nbins][M] complex128 (zeros for finished bins);  scale_out_dev [nbins] float64: P_max or 0
+ *
+ * b2_das_rank1_update: out[g][f] += alpha * scale_f * (|sum_m conj(h_gm) v_fm|^2 - [remove_diag] sum_m |h_gm|^2 |v_fm|^2)
+ * with the steering vectors h_g of the map kernels -- Re(h_g^H A_f h_g) of the rank-one matrices A_f = scale_f v_f v_f^H
+ * in O(G F M), which is what :285-289 subtracts from the dirty map (alpha = -safety_factor).
+ *   vectors_dev [nbins][M] complex128, scale_dev [nbins] float64 (0 skips the bin), out_dev [G][nbins] float64 */
+int b2_cleansc_component(void *D0_dev, void *D1_dev, int M, int nbins, const void *peak_dev, const void *pmax_dev,
+                         void *active_dev, const void *wave_numbers_dev, const void *mic_xyz_dev,
+                         const double *center_xyz, const void *grid_xyz_dev, int steering, double safety_factor,
+                         int remove_diag, void *h_out_dev, void *scale_out_dev, void *stream);
+int b2_das_rank1_update(const void *vectors_dev, const void *scale_dev, int M, int nbins, const void *freqs_dev,
+                        double c, const void *mic_xyz_dev, const double *center_xyz, const void *grid_xyz_dev,
+                        int64_t G, int steering, int remove_diag, double alpha, void *out_dev, void *stream);
+
 /* Batched Hermitian eigen-decomposition of small matrices, one CTA per matrix (parallel two-sided Jacobi in shared
  * memory, float64).  Replaces the per-bin `np.linalg.eigh(csm)` of BeamformerOrthogonal (beamforming/beamforming.py:
  * 1107) and the `np.linalg.svd(csm)` of BeamformerFunctional (:1201; for a Hermitian matrix the singular

@@ -49,6 +49,7 @@ res = {
     "functional": timed(lambda: BF.BeamformerFunctional(sig, ma, grid, st), 2000.0, 3, 10),
     "orthogonal": timed(lambda: BF.BeamformerOrthogonal(sig, ma, grid, st), 2000.0, 3, 8),
     "cleansc": timed(lambda: BF.BeamformerCleanSC(sig, ma, grid, st), 2000.0, 3, 16),
+    "cleansc_128_iterations": timed(lambda: BF.BeamformerCleanSC(sig, ma, grid, st), 2000.0, 3),
 }
 print(json.dumps({"metric": "f1 beamformer maps (public API, CSM cached on the device)", "unit": "ms per get_beamformer_map",
                   "config": {"M": M, "seconds": SECONDS, "nfft": WL, "G": G, "fc": 2000.0, "octave_fraction": 3,
