@@ -273,6 +273,31 @@ def test_golden_cleansc(golden_dir):
         quiet_map(BF.BeamformerCleanSC(sig, ma, grid, st), 2000.0, 3, 5, 1.5)
 
 
+@pytest.mark.parametrize("form", ["Inverse", "TruePower"])
+def test_other_beamformers_all_formulations_against_oracle(golden_dir, form):
+    """The golden maps of the four other beamformers use the Classic and TrueLocation steering vectors; the CLEAN-SC
+    component kernel and the fp64 re-check of the Orthogonal beamformer evaluate the steering vector themselves, so the
+    two remaining formulations are checked against the oracle (itself pinned to those golden maps)."""
+    g = np.load(os.path.join(golden_dir, "das_small.npz"))
+    sig, ma = _golden_setup(g)
+    grid = BF.Regular2DGrid(g["line1"], g["line2"], ("x", "y"), float(g["value3"]))
+    st = BF.SteeringVector(getattr(BF.SteeringVectorType, form))
+    f, csm = sig.get_csm()
+    mic = np.stack([g["mic_x"], g["mic_y"], g["mic_z"]], 1)
+    low = form.lower()
+    for fc, frac in [(2000.0, 3), (3000.0, 0)]:
+        m, _ = quiet_map(BF.BeamformerCleanSC(sig, ma, grid, st), fc, frac, 12, 0.7, True)
+        ref = R.clean_sc_map(f, csm, mic, grid.coordinates, fc, frac, 12, 0.7, True, 343.0, low).reshape(m.shape)
+        assert np.max(np.abs(m - ref)) <= 1e-7 * np.max(np.abs(ref)), ("cleansc", form, fc)
+        m, _ = quiet_map(BF.BeamformerOrthogonal(sig, ma, grid, st), fc, frac, 4)
+        ref = R.orthogonal_map(f, csm, mic, grid.coordinates, fc, frac, 4, 343.0, low).reshape(m.shape)
+        assert np.array_equal(m != 0, ref != 0), ("orthogonal", form, fc)
+        assert np.max(np.abs(m - ref)) <= 1e-8 * np.max(np.abs(ref)), ("orthogonal", form, fc)
+        m, _ = quiet_map(BF.BeamformerFunctional(sig, ma, grid, st), fc, frac, 10)
+        ref = R.functional_map(f, csm, mic, grid.coordinates, fc, frac, 10, 343.0, low).reshape(m.shape)
+        assert_map_close(m, ref, rel=2e-4, db=0.05)
+
+
 @pytest.mark.parametrize("mode", [m for m in MODES if m in ("f16x3", "mixed", "tf32x3")])
 @pytest.mark.parametrize("M", [300, 520])
 def test_many_microphones_against_oracle(mode, M):
