@@ -38,6 +38,10 @@ class Config:
     #: host recordings above this size are uploaded in frame chunks on a copy stream, so that the
     #: upload of chunk i+1 overlaps K0/K1/K2 of chunk i (0 disables the chunking)
     h2d_chunk_bytes: int = 768 << 20
+    #: pageable host recordings above this size go through a ring of pinned staging buffers filled by
+    #: `h2d_stage_threads` host threads (0 leaves the upload to the driver's own staging)
+    h2d_stage_min_bytes: int = 64 << 20
+    h2d_stage_threads: int = 6
     #: last-call statistics (kernel times are only filled when `profile` is on)
     profile: bool = False
     stats: dict = field(default_factory=dict)
@@ -134,7 +138,86 @@ def _twiddles(wl: int, prec: int, device):
     return tw
 
 
-def _as_device_block(x, t0: int, t1: int, device):
+class _Stager:
+    """Pageable host memory -> device through pinned staging buffers.
+
+    A `cudaMemcpy` from pageable memory is staged by the driver through one bounce buffer with one copying
+    thread (measured: 13.7 GB/s for the 5.9 GB recording of the benchmark against 50+ GB/s from pinned memory).
+    Here several host threads copy slices into a ring of pinned slots (numpy releases the GIL for the copy) and
+    every filled slot goes to the device with an asynchronous copy on the current stream; a slot is reused when
+    the event recorded behind its copy has passed."""
+
+    SLOT_BYTES = 32 << 20
+    SLOTS = 8
+
+    def __init__(self):
+        self.ring = None
+        self.pool = None
+
+    def upload(self, src: np.ndarray, device, out=None):
+        """`src`: C-contiguous numpy array; returns a CUDA tensor of the same shape and dtype (`out` if given)."""
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+
+        torch = _torch()
+        if self.ring is None:
+            self.ring = torch.empty(self.SLOTS * self.SLOT_BYTES, dtype=torch.uint8).pin_memory()
+            self.ring_np = self.ring.numpy()
+        workers = max(1, int(config.h2d_stage_threads))
+        if self.pool is None or self.pool._max_workers != workers:
+            self.pool = ThreadPoolExecutor(max_workers=workers)
+        if out is None:
+            out = torch.empty(src.shape, dtype=torch.from_numpy(src[:0]).dtype, device=device)
+        src_b = src.reshape(-1).view(np.uint8)
+        dst_b = out.reshape(-1).view(torch.uint8)
+        n, sb = src_b.nbytes, self.SLOT_BYTES
+        pieces = [(o, min(sb, n - o)) for o in range(0, n, sb)]
+        stream = torch.cuda.current_stream(device)
+        events = [None] * self.SLOTS
+        fill = lambda s, o, m: np.copyto(self.ring_np[s * sb:s * sb + m], src_b[o:o + m])   # noqa: E731
+        pending, nxt = deque(), 0
+        for i, (o, m) in enumerate(pieces):
+            while nxt < len(pieces) and nxt < i + self.SLOTS:
+                slot = nxt % self.SLOTS
+                if events[slot] is not None:
+                    events[slot].synchronize()               # the device copy out of this slot has finished
+                pending.append(self.pool.submit(fill, slot, *pieces[nxt]))
+                nxt += 1
+            pending.popleft().result()
+            slot = i % self.SLOTS
+            dst_b[o:o + m].copy_(self.ring[slot * sb:slot * sb + m], non_blocking=True)
+            events[slot] = torch.cuda.Event()
+            events[slot].record(stream)
+        return out
+
+
+_stager = _Stager()
+
+
+def _host_to_device(arr: np.ndarray, device, slot: str | None = None):
+    """C-contiguous host array -> CUDA tensor: asynchronous from pinned memory, staged by `_Stager` from large
+    pageable arrays, the driver's own path otherwise.  With `slot` the destination is that workspace buffer
+    (the caller orders its reuse) instead of a fresh allocation."""
+    torch = _torch()
+    t = torch.from_numpy(arr)
+    out = None
+    if slot is not None:
+        buf = _workspaces.get((slot, str(device)))                 # never shrunk: the last chunk of a call is the small one
+        if buf is None or buf.numel() < arr.nbytes:
+            if buf is not None:
+                torch.cuda.synchronize(device)                         # rare (a larger recording): nobody reads the old one
+            _workspaces.pop((slot, str(device)), None)
+            buf = _workspaces[(slot, str(device))] = torch.empty(max(arr.nbytes, 16), dtype=torch.uint8, device=device)
+        out = buf[:arr.nbytes].view(t.dtype).reshape(arr.shape)
+    if (config.h2d_stage_threads > 0 and arr.nbytes >= config.h2d_stage_min_bytes and not t.is_pinned()):
+        return _stager.upload(arr, device, out)
+    if out is None:
+        return t.to(device, non_blocking=True)
+    out.copy_(t, non_blocking=True)
+    return out
+
+
+def _as_device_block(x, t0: int, t1: int, device, slot: str | None = None):
     """Upload rows [t0, t1) of the (L, M) recording without changing its memory order.
 
     Returns (tensor, in_dtype code, stride_t, stride_m) for b2_prepare_channels.  `x` may be a
@@ -155,13 +238,10 @@ def _as_device_block(x, t0: int, t1: int, device):
     code = N.F64 if x.dtype == np.float64 else N.F32
     xs = x[t0:t1]
     if xs.flags.c_contiguous:
-        t = torch.from_numpy(xs).to(device, non_blocking=True)
-        return t, code, xs.shape[1], 1
+        return _host_to_device(xs, device, slot), code, xs.shape[1], 1
     if xs.T.flags.c_contiguous:          # (channels, time) storage seen through Signal's transpose
-        t = torch.from_numpy(xs.T).to(device, non_blocking=True)
-        return t, code, 1, xs.shape[0]
-    t = torch.from_numpy(np.ascontiguousarray(xs)).to(device, non_blocking=True)
-    return t, code, xs.shape[1], 1
+        return _host_to_device(xs.T, device, slot), code, 1, xs.shape[0]
+    return _host_to_device(np.ascontiguousarray(xs), device, slot), code, xs.shape[1], 1
 
 
 class _Timer:
@@ -283,26 +363,36 @@ def _csm_partial_sums(torch, lib, prec, device, x, length, wl, step, window, det
         assert t0 >= row_offset and t1 - row_offset <= x.shape[0], "frame range reads samples outside this shard"
         return t0, t1
 
-    # the upload of chunk i+1 is issued (on a copy stream) right after the kernels of chunk i were enqueued
+    # the upload of chunk i+1 is issued (on a copy stream) right after the kernels of chunk i were enqueued.
+    # numpy recordings land in two alternating workspace buffers (fresh 768 MB tensors per chunk made the caching
+    # allocator cudaMalloc 5 GB more on every call: profiles/r2_e2e_stage1_diag.txt); a buffer is written again
+    # only after the K0 launch that read it has finished (`consumed`).
     copy_stream = torch.cuda.Stream(device=device) if (on_host and len(chunks) > 1) else None
+    slots = ("h2d0", "h2d1") if isinstance(x, np.ndarray) else (None, None)
+    consumed = [None, None]
+    if copy_stream is not None:
+        copy_stream.wait_stream(cur)                     # earlier calls may still be reading the buffers
 
-    def upload(c):
-        t0, t1 = rows_of(c)
+    def upload(ci):
+        t0, t1 = rows_of(chunks[ci])
         if copy_stream is None:
-            return _as_device_block(x, t0 - row_offset, t1 - row_offset, device), None
+            return _as_device_block(x, t0 - row_offset, t1 - row_offset, device, slots[ci % 2]), None
         with torch.cuda.stream(copy_stream):
-            blk = _as_device_block(x, t0 - row_offset, t1 - row_offset, device)
+            if consumed[ci % 2] is not None:
+                copy_stream.wait_event(consumed[ci % 2])
+            blk = _as_device_block(x, t0 - row_offset, t1 - row_offset, device, slots[ci % 2])
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return blk, ev
 
     pending = []                                         # handles of the overlapped reductions
-    nxt = upload(chunks[0]) if chunks else None
+    nxt = upload(0) if chunks else None
     for ci, (kc, kn) in enumerate(chunks):
         (xs, code, s_t, s_m), ev = nxt
         if ev is not None:
             cur.wait_event(ev)
-            xs.record_stream(cur)
+            if slots[0] is None:
+                xs.record_stream(cur)
         nfr = kn - kc
         Kp = (nfr + tile - 1) // tile * tile
         t0, t1 = rows_of((kc, kn))
@@ -313,6 +403,9 @@ def _csm_partial_sums(torch, lib, prec, device, x, length, wl, step, window, det
         N.check(lib.b2_prepare_channels(N.ptr(xs), code, s_t, s_m, 0, t1 - t0, M, N.ptr(xc), Lp, prec, st),
                 "b2_prepare_channels")
         _count()
+        if slots[0] is not None:
+            consumed[ci % 2] = torch.cuda.Event()
+            consumed[ci % 2].record(cur)
         timer.mark("k0_prepare")
         X = _workspace_tensor("spectra", (_spectra_elems(lib, wl, M, Kp),), cdt, device)
         N.check(lib.b2_welch_rfft(N.ptr(xc), Lp, M, wl, step, nfr, N.ptr(win), N.ptr(tw), int(bool(detrend)),
@@ -334,7 +427,7 @@ def _csm_partial_sums(torch, lib, prec, device, x, length, wl, step, window, det
                     pending.append(reduce_fn(S[b0:b1]))
         timer.mark("k2_herk")
         if ci + 1 < len(chunks):
-            nxt = upload(chunks[ci + 1])
+            nxt = upload(ci + 1)
         del xs, xc, X
     if reduce_fn is not None:
         if not chunks or diag_only:

@@ -128,6 +128,31 @@ def test_input_layouts_and_dtypes():
     assert_csm_close(cd.cpu().numpy(), ref)
 
 
+def test_pageable_recordings_go_through_the_pinned_staging_ring():
+    """Large pageable numpy recordings are uploaded through `engine._Stager` (threads -> pinned slots -> async
+    copies): bit-identical device data, several ring rounds, row- and channel-major storage, ragged sizes."""
+    rng = np.random.default_rng(8)
+    old = engine.config.h2d_stage_min_bytes, engine._Stager.SLOT_BYTES
+    try:
+        engine.config.h2d_stage_min_bytes = 1 << 20
+        engine._Stager.SLOT_BYTES = (1 << 20) + 4096          # 8 slots of ~1 MB: the 20 MB upload laps the ring twice
+        engine._stager.ring = None
+        x = rng.standard_normal((262_147, 10))
+        for arr in (x, np.ascontiguousarray(x.T).T):
+            t, code, s_t, s_m = engine._as_device_block(arr, 3, x.shape[0] - 5, torch.device("cuda", 0))
+            torch.cuda.synchronize()
+            got = t.cpu().numpy()
+            want = arr[3:x.shape[0] - 5]
+            assert np.array_equal(got if s_m == 1 else got.T, want)
+        xs = x[:40_000]
+        ref = R.csm_welch(xs, 8000, 256, "hann", 50, True, "fftbackward")[1]
+        c = dsp.Signal(None, xs, 8000).set_spectrum_parameters(window_length_samples=256).get_csm()[1]
+        assert_csm_close(c, ref)
+    finally:
+        engine.config.h2d_stage_min_bytes, engine._Stager.SLOT_BYTES = old
+        engine._stager.ring = None
+
+
 def test_frame_chunking_and_sharding_are_exact_partitions():
     """Sums over disjoint frame ranges add up to the full sum (what frame sharding relies on)."""
     rng = np.random.default_rng(6)
