@@ -153,6 +153,7 @@ class _Stager:
     def __init__(self):
         self.ring = None
         self.pool = None
+        self.workers = 0
 
     def upload(self, src: np.ndarray, device, out=None):
         """`src`: C-contiguous numpy array; returns a CUDA tensor of the same shape and dtype (`out` if given)."""
@@ -164,8 +165,10 @@ class _Stager:
             self.ring = torch.empty(self.SLOTS * self.SLOT_BYTES, dtype=torch.uint8).pin_memory()
             self.ring_np = self.ring.numpy()
         workers = max(1, int(config.h2d_stage_threads))
-        if self.pool is None or self.pool._max_workers != workers:
-            self.pool = ThreadPoolExecutor(max_workers=workers)
+        if self.pool is None or self.workers != workers:
+            if self.pool is not None:
+                self.pool.shutdown(wait=True)
+            self.pool, self.workers = ThreadPoolExecutor(max_workers=workers), workers
         if out is None:
             out = torch.empty(src.shape, dtype=torch.from_numpy(src[:0]).dtype, device=device)
         src_b = src.reshape(-1).view(np.uint8)

@@ -41,6 +41,9 @@ def test_two_devices_from_one_process():
             out, _ = engine.das_map(op, 40, f, np.ones(40), 343.0, mic, mic[0], g, 3, True, mode)
             assert out.device.index == d
             maps.append(out.cpu().numpy())
+            lam, vec = engine.hermitian_eig(c[60:64])                      # shared-memory opt-in is per device, too
+            assert lam.device.index == d
+            assert np.max(np.abs(lam.cpu().numpy() - np.linalg.eigvalsh(got[60:64]))) <= 1e-12 * np.abs(got[60:64]).max() * 40
     assert np.max(np.abs(maps[0] - maps[1])) <= 1e-12 * maps[0].max()
     assert np.max(np.abs(maps[0] - maps[2])) <= 1e-12 * maps[0].max()
 
