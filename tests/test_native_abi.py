@@ -51,6 +51,21 @@ def test_host_only_entry_points():
     with pytest.raises(AssertionError):
         _native.check(lib.b2_das_prepare(None, 4, 3, 0, 1, 1, None, 0, None))
     assert lib.b2_das_operand_bytes(64, 20, _native.MAP_SIMT_F32) == 20 * 64 * 64 * 8
+    # spectra layout of b2_welch_rfft: the bin -> slot map is a permutation into (wl/8 + 1) groups of 4 slots that
+    # keeps bins p and wl/2 - p at slots p and wl/4 + p (what the untangling step writes together)
+    for wl in (8, 16, 256, 4096, 16384):
+        nc = wl // 2
+        slots = [lib.b2_welch_bin_slot(wl, f) for f in range(nc + 1)]
+        assert sorted(slots) == list(range(nc + 1))
+        assert all(slots[p] == p and slots[nc - p] == nc // 2 + p for p in range(nc // 2))
+        assert slots[nc // 2] == nc
+        assert lib.b2_welch_spectra_elems(wl, 7, 48) == 3 * (wl // 8 + 1) * 7 * 64
+    assert lib.b2_welch_bin_slot(4096, 2049) == -1 and lib.b2_welch_bin_slot(4000, 0) == -1
+    assert lib.b2_welch_spectra_elems(4096, 7, 40) == -1
+    assert lib.b2_heig_max_order() == 80
+    assert lib.b2_heig_jacobi(None, 4, 1, None, None, None, None) == _native.E_INVAL
+    assert lib.b2_cleansc_component(None, None, 4, 1, None, None, None, None, None, None, None, 0, 0.5, 0, None, None, None) == _native.E_INVAL
+    assert lib.b2_das_rank1_update(None, None, 4, 1, None, 343.0, None, None, None, 10, 0, 0, -0.5, None, None) == _native.E_INVAL
 
 
 def test_no_cpu_fallback():
