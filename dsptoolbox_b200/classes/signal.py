@@ -16,6 +16,7 @@ from warnings import warn
 
 import numpy as np
 
+from .. import engine
 from ..standard import _spectral_methods as _sm
 from ..standard.enums import SpectrumMethod, SpectrumScaling, Window
 from ._multichannel_data import MultichannelData
@@ -196,7 +197,7 @@ class Signal(MultichannelData):
     def get_csm(self, force_computation: bool = False):
         """Cross-spectral matrix as fresh host arrays (f float64 [nb], csm complex128 [nb, M, M])."""
         f, csm = self.get_csm_device(force_computation)
-        return f, csm.cpu().numpy()
+        return f, engine.to_host(csm)
 
     # ---- explicitly out of scope -------------------------------------------------------------------
     def get_spectrum(self, force_computation: bool = False):

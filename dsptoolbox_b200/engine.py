@@ -194,7 +194,63 @@ class _Stager:
         return out
 
 
+    def download(self, t) -> np.ndarray:
+        """Contiguous CUDA tensor -> fresh (pageable) numpy array through the same ring, the other way round:
+        asynchronous device copies into pinned slots, host threads empty them into the result."""
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+
+        torch = _torch()
+        if self.ring is None:
+            self.ring = torch.empty(self.SLOTS * self.SLOT_BYTES, dtype=torch.uint8).pin_memory()
+            self.ring_np = self.ring.numpy()
+        workers = max(1, int(config.h2d_stage_threads))
+        if self.pool is None or self.workers != workers:
+            if self.pool is not None:
+                self.pool.shutdown(wait=True)
+            self.pool, self.workers = ThreadPoolExecutor(max_workers=workers), workers
+        t = t.contiguous()
+        out = np.empty(tuple(t.shape), dtype=torch.empty((), dtype=t.dtype).numpy().dtype)
+        src_b = t.reshape(-1).view(torch.uint8)
+        dst_b = out.reshape(-1).view(np.uint8)
+        n, sb = dst_b.nbytes, self.SLOT_BYTES
+        pieces = [(o, min(sb, n - o)) for o in range(0, n, sb)]
+        stream = torch.cuda.current_stream(t.device)
+        drain = lambda s, o, m: np.copyto(dst_b[o:o + m], self.ring_np[s * sb:s * sb + m])   # noqa: E731
+        copies, emptied, nxt = deque(), [None] * self.SLOTS, 0
+        for i, (o, m) in enumerate(pieces):
+            while nxt < len(pieces) and nxt < i + self.SLOTS:
+                slot = nxt % self.SLOTS
+                if emptied[slot] is not None:
+                    emptied[slot].result()                   # the host copy out of this slot has finished
+                po, pm = pieces[nxt]
+                self.ring[slot * sb:slot * sb + pm].copy_(src_b[po:po + pm], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                copies.append(ev)
+                nxt += 1
+            copies.popleft().synchronize()
+            emptied[i % self.SLOTS] = self.pool.submit(drain, i % self.SLOTS, o, m)
+        for f in emptied:
+            if f is not None:
+                f.result()
+        return out
+
+
 _stager = _Stager()
+
+
+def to_host(t) -> np.ndarray:
+    """CUDA tensor -> numpy array (what the reference API returns): large results go through the pinned staging
+    ring (a plain `.cpu()` into pageable memory runs at ~10 GB/s), small ones directly."""
+    if not (config.h2d_stage_threads > 0 and getattr(t, "is_cuda", False)
+            and t.numel() * t.element_size() >= config.h2d_stage_min_bytes):
+        return t.cpu().numpy()
+    torch = _torch()
+    if t.is_complex():
+        real = _stager.download(torch.view_as_real(t.contiguous()))
+        return real.view(np.complex128 if t.dtype == torch.complex128 else np.complex64).reshape(tuple(t.shape))
+    return _stager.download(t)
 
 
 def _host_to_device(arr: np.ndarray, device, slot: str | None = None):

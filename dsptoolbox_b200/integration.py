@@ -44,7 +44,7 @@ def csm_welch_b200(time_data, sampling_rate_hz, window_length_samples, window_ty
     """Drop-in for the reference's `_csm_welch` (same positional signature, host arrays out)."""
     f, csm = b2sm.csm_welch_device(time_data, sampling_rate_hz, window_length_samples, _window_spec(window_type),
                                    overlap_percent, detrend, average, _scaling(scaling))
-    return f, csm.cpu().numpy()
+    return f, engine.to_host(csm)
 
 
 def _make_get_beamformer_map(ref):

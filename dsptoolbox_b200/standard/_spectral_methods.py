@@ -107,7 +107,7 @@ def _csm_welch(time_data, sampling_rate_hz: int, window_length_samples: int, win
     """
     f, csm = csm_welch_device(time_data, sampling_rate_hz, window_length_samples, window_type,
                               overlap_percent, detrend, average, scaling)
-    return f, csm.cpu().numpy()
+    return f, engine.to_host(csm)
 
 
 def _welch(x, y, fs_hz: int, window_type, window_length_samples: int, overlap_percent: float,
@@ -198,7 +198,7 @@ def _stft(x, fs_hz: int, window_length_samples: int, window_type, overlap_percen
     """Drop-in for reference _spectral_methods.py:176-282: host arrays (time_s, freqs_hz, stft)."""
     t, f, st = stft_device(x, fs_hz, window_length_samples, window_type, overlap_percent, fft_length_samples,
                            detrend, padding, scaling)
-    return t, f, st.cpu().numpy()
+    return t, f, engine.to_host(st)
 
 
 # --------------------------------------------------------------------------- next row f3: single-FFT spectrum and CSM

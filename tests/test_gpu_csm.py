@@ -148,6 +148,12 @@ def test_pageable_recordings_go_through_the_pinned_staging_ring():
         ref = R.csm_welch(xs, 8000, 256, "hann", 50, True, "fftbackward")[1]
         c = dsp.Signal(None, xs, 8000).set_spectrum_parameters(window_length_samples=256).get_csm()[1]
         assert_csm_close(c, ref)
+        # ... and the way back (engine.to_host: device -> pinned slots -> host threads -> numpy), real and complex
+        for td in (torch.randn((1_300_001, 3), device="cuda", dtype=torch.float64),
+                   torch.randn((700_003, 2), device="cuda", dtype=torch.complex128),
+                   torch.randn((2_000_001,), device="cuda", dtype=torch.float32)):
+            got = engine.to_host(td)
+            assert got.dtype == td.cpu().numpy().dtype and np.array_equal(got, td.cpu().numpy())
     finally:
         engine.config.h2d_stage_min_bytes, engine._Stager.SLOT_BYTES = old
         engine._stager.ring = None
